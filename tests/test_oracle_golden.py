@@ -1,0 +1,108 @@
+"""Pin oracle/fusion_fpn_oracle.py against fixtures generated from the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_fpn_oracle as O
+
+CROPS = ['relative_2d_max', 'relative_2d', 'oct']
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+@pytest.mark.parametrize('crop', CROPS)
+def test_oracle_matches_reference_forward_backward(golden_dir, crop):
+    fx = _load(golden_dir, f'fusion_{crop}.npz')
+    B, S, H, W, S2, W2 = [int(v) for v in fx['shape']]
+    sd = O.make_state_dict(seed=int(fx['seed_weights']), dtype=torch.float64)
+    batch = O.synthetic_batch(B, S, H, W, S2, W2, seed=int(fx['seed_batch']), dtype=torch.float64)
+    stages, rec = {}, O.BNRecorder()
+    loss, pred, grads = O.loss_and_grads(sd, batch, crop=crop, stages=stages, rec=rec)
+    # fixtures and oracle both fp64: only reduction-order noise is left
+    np.testing.assert_allclose(pred.numpy(), fx['prediction'], rtol=0, atol=1e-10)
+    assert abs(loss.item() - float(fx['loss'])) < 1e-11
+    # stage checksums
+    alias = {'zdimRed%d' % l: None for l in range(1, 6)}
+    for l in range(1, 6):
+        a = stages[f'conv{l}'].double()
+        ref = fx[f'act/conv{l}']
+        assert list(a.shape) == [int(v) for v in ref[3:]]
+        assert abs(a.abs().sum().item() - ref[1]) <= 1e-10 * ref[1]
+        a2 = stages[f'conv{l}_2d'].double()
+        ref2 = fx[f'act/conv{l}_2d']
+        assert abs(a2.abs().sum().item() - ref2[1]) <= 1e-10 * ref2[1]
+    for l in range(1, 5):
+        a = stages[f'up{l}'].double()
+        ref = fx[f'act/up_concat{l}']
+        assert list(a.shape) == [int(v) for v in ref[3:]]
+        assert abs(a.abs().sum().item() - ref[1]) <= 1e-10 * ref[1]
+    # gradients: full tensors for the small ones, (sum, l2) for all 275
+    for k in fx.files:
+        if k.startswith('grad/'):
+            g, r = grads[k[5:]].numpy(), fx[k]
+            assert np.abs(g - r).max() <= 1e-8 * max(np.abs(r).max(), 1e-6) + 1e-12, k
+    names = [str(n) for n in fx['grad_names']]
+    assert names == O.param_keys(sd)
+    l2 = np.array([grads[n].double().norm().item() for n in names])
+    tot_ref = np.sqrt((fx['grad_l2'] ** 2).sum())
+    assert abs(np.sqrt((l2 ** 2).sum()) - tot_ref) <= 1e-9 * tot_ref
+    big = fx['grad_l2'] > 1e-3 * fx['grad_l2'].max()
+    np.testing.assert_allclose(l2[big], fx['grad_l2'][big], rtol=1e-7)
+    # BN running statistics
+    for k in fx.files:
+        if k.startswith('bn/'):
+            np.testing.assert_allclose(rec.updates[k[3:]].numpy(), fx[k], rtol=1e-9, atol=1e-12)
+
+
+def test_index_oracles_match_torch(golden_dir):
+    ix = _load(golden_dir, 'index_ops.npz')
+    for name, k in (('p122', (1, 2, 2)), ('p222', (2, 2, 2))):
+        x = ix[f'{name}/x'][0, 0]
+        val, idx = O.maxpool_argmax_firstmax(x, k)
+        np.testing.assert_array_equal(idx, ix[f'{name}/idx'][0, 0])
+        np.testing.assert_array_equal(val, ix[f'{name}/val'][0, 0])       # NaN == NaN in assert_array_equal
+    _, idx = O.maxpool_argmax_firstmax(np.ones((2, 4, 4), np.float32), (2, 2, 2))
+    np.testing.assert_array_equal(idx, ix['const/idx'][0, 0])
+    assert idx.ravel().tolist() == [0, 2, 8, 10]
+    for name, o in (('a8x32', (8, 32)), ('a8x16', (8, 16)), ('a3x7', (3, 7))):
+        x = ix[f'{name}/x'][0, 0, :, :, 0]
+        val, idx = O.adaptive_maxpool2d_argmax(x, o)
+        np.testing.assert_array_equal(idx, ix[f'{name}/idx'][0, 0, :, :, 0])
+        np.testing.assert_array_equal(val, ix[f'{name}/val'][0, 0, :, :, 0])
+    _, idx = O.adaptive_maxpool2d_argmax(np.arange(7.)[:, None], (3, 1))
+    np.testing.assert_array_equal(idx[:, 0], ix['ar7to3/idx'].ravel())
+    assert idx[:, 0].tolist() == [2, 4, 6]
+    for f in ((2, 2, 1), (1, 2, 1)):
+        src = torch.arange(4 * 6, dtype=torch.float32).view(1, 1, 4, 6, 1)
+        np.testing.assert_array_equal(O.upsample_nearest(src, f).numpy(), ix[f'up{f[0]}{f[1]}{f[2]}/out'])
+    assert O.nearest_index_table(4, 2).tolist() == [0, 0, 1, 1, 2, 2, 3, 3]
+    assert O.nearest_index_table(5, 1).tolist() == [0, 1, 2, 3, 4]
+
+
+def test_projection_depth_algebra():
+    # 128 -> 8 -> 5, 496 -> 31 -> 28, 64 -> 4 -> 1
+    assert O.projection_depth(128, 4) == 5 and O.projection_depth(64, 3) == 5 and O.projection_depth(8, 0) == 5
+    assert O.projection_depth(496, 4) == 28 and O.projection_depth(64, 4) == 1
+
+
+def test_mac_count_matches_survey():
+    sd = O.make_state_dict()
+    assert abs(O.conv_mac_count(sd, 64, 128, 128, 128, 128) / 1e9 - 39.31) < 0.01
+    assert abs(O.conv_mac_count(sd, 32, 128, 128, 320, 128) / 1e9 - 21.40) < 0.01
+    assert abs(O.conv_mac_count(sd, 32, 496, 128, 320, 128) / 1e9 - 75.33) < 0.01
+    assert sum(sd[k].numel() for k in O.param_keys(sd)) == 6142481 and len(sd) == 548
+
+
+def test_oracle_fp64_agrees_with_fp32():
+    sd32 = O.make_state_dict(seed=5)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd32.items()}
+    b32 = O.synthetic_batch(1, 4, 64, 16, 4, 16, seed=2)
+    b64 = {k: v.double() for k, v in b32.items()}
+    p32 = O.fpn_hybrid_fusion_forward(sd32, b32, 'oct')['prediction']
+    p64 = O.fpn_hybrid_fusion_forward(sd64, b64, 'oct')['prediction']
+    assert (p32.double() - p64).norm() / p64.norm() < 1e-4
