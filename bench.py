@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the fusion-FPN training step (forward + loss + backward + SGD) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  Metric = BASELINE.json's "fwd+bwd samples/sec"; workload at N=1 = configs[1]
+(C2: FPNHybridFusion, batch 8, image 1x32x128x128, SLO 320x128, crop relative_2d_max, bf16 storage / fp32
+accumulate), weak-scaled (8 samples per GPU) for N>1, one process per GPU over NCCL.
+`value`  : steps timed with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max
+           over ranks).  The per-step working set (several GB of activations) is far larger than the 126 MB
+           L2, so no explicit L2 flush is needed between iterations.
+`e2e`    : same step driven from pinned HOST buffers through the public module API: H2D copy of image / slo
+           / mask every step and a D2H read of the loss inside the timed region.
+`roofline`: the dominant kernel timed alone with CUDA events, algorithmic bytes / time vs MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the oracle port (torch CPU ops restating the reference) on the host cores.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'multimodal-fusion-fpn_b200'))
+
+WORKLOAD = dict(name='C2: FPNHybridFusion GA segmentation, batch 8/GPU, image 1x32x128x128, slo 320x128, '
+                     'crop relative_2d_max', B=8, S=32, H=128, W=128, S2=320, W2=128)
+METRIC, UNIT = 'fwd+bwd samples/sec', 'samples/s'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms',
+                                          '100', '-i', str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            out['reasons'] = ['nvidia-smi unavailable']
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    c = [x.strip() for x in line.split(',')]
+                    if len(c) < 9:
+                        continue
+                    try:
+                        sm.append(float(c[1])); mx.append(float(c[2]))
+                    except ValueError:
+                        continue
+                    for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
+                        if v.lower().startswith('active'):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_rate(steps, warmup, threads=None):
+    """Oracle port (oracle/fusion_fpn_oracle.py: torch CPU ops restating the reference, fp32) on the host cores.
+    Each step = forward + Mix loss + backward of ONE sample of the workload shape."""
+    import torch
+    from oracle import fusion_fpn_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    w = WORKLOAD
+    sd = O.make_state_dict(seed=1234)
+    batch = O.synthetic_batch(1, w['S'], w['H'], w['W'], w['S2'], w['W2'], seed=1234)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.loss_and_grads(sd, batch)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return 1.0 / sec, sec, threads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 8), min(args.warmup, 2)
+    rate, sec, threads = cpu_reference_rate(steps, warmup)
+    sample = (f'oracle port of the reference (torch {__import__("torch").__version__} CPU ops, fp32), {threads} host threads; '
+              f'each step = fwd+loss+bwd of 1 sample of the C2 shape; {steps} timed after {warmup} warm-up')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
+            'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD['name'], 'per_step_samples': 1},
+            'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def kernel_roofline(torch, ops, peak_gbs, peak_src, iters=20):
+    """Time the dominant kernels alone (CUDA events on the launching stream, inputs >> L2 at the C2 shape)."""
+    w = WORKLOAD
+    B, S, W_, H = w['B'], w['S'], w['W'], w['H']
+    res = []
+    g = torch.Generator(device='cuda').manual_seed(0)
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    dt = torch.bfloat16
+    C = 16
+    x = torch.randn(B, S, W_, H, C, device='cuda', generator=g).to(dt)
+    wt = torch.randn(C, C, 1, 3, 3, device='cuda', generator=g) * 0.1
+    sc = torch.ones(C, device='cuda'); sh = torch.zeros(C, device='cuda')
+    nbytes = 2 * x.numel() * 2
+    t = timeit(lambda: ops.conv_fwd(x, wt, (1, 3, 3), (1, 1, 1), (0, 1, 1), sc, sh, True))
+    res.append(dict(kernel='conv_fwd (1,3,3) 16->16 level-1 (BN+ReLU on load, stats epilogue)', bytes=nbytes, sec=t))
+    wz = torch.randn(C, C, 1, 1, 3, device='cuda', generator=g) * 0.1
+    t = timeit(lambda: ops.conv_fwd(x, wz, (1, 1, 3), (1, 1, 2), (0, 0, 1), sc, sh, True))
+    res.append(dict(kernel='projection conv (1,1,3) s(1,1,2) 16->16 level-1', bytes=int(x.numel() * 2 * 1.5), sec=t))
+    y = torch.randn_like(x)
+    t = timeit(lambda: ops.block_end_fwd(y, sc, sh, x))
+    res.append(dict(kernel='block_end_fwd (BN apply + residual + ReLU) level-1', bytes=3 * x.numel() * 2, sec=t))
+    t = timeit(lambda: ops.bn_bwd_reduce(y, x, sc, sh, True))
+    res.append(dict(kernel='bn_bwd_reduce level-1', bytes=2 * x.numel() * 2, sec=t))
+    for r in res:
+        r['gbs'] = r['bytes'] / r['sec'] / 1e9
+        r['frac'] = r['gbs'] / peak_gbs
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-roofline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a B200: there is no CPU path for the product'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from __graft_entry__ import import_mirror
+    cfg, fusion_nets, loss_mod, weight_init = import_mirror()
+    import ffpn
+    from ffpn import ops
+    from ffpn.trainer import FusionTrainer
+    from oracle import fusion_fpn_oracle as O            # synthetic batch generator + cpu_baseline only
+
+    dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    ffpn.set_compute_dtype(dtype)
+    torch.manual_seed(1234)                                # train.py:42
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = fusion_nets.factory_classes['FPNHybridFusion']()
+    model.apply(weight_init.weight_init)                   # train.py:56
+    model = model.cuda().train()
+    crit = loss_mod.Mix({'Dice': loss_mod.Dice_loss_jointv2('prediction', 'mask'),
+                         'BCE': loss_mod.BCE_Lossv2('prediction', 'mask')})
+    w = WORKLOAD
+    host = O.synthetic_batch(w['B'], w['S'], w['H'], w['W'], w['S2'], w['W2'], seed=1234 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+    trainer = FusionTrainer(model, crit, lr=cfg.learning_rate, momentum=0.9, weight_decay=1e-4)
+
+    n0 = ffpn.lib.launch_count(local_rank)
+    trainer.step(dev)                                      # eager step: counts our launches per step
+    torch.cuda.synchronize()
+    launches_per_step = ffpn.lib.launch_count(local_rank) - n0
+    use_graph = not args.no_graph
+    if use_graph:
+        trainer.capture(dev)
+    step = (lambda b=None: trainer.replay(b)) if use_graph else (lambda b=None: trainer.step(b if b is not None else dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    # ---- end to end: pinned host -> device every step, loss read back every step ---------------------------
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = 0.0
+    for _ in range(args.steps):
+        # graph path: replay() copies the pinned host tensors straight into the captured step's input buffers
+        b = host if use_graph else {k: v.cuda(non_blocking=True) for k, v in host.items()}
+        last = float(step(b).item())
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    t = torch.tensor([ms, ms_e2e], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    samples = w['B'] * world * args.steps
+    value, e2e_value = samples / (ms * 1e-3), samples / (ms_e2e * 1e-3)
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': w['name'], 'per_gpu_batch': w['B'], 'global_batch': w['B'] * world,
+                       'parallelism': f'dp{world}', 'cuda_graph': use_graph, 'optimizer': 'SGD(0.1, 0.9, wd 1e-4) fused',
+                       'l2': 'per-step working set >> 126 MB L2 (no flush needed)', 'final_loss': last},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(launches_per_step * args.steps)}
+    if rank == 0:
+        peak, src = peaks()
+        if not args.no_kernel_roofline:
+            ks = kernel_roofline(torch, ops, peak, src)
+            top = ks[0]
+            line['roofline'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['gbs'], 'peak': peak, 'unit': 'GB/s',
+                                'frac': top['frac'], 'traffic': None, 'peak_source': src,
+                                'algorithmic_bytes_per_launch': top['bytes'], 'sec_per_launch': top['sec']}
+            line['kernels'] = [{k: r[k] for k in ('kernel', 'gbs', 'frac', 'sec', 'bytes')} for r in ks]
+            # whole-step roofline: conv-boundary traffic model of SURVEY.md section 8d (bf16, fwd+bwd = 3 x fwd)
+            step_bytes = 367.2e6 * 2 * 3 * w['B']
+            line['step_roofline'] = {'model_bytes_per_step': step_bytes, 'achieved_gbs': step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                                     'frac': step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, threads = cpu_reference_rate(3, 1)
+            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                    'sample': 'oracle port (torch CPU fp32), fwd+loss+bwd of 1 sample of the C2 shape, '
+                                              '3 timed after 1 warm-up'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,182 @@
+/*
+ * ffpn.h -- C ABI of libfusionfpn.so: the sm_100a CUDA kernels behind the projective multimodal
+ * fusion FPN forward/backward (reference: j-morano/multimodal-fusion-fpn, models/fusion_nets.py +
+ * models/fpn/*).
+ *
+ * The reference has no FFI: its "operator boundary" is the set of ATen ops its nn.Modules dispatch
+ * to.  Every entry point below replaces one of those ops (or a fused group of
+ * them) and cites the reference call site it stands in for.  The Python host mirror
+ * (multimodal-fusion-fpn_b200/ffpn/) binds them with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  All tensor pointers are DEVICE pointers that
+ *    the caller owns (PyTorch caching allocator); the library borrows them for the call.
+ *  - every function returns 0 on success, non-zero on error (never throws/aborts); the message is
+ *    available from ffpn_last_error(ctx).
+ *  - all work is enqueued on the cudaStream_t passed in (as void*); no hidden synchronisation.
+ *  - activations are channels-last: (B, S, W, H, C) contiguous, i.e. the reference's logical
+ *    (B, C, S, W, H) tensor in torch.channels_last_3d memory format.  2-D features are H == 1.
+ *    dtype: FFPN_F32 (exact path) or FFPN_BF16 (bf16 storage, fp32 accumulate).
+ *  - weights, BatchNorm vectors and all statistics are fp32; conv weights stay in the reference's
+ *    layout [Cout, Cin, kS, kW, kH] (state_dict compatible).
+ */
+#ifndef FFPN_H
+#define FFPN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFPN_ABI_VERSION 1
+#define FFPN_F32 0
+#define FFPN_BF16 1
+/* rows of a per-block partial-statistics buffer: [FFPN_STAT_ROWS][ncols] floats */
+#define FFPN_STAT_ROWS 1184
+
+typedef struct ffpn_ctx ffpn_ctx;
+
+/* Convolution geometry.  Only what the reference uses: stride and padding per axis, no dilation, no
+ * groups, bias-free (every conv on the path is bias=False except final1, see ffpn_head_fwd). */
+typedef struct ffpn_conv_desc {
+  int64_t B, S, W, H;      /* input extent  */
+  int64_t oS, oW, oH;      /* output extent */
+  int32_t Cin, Cout;
+  int32_t kS, kW, kH;
+  int32_t sS, sW, sH;
+  int32_t pS, pW, pH;
+  int32_t dtype;           /* FFPN_F32 | FFPN_BF16 (activations in and out) */
+  int32_t impl;            /* 0 = auto, 1 = force SIMT kernel, 2 = force tcgen05 kernel (error if unsupported) */
+} ffpn_conv_desc;
+
+int ffpn_abi_version(void);
+int ffpn_create(ffpn_ctx** ctx, int device);
+void ffpn_destroy(ffpn_ctx* ctx);
+const char* ffpn_last_error(ffpn_ctx* ctx);
+/* number of kernel launches issued through this ctx since creation (bench.py's gpu_launches) */
+int64_t ffpn_launch_count(ffpn_ctx* ctx);
+/* bytes of scratch a conv call of this geometry may use (packed bf16 weights for the tcgen05 path) */
+size_t ffpn_conv_workspace_bytes(const ffpn_conv_desc* d);
+
+/* ---- convolution (replaces aten::convolution / convolution_backward -> cuDNN; reference call sites
+ *      fusion3D2D.py:601-647 (3-D), :762-808 (2-D), :232,267,318-324,925-931) ------------------------
+ * fwd:  y = conv(f(x), w),  f(x) = in_relu ? max(in_scale*x+in_shift, 0) : in_scale*x+in_shift  applied on
+ *       load (the producer's BatchNorm+ReLU, fusion3D2D.py:609-610), identity when in_scale == NULL.
+ *       Zero padding is applied AFTER f, as in the reference.  When stat_partial != NULL the kernel also
+ *       writes per-block partial sums of y and y*y: [rows][2][Cout] floats, *stat_rows = rows written. */
+int ffpn_conv_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale,
+                  const float* in_shift, int in_relu, const float* w, void* y, float* stat_partial,
+                  int* stat_rows, void* ws, size_t ws_bytes, void* stream);
+/* dgrad: dx = conv_transpose(dy, w) [+ addend]  (gradient w.r.t. f(x), i.e. before the producer's ReLU
+ *        mask).  addend (nullable, same shape/dtype as dx) fuses the residual-branch gradient sum of
+ *        fusion3D2D.py:724-725's backward. */
+int ffpn_conv_dgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* dy, const float* w,
+                    const void* addend, void* dx, void* ws, size_t ws_bytes, void* stream);
+/* wgrad: dw += sum_pos dy[pos] (x) f(x)[pos*stride - pad + tap]; dw is fp32 [Cout,Cin,kS,kW,kH] and is
+ *        ACCUMULATED into (caller zeroes it). */
+int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale,
+                    const float* in_shift, int in_relu, const void* dy, float* dw, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* ---- BatchNorm (replaces aten::native_batch_norm(+_backward); nn.BatchNorm3d/2d at fusion3D2D.py:609,
+ *      622,634,647,770,...).  Training: batch mean / biased variance from the conv's partial sums,
+ *      running stats momentum/unbiased update in place; eval: running stats.  Emits the affine
+ *      scale = gamma*invstd, shift = beta - mean*scale that consumers apply on load. */
+int ffpn_bn_finalize(ffpn_ctx* ctx, const float* stat_partial, int stat_rows, int C, double count,
+                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float momentum, float eps, int training, float* scale, float* shift,
+                     float* save_mean, float* save_invstd, void* stream);
+/* backward pass 1: G = dA * (relu ? (scale*y+shift > 0) : 1); partial sums of G and G*y ->
+ *      [rows][2][C].  P = number of positions. */
+int ffpn_bn_bwd_reduce(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* dA, const void* y,
+                       const float* scale, const float* shift, int relu, float* partial, int* rows,
+                       void* stream);
+/* backward pass 2 (tiny): dgamma, dbeta (written) and the coefficients of
+ *      dy = cA*G + cP*y + cQ   (per channel).  ycol selects which "G*y" column of a multi-column partial
+ *      buffer to use (ffpn_block_end_bwd writes [rows][ncols][C] with col0 = sum G). */
+int ffpn_bn_bwd_finalize(ffpn_ctx* ctx, const float* partial, int rows, int ncols, int ycol, int C,
+                         double count, const float* gamma, const float* save_mean,
+                         const float* save_invstd, float* dgamma, float* dbeta, float* cA, float* cP,
+                         float* cQ, void* stream);
+/* backward pass 3: dy = cA * (dA * mask) + cP*y + cQ   (mask as in pass 1; dy may alias dA) */
+int ffpn_bn_bwd_apply(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* dA, const void* y,
+                      const float* scale, const float* shift, int relu, const float* cA,
+                      const float* cP, const float* cQ, void* dy, void* stream);
+
+/* ---- residual block end (replaces BN-apply + add_ + relu_, fusion3D2D.py:724-727) --------------------
+ * z = relu(a*y + b + r),  r = ra*res + rb (raw shortcut conv output), res (identity shortcut, ra==NULL)
+ * or 0 (res == NULL, non-residual block). */
+int ffpn_block_end_fwd(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* y, const float* a,
+                       const float* b, const void* res, const float* ra, const float* rb, void* z,
+                       void* stream);
+/* G = (dz + route(dzp)) * (z > 0): gradient at the block-end ReLU input.  dzp (nullable) is the gradient
+ * of the max-pooled tensor, routed to each window's first maximum (NaN wins) exactly like
+ * max_pool3d_with_indices_backward (fusion3D2D.py:87-90); pool kernel (kS,kW,kH),
+ * stride = kernel, floor.  Also writes partial sums [rows][ncols][C]: col0 = sum G, col1 = sum G*y,
+ * col2 = sum G*yres (when yres != NULL); ncols = yres ? 3 : 2. */
+int ffpn_block_end_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S, int64_t W, int64_t H, int C,
+                       int kS, int kW, int kH, const void* dz, const void* dzp, const void* z,
+                       const void* y, const void* yres, void* G, float* partial, int* rows,
+                       void* stream);
+
+/* ---- max pooling (replaces aten::max_pool3d/2d_with_indices, fusion3D2D.py:87-90,168-171) -----------
+ * idx (nullable): int64 flat index into (S,W,H) per (b,c), PyTorch's convention, laid out like zp. */
+int ffpn_maxpool_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S, int64_t W, int64_t H, int C, int kS,
+                     int kW, int kH, const void* z, void* zp, int64_t* idx, void* stream);
+/* stand-alone backward (argmax recomputed from z with the same rule): dz = route(dzp), zeros elsewhere */
+int ffpn_maxpool_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S, int64_t W, int64_t H, int C, int kS,
+                     int kW, int kH, const void* z, const void* dzp, void* dz, void* stream);
+
+/* ---- projection tail (replaces BN+ReLU of the (1,1,4) block and torch.mean(dim=4), fusion3D2D.py:527-536)
+ * out[b,s,w,coff+c] = mean_h relu(a*y[b,s,w,h,c]+b); out has channel stride ostride (a concat buffer). */
+int ffpn_proj_tail_fwd(ffpn_ctx* ctx, int dtype, int64_t EW, int64_t H, int C, const void* y,
+                       const float* a, const float* b, void* out, int ostride, int coff, void* stream);
+/* dA[b,s,w,h,c] = dout[b,s,w,coff+c] / H   (gradient w.r.t. the ReLU output; mask applied by bn_bwd_*) */
+int ffpn_proj_tail_bwd(ffpn_ctx* ctx, int dtype, int64_t EW, int64_t H, int C, const void* dout,
+                       int ostride, int coff, void* dA, void* stream);
+
+/* ---- 2-D feature resize into a concat slice (fusion3D2D.py:544-564) ---------------------------------
+ * mode 0: copy (interpolate=None), 1: adaptive max (F.adaptive_max_pool3d), 2: bilinear, half-pixel,
+ * align_corners=False (F.interpolate 'trilinear' with depth 1).  idx (mode 1): int32 argmax into Si*Wi. */
+int ffpn_resize2d_fwd(ffpn_ctx* ctx, int dtype, int mode, int64_t B, int64_t Si, int64_t Wi, int64_t So,
+                      int64_t Wo, int C, const void* x, void* out, int ostride, int coff, int32_t* idx,
+                      void* stream);
+int ffpn_resize2d_bwd(ffpn_ctx* ctx, int dtype, int mode, int64_t B, int64_t Si, int64_t Wi, int64_t So,
+                      int64_t Wo, int C, const void* dout, int ostride, int coff, const int32_t* idx,
+                      void* dx, void* stream);
+
+/* ---- nearest upsample by integer factors into a concat slice (Upsample_Custom3d_nearest,
+ *      components.py:259-268: idx = ceil((i+1)/f) - 1 == i / f for integer f) --------------------------- */
+int ffpn_upsample_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t Si, int64_t Wi, int fS, int fW, int C,
+                      const void* x, void* out, int ostride, int coff, void* stream);
+int ffpn_upsample_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t Si, int64_t Wi, int fS, int fW, int C,
+                      const void* dout, int ostride, int coff, void* dx, void* stream);
+/* copy a (P, C) tensor into / out of a channel slice (torch.cat and its backward, fusion3D2D.py:572,966) */
+int ffpn_slice_copy(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* src, int sstride, int soff,
+                    void* dst, int dstride, int doff, void* stream);
+
+/* ---- head: final1 = Conv3d(C -> n, 1x1x1, bias) (fusion3D2D.py:223,579); logits fp32 in the
+ *      reference layout (B, n, S, W, 1) ---------------------------------------------------------------- */
+int ffpn_head_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, const void* x,
+                  const float* w, const float* bias, float* logits, void* stream);
+/* dx (activations dtype), dw[n][C] and dbias[n] (fp32, written) from dlogits */
+int ffpn_head_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, const void* x,
+                  const float* w, const float* dlogits, void* dx, float* dw, float* dbias, void* stream);
+
+/* ---- input packing: fp32 (R, H, W) -> activations dtype (R, W, H)  (the permute of
+ *      fusion_nets.py:114 made physical; R = B*S) ----------------------------------------------------- */
+int ffpn_pack_volume(ffpn_ctx* ctx, int dtype, int64_t R, int64_t H, int64_t W, const float* src, void* dst,
+                     void* stream);
+int ffpn_cast(ffpn_ctx* ctx, int dtype, int64_t n, const float* src, void* dst, void* stream);
+
+/* ---- optimiser: torch.optim.SGD(momentum, weight_decay) of train.py:126-133 on flat fp32 buffers;
+ *      g is first scaled by grad_scale (1/world_size after the NCCL sum all-reduce). ----------------- */
+int ffpn_sgd_step(ffpn_ctx* ctx, int64_t n, float* p, const float* g, float* mom, float lr, float momentum,
+                  float weight_decay, float grad_scale, int first_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFPN_H */

@@ -1,0 +1,93 @@
+// C-ABI entry points that are not defined next to their kernels: ctx lifetime and the convolution dispatcher.
+#include "common.cuh"
+
+int ffpn_conv_fwd_simt(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const float*,
+                       void*, float*, int*, cudaStream_t);
+int ffpn_conv_dgrad_simt(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const void*, void*, cudaStream_t);
+int ffpn_conv_wgrad_simt(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const void*,
+                         float*, cudaStream_t);
+// conv_tc.cu
+bool ffpn_tc_fwd_supported(const ffpn_conv_desc* d);
+bool ffpn_tc_dgrad_supported(const ffpn_conv_desc* d);
+bool ffpn_tc_wgrad_supported(const ffpn_conv_desc* d);
+size_t ffpn_tc_workspace_bytes(const ffpn_conv_desc* d);
+int ffpn_conv_fwd_tc(ffpn_ctx*, const ffpn_conv_desc*, bool transposed, const void*, const float*, const float*, int,
+                     const float*, const void* addend, void*, float*, int*, void*, size_t, cudaStream_t);
+int ffpn_conv_wgrad_tc(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const void*,
+                       float*, void*, size_t, cudaStream_t);
+
+static int check_desc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const char* who) {
+  if (!ctx) return 1;
+  if (!d) FFPN_FAIL(ctx, "%s: null descriptor", who);
+  if (d->dtype != FFPN_F32 && d->dtype != FFPN_BF16) FFPN_FAIL(ctx, "%s: unknown dtype %d", who, d->dtype);
+  if (d->B <= 0 || d->S <= 0 || d->W <= 0 || d->H <= 0 || d->Cin <= 0 || d->Cout <= 0) FFPN_FAIL(ctx, "%s: empty tensor", who);
+  if (d->kS <= 0 || d->kW <= 0 || d->kH <= 0 || d->sS <= 0 || d->sW <= 0 || d->sH <= 0) FFPN_FAIL(ctx, "%s: bad kernel/stride", who);
+  const int64_t eS = (d->S + 2 * d->pS - d->kS) / d->sS + 1, eW = (d->W + 2 * d->pW - d->kW) / d->sW + 1,
+                eH = (d->H + 2 * d->pH - d->kH) / d->sH + 1;
+  if (eS != d->oS || eW != d->oW || eH != d->oH || eS <= 0 || eW <= 0 || eH <= 0)
+    FFPN_FAIL(ctx, "%s: output extent (%lld,%lld,%lld) inconsistent with geometry (expected %lld,%lld,%lld)", who,
+              (long long)d->oS, (long long)d->oW, (long long)d->oH, (long long)eS, (long long)eW, (long long)eH);
+  if (d->B * d->S * d->W * d->H >= (1ll << 31) || d->B * d->oS * d->oW * d->oH >= (1ll << 31))
+    FFPN_FAIL(ctx, "%s: more than 2^31 positions", who);
+  return 0;
+}
+
+extern "C" int ffpn_abi_version(void) { return FFPN_ABI_VERSION; }
+
+extern "C" int ffpn_create(ffpn_ctx** out, int device) {
+  if (!out) return 1;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return 2;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 3;
+  if (prop.major != 10) return 4;   // sm_100a only: no fallback path exists
+  ffpn_ctx* c = new ffpn_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->launches = 0;
+  c->err[0] = 0;
+  *out = c;
+  return 0;
+}
+
+extern "C" void ffpn_destroy(ffpn_ctx* ctx) { delete ctx; }
+extern "C" const char* ffpn_last_error(ffpn_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+extern "C" int64_t ffpn_launch_count(ffpn_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" size_t ffpn_conv_workspace_bytes(const ffpn_conv_desc* d) { return d ? ffpn_tc_workspace_bytes(d) : 0; }
+
+extern "C" int ffpn_conv_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale,
+                             const float* in_shift, int in_relu, const float* w, void* y, float* stat_partial,
+                             int* stat_rows, void* ws, size_t ws_bytes, void* stream) {
+  if (check_desc(ctx, d, "conv_fwd")) return 1;
+  if ((in_scale == nullptr) != (in_shift == nullptr)) FFPN_FAIL(ctx, "conv_fwd: in_scale/in_shift must both be set or both null");
+  if (stat_partial != nullptr && stat_rows == nullptr) FFPN_FAIL(ctx, "conv_fwd: stat_rows is null");
+  const bool tc_ok = ffpn_tc_fwd_supported(d);
+  if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_fwd: tcgen05 kernel does not support this geometry");
+  if (tc_ok && d->impl != 1)
+    return ffpn_conv_fwd_tc(ctx, d, false, x, in_scale, in_shift, in_relu, w, nullptr, y, stat_partial, stat_rows, ws, ws_bytes, (cudaStream_t)stream);
+  return ffpn_conv_fwd_simt(ctx, d, x, in_scale, in_shift, in_relu, w, y, stat_partial, stat_rows, (cudaStream_t)stream);
+}
+
+extern "C" int ffpn_conv_dgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* dy, const float* w, const void* addend,
+                               void* dx, void* ws, size_t ws_bytes, void* stream) {
+  if (check_desc(ctx, d, "conv_dgrad")) return 1;
+  const bool tc_ok = ffpn_tc_dgrad_supported(d);
+  if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_dgrad: tcgen05 kernel does not support this geometry");
+  if (tc_ok && d->impl != 1)
+    return ffpn_conv_fwd_tc(ctx, d, true, dy, nullptr, nullptr, 0, w, addend, dx, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+  return ffpn_conv_dgrad_simt(ctx, d, dy, w, addend, dx, (cudaStream_t)stream);
+}
+
+extern "C" int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale,
+                               const float* in_shift, int in_relu, const void* dy, float* dw, void* ws, size_t ws_bytes,
+                               void* stream) {
+  if (check_desc(ctx, d, "conv_wgrad")) return 1;
+  if ((in_scale == nullptr) != (in_shift == nullptr)) FFPN_FAIL(ctx, "conv_wgrad: in_scale/in_shift must both be set or both null");
+  const bool tc_ok = ffpn_tc_wgrad_supported(d);
+  if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_wgrad: tcgen05 kernel does not support this geometry");
+  if (tc_ok && d->impl != 1)
+    return ffpn_conv_wgrad_tc(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, ws, ws_bytes, (cudaStream_t)stream);
+  return ffpn_conv_wgrad_simt(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, (cudaStream_t)stream);
+}

@@ -1,0 +1,362 @@
+"""torch.autograd Functions that run the fusion-FPN stages on the sm_100a kernels.
+
+Tensors crossing these Functions are LOGICAL reference-shaped tensors -- (B, C, S, W, H) for 3-D features
+and (B, C, S', W') for 2-D ones -- stored channels-last (torch.channels_last_3d / channels_last), so a
+caller sees the same shapes the reference produces while the kernels see (B, S, W, H, C).
+"""
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+
+_COMPUTE_DTYPE = torch.bfloat16
+
+
+def set_compute_dtype(dtype: torch.dtype) -> None:
+    """Activation storage type of the kernels: torch.bfloat16 (default, fp32 accumulate) or torch.float32."""
+    global _COMPUTE_DTYPE
+    assert dtype in (torch.bfloat16, torch.float32)
+    _COMPUTE_DTYPE = dtype
+
+
+def get_compute_dtype() -> torch.dtype:
+    return _COMPUTE_DTYPE
+
+
+# ---- layout helpers ------------------------------------------------------------------------------------
+def to_phys(x: torch.Tensor) -> torch.Tensor:
+    """logical (B,C,S,W,H) / (B,C,S,W) -> physical (B,S,W,H,C) contiguous in the compute dtype."""
+    if x.dim() == 5:
+        p = x.permute(0, 2, 3, 4, 1)
+    elif x.dim() == 4:
+        p = x.permute(0, 2, 3, 1).unsqueeze(3)
+    else:
+        raise ValueError(f'expected a 4-D or 5-D feature tensor, got {tuple(x.shape)}')
+    if not p.is_contiguous():
+        p = p.contiguous()          # boundary only: a caller handed us a non-channels-last tensor
+    if p.dtype != _COMPUTE_DTYPE:
+        p = ops.cast(p.float() if p.dtype != torch.float32 else p, _COMPUTE_DTYPE)
+    return p
+
+
+def to_logical(p: torch.Tensor, ndim: int) -> torch.Tensor:
+    if ndim == 5:
+        return p.permute(0, 4, 1, 2, 3)
+    return p.squeeze(3).permute(0, 3, 1, 2)
+
+
+def k3(t) -> Tuple[int, int, int]:
+    t = tuple(int(v) for v in (t if isinstance(t, (tuple, list)) else (t,) * 3))
+    return t if len(t) == 3 else (t[0], t[1], 1)       # 2-D (kS', kW') acts on (S, W) with H == 1
+
+
+def p3(t) -> Tuple[int, int, int]:
+    t = tuple(int(v) for v in (t if isinstance(t, (tuple, list)) else (t,) * 3))
+    return t if len(t) == 3 else (t[0], t[1], 0)
+
+
+@dataclass
+class ConvXSpec:
+    kernels: tuple          # per conv (kS,kW,kH)
+    strides: tuple
+    pads: tuple
+    residual: bool
+    has_ds: bool
+    ds_stride: tuple
+    pool: Optional[tuple]   # fused max-pool kernel or None
+    tail: str               # 'relu' (block end) | 'mean' (projection tail: BN+ReLU+mean over depth)
+    training: bool
+    momentum: float
+    eps: float
+    need_dx: bool
+    ndim: int
+
+
+class ConvXFunction(torch.autograd.Function):
+    """One residual block (unet3dConvX / unet2dConvX, reference fusion3D2D.py:717-732, :878-893):
+    k x [conv -> BN -> ReLU] (last without ReLU), optional 1x1x1 conv+BN shortcut, add, ReLU; optionally
+    fused with the max-pool that follows it (fusion3D2D.py:515-521) or with the projection's depth mean
+    (:527-536).  tensors = per conv (w, gamma, beta, running_mean, running_var), then the shortcut's."""
+
+    @staticmethod
+    def forward(ctx, spec: ConvXSpec, x, *tensors):
+        k = len(spec.kernels)
+        xp = to_phys(x)
+        ys, affs = [], []
+        cur, cur_aff = xp, None
+        for i in range(k):
+            w, g, b, rm, rv = tensors[5 * i: 5 * i + 5]
+            y, partial, rows = ops.conv_fwd(cur, w, spec.kernels[i], spec.strides[i], spec.pads[i],
+                                            None if cur_aff is None else cur_aff[0],
+                                            None if cur_aff is None else cur_aff[1], cur_aff is not None,
+                                            want_stats=spec.training)
+            count = y.numel() // y.shape[-1]
+            aff = ops.bn_finalize(partial, rows, count, g, b, rm, rv, spec.momentum, spec.eps, spec.training)
+            ys.append(y)
+            affs.append(aff)
+            cur, cur_aff = y, aff
+        yd, affd = None, None
+        if spec.residual and spec.has_ds:
+            wd, gd, bd, rmd, rvd = tensors[5 * k: 5 * k + 5]
+            yd, partial, rows = ops.conv_fwd(xp, wd, (1, 1, 1), spec.ds_stride, (0, 0, 0), want_stats=spec.training)
+            affd = ops.bn_finalize(partial, rows, yd.numel() // yd.shape[-1], gd, bd, rmd, rvd, spec.momentum, spec.eps,
+                                   spec.training)
+        a, b = affs[-1][0], affs[-1][1]
+        zp = None
+        if spec.tail == 'mean':
+            assert not spec.residual and spec.pool is None
+            z = ops.proj_tail_fwd(ys[-1], a, b)
+        else:
+            if spec.residual:
+                z = ops.block_end_fwd(ys[-1], a, b, yd if yd is not None else xp, None if affd is None else affd[0],
+                                      None if affd is None else affd[1])
+            else:
+                z = ops.block_end_fwd(ys[-1], a, b)
+            if spec.pool is not None:
+                zp = ops.maxpool_fwd(z, spec.pool)
+        ctx.spec = spec
+        ctx.x_shape = tuple(xp.shape)
+        ctx.nt = len(tensors)
+        flat = [xp, z] + ys + [t for aff in affs for t in aff]
+        if yd is not None:
+            flat += [yd] + list(affd)
+        ctx.save_for_backward(*flat, *tensors)
+        ctx.nflat = len(flat)
+        zl = to_logical(z, spec.ndim)
+        if spec.pool is not None:
+            return zl, to_logical(zp, spec.ndim)
+        return zl
+
+    @staticmethod
+    def backward(ctx, dz, dzp=None):
+        spec: ConvXSpec = ctx.spec
+        k = len(spec.kernels)
+        saved = ctx.saved_tensors
+        flat, tensors = saved[:ctx.nflat], saved[ctx.nflat:]
+        xp, z = flat[0], flat[1]
+        ys = list(flat[2:2 + k])
+        affs = [flat[2 + k + 4 * i: 2 + k + 4 * i + 4] for i in range(k)]
+        yd, affd = None, None
+        if spec.residual and spec.has_ds:
+            yd = flat[2 + 5 * k]
+            affd = flat[3 + 5 * k: 7 + 5 * k]
+        grads = [None] * ctx.nt
+        dzp_p = to_phys(dzp) if dzp is not None else None
+        dz_p = to_phys(dz) if dz is not None else None
+        y_last = ys[-1]
+        count = y_last.numel() // y_last.shape[-1]
+        g_last = tensors[5 * (k - 1) + 1]
+        if spec.tail == 'mean':
+            dA = ops.proj_tail_bwd(dz_p, y_last.shape)
+            partial, rows = ops.bn_bwd_reduce(dA, y_last, affs[-1][0], affs[-1][1], True)
+            dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, 2, 1, count, g_last, affs[-1][2], affs[-1][3])
+            dy = ops.bn_bwd_apply(dA, y_last, affs[-1][0], affs[-1][1], True, cA, cP, cQ, out=dA)
+            G = None
+        else:
+            G, partial, rows, ncols = ops.block_end_bwd(dz_p, dzp_p, z, y_last, yd, spec.pool)
+            dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 1, count, g_last, affs[-1][2], affs[-1][3])
+            dy = ops.bn_bwd_apply(G, y_last, affs[-1][0], affs[-1][1], False, cA, cP, cQ)
+        grads[5 * (k - 1) + 1], grads[5 * (k - 1) + 2] = dg, db
+        # shortcut branch
+        dx_short = None
+        if spec.residual:
+            if yd is not None:
+                wd, gd = tensors[5 * k], tensors[5 * k + 1]
+                dgd, dbd, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 2, yd.numel() // yd.shape[-1], gd,
+                                                           affd[2], affd[3])
+                dyd = ops.bn_bwd_apply(G, yd, affd[0], affd[1], False, cA, cP, cQ)
+                grads[5 * k] = ops.conv_wgrad(xp, dyd, wd.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0))
+                grads[5 * k + 1], grads[5 * k + 2] = dgd, dbd
+                if spec.need_dx:
+                    dx_short = ops.conv_dgrad(dyd, wd, xp.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0))
+            else:
+                dx_short = G
+        # main branch, last conv to first
+        dx = None
+        for i in range(k - 1, -1, -1):
+            w = tensors[5 * i]
+            if i > 0:
+                inp, a_in, b_in = ys[i - 1], affs[i - 1][0], affs[i - 1][1]
+            else:
+                inp, a_in, b_in = xp, None, None
+            grads[5 * i] = ops.conv_wgrad(inp, dy, w.shape, spec.kernels[i], spec.strides[i], spec.pads[i], a_in, b_in,
+                                          i > 0)
+            if i > 0:
+                dA = ops.conv_dgrad(dy, w, inp.shape, spec.kernels[i], spec.strides[i], spec.pads[i])
+                cnt = inp.numel() // inp.shape[-1]
+                partial, rows = ops.bn_bwd_reduce(dA, inp, a_in, b_in, True)
+                dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, 2, 1, cnt, tensors[5 * (i - 1) + 1],
+                                                         affs[i - 1][2], affs[i - 1][3])
+                grads[5 * (i - 1) + 1], grads[5 * (i - 1) + 2] = dg, db
+                dy = ops.bn_bwd_apply(dA, inp, a_in, b_in, True, cA, cP, cQ, out=dA)
+            elif spec.need_dx:
+                dx = ops.conv_dgrad(dy, w, inp.shape, spec.kernels[i], spec.strides[i], spec.pads[i], addend=dx_short)
+                dx_short = None
+        if spec.need_dx and dx is None:
+            dx = dx_short
+        dxl = to_logical(dx, spec.ndim) if (spec.need_dx and dx is not None) else None
+        return (None, dxl) + tuple(grads)
+
+
+class MaxPoolFunction(torch.autograd.Function):
+    """Stand-alone nn.MaxPool3d / nn.MaxPool2d (kernel = stride, floor); fusion3D2D.py:87-90,168-171."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, ndim):
+        xp = to_phys(x)
+        zp = ops.maxpool_fwd(xp, kernel)
+        ctx.save_for_backward(xp)
+        ctx.kernel, ctx.ndim = kernel, ndim
+        return to_logical(zp, ndim)
+
+    @staticmethod
+    def backward(ctx, dzp):
+        (xp,) = ctx.saved_tensors
+        return to_logical(ops.maxpool_bwd(xp, to_phys(dzp), ctx.kernel), ctx.ndim), None, None
+
+
+class MeanDepthFunction(torch.autograd.Function):
+    """torch.mean(x, dim=4, keepdim=True) on a channels-last feature (fusion3D2D.py:528-536), for callers that
+    use the projection modules stand-alone; the fused path is ConvXSpec.tail == 'mean'."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xp = to_phys(x)
+        C = xp.shape[-1]
+        one = torch.ones(C, dtype=torch.float32, device=xp.device)
+        zero = torch.zeros(C, dtype=torch.float32, device=xp.device)
+        ctx.shape = tuple(xp.shape)
+        # inputs here are post-ReLU (>= 0): relu(1*x+0) == x
+        ctx.nonneg = True
+        return to_logical(ops.proj_tail_fwd(xp, one, zero), 5)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return to_logical(ops.proj_tail_bwd(to_phys(dout), ctx.shape), 5)
+
+
+class Resize2DFunction(torch.autograd.Function):
+    """conv_2d[:,:,:,:,None] then None / F.interpolate(trilinear) / F.adaptive_max_pool3d to the en-face grid
+    (fusion3D2D.py:544-564).  Input (B,C,S',W') logical; output (B,C,S,W,1)."""
+
+    @staticmethod
+    def forward(ctx, x, size, mode):
+        xp = to_phys(x)
+        out, idx = ops.resize2d_fwd(xp, int(size[0]), int(size[1]), mode)
+        ctx.mode, ctx.x_shape, ctx.in_ndim = mode, tuple(xp.shape), x.dim()
+        ctx.save_for_backward(idx if idx is not None else torch.empty(0, device=xp.device))
+        return to_logical(out, 5)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dx = ops.resize2d_bwd(to_phys(dout), ctx.x_shape, ctx.mode, idx if idx.numel() else None)
+        return to_logical(dx, ctx.in_ndim), None, None
+
+
+class UpCatFunction(torch.autograd.Function):
+    """Upsample_Custom3d_nearest(deeper) and torch.cat([skip..., up], 1) (fusion3D2D.py:956-966,
+    components.py:72-76, :259-268) written straight into one concat buffer."""
+
+    @staticmethod
+    def forward(ctx, factor, deeper, *skips):
+        dp = to_phys(deeper)
+        sp = [to_phys(s) for s in skips]
+        fS, fW = int(factor[0]), int(factor[1])
+        B, Si, Wi, H, Cd = dp.shape
+        if H != 1 or int(factor[2]) != 1:
+            raise ValueError('the decoder upsamples en-face maps only (depth 1, factor (fS, fW, 1))')
+        So, Wo = Si * fS, Wi * fW
+        for s in sp:
+            if tuple(s.shape[:4]) != (B, So, Wo, 1):
+                raise RuntimeError(f'Sizes of tensors must match except in dimension 1: skip {tuple(s.shape)} vs '
+                                   f'upsampled {(B, So, Wo, 1, Cd)}')
+        Ctot = sum(s.shape[-1] for s in sp) + Cd
+        cat = torch.empty((B, So, Wo, 1, Ctot), dtype=dp.dtype, device=dp.device)
+        off = 0
+        for s in sp:
+            ops.slice_copy(s, 0, cat, off, s.shape[-1])
+            off += s.shape[-1]
+        ops.upsample_fwd(dp, fS, fW, out=cat, coff=off)
+        ctx.meta = (fS, fW, tuple(dp.shape), [tuple(s.shape) for s in sp])
+        return to_logical(cat, 5)
+
+    @staticmethod
+    def backward(ctx, dcat):
+        fS, fW, dshape, sshapes = ctx.meta
+        dc = to_phys(dcat)
+        outs, off = [], 0
+        for sh in sshapes:
+            g = torch.empty(sh, dtype=dc.dtype, device=dc.device)
+            ops.slice_copy(dc, off, g, 0, sh[-1])
+            outs.append(to_logical(g, 5))
+            off += sh[-1]
+        dd = ops.upsample_bwd(dc, dshape, fS, fW, coff=off)
+        return (None, to_logical(dd, 5)) + tuple(outs)
+
+
+class CatFunction(torch.autograd.Function):
+    """torch.cat(tensors, 1) for channels-last en-face maps (fusion3D2D.py:572)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        ps = [to_phys(x) for x in xs]
+        Ctot = sum(p.shape[-1] for p in ps)
+        cat = torch.empty(tuple(ps[0].shape[:4]) + (Ctot,), dtype=ps[0].dtype, device=ps[0].device)
+        off = 0
+        for p in ps:
+            if tuple(p.shape[:4]) != tuple(ps[0].shape[:4]):
+                raise RuntimeError('Sizes of tensors must match except in dimension 1')
+            ops.slice_copy(p, 0, cat, off, p.shape[-1])
+            off += p.shape[-1]
+        ctx.shapes = [tuple(p.shape) for p in ps]
+        return to_logical(cat, 5)
+
+    @staticmethod
+    def backward(ctx, dcat):
+        dc = to_phys(dcat)
+        outs, off = [], 0
+        for sh in ctx.shapes:
+            g = torch.empty(sh, dtype=dc.dtype, device=dc.device)
+            ops.slice_copy(dc, off, g, 0, sh[-1])
+            outs.append(to_logical(g, 5))
+            off += sh[-1]
+        return tuple(outs)
+
+
+class HeadFunction(torch.autograd.Function):
+    """final1 = nn.Conv3d(C, n_classes, 1) with bias (fusion3D2D.py:223,579) -> fp32 logits (B,n,S,W,1)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        xp = to_phys(x)
+        ctx.save_for_backward(xp, w)
+        ctx.has_bias = bias is not None
+        return ops.head_fwd(xp, w, bias)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        xp, w = ctx.saved_tensors
+        dx, dw, db = ops.head_bwd(xp, w, dlogits.contiguous().float(), need_dx=ctx.needs_input_grad[0])
+        return (to_logical(dx, 5) if dx is not None else None), dw, (db if ctx.has_bias else None)
+
+
+def pack_oct(oct: torch.Tensor) -> torch.Tensor:
+    """(B,1,S,W,H) logical OCT volume as handed over by FPNHybridFusion.forward (a permuted *view* of the
+    dataloader's (B,1,S,H,W) batch, fusion_nets.py:114) -> channels-last compute-dtype tensor, same logical
+    shape.  The H<->W transpose is done by one kernel instead of a strided read in the first conv."""
+    if oct.dim() != 5 or oct.shape[1] != 1:
+        raise ValueError(f'expected a (B,1,S,W,H) volume, got {tuple(oct.shape)}')
+    src = oct.permute(0, 1, 2, 4, 3)                       # back to (B,1,S,H,W)
+    if src.is_contiguous() and src.dtype == torch.float32:
+        p = ops.pack_volume(src, _COMPUTE_DTYPE)           # memory order (B,1,S,W,H); C == 1
+        B, _, S, W, H = oct.shape
+        return p.view(B, S, W, H, 1).permute(0, 4, 1, 2, 3)
+    return to_logical(to_phys(oct.float()), 5)
+
+
+def pack_image2d(img: torch.Tensor) -> torch.Tensor:
+    """(B,1,S',W') fp32 -> channels-last compute dtype (same logical shape)."""
+    return to_logical(to_phys(img.float().contiguous() if img.dtype != torch.float32 else img), 4)

@@ -1,0 +1,287 @@
+"""Thin tensor-level wrappers over the C ABI.  Tensors here are PHYSICAL channels-last activations
+(B, S, W, H, C) contiguous; all launches go to torch's current CUDA stream."""
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import lib
+from .lib import ConvDesc, STAT_ROWS
+
+_CONV_IMPL = 0          # 0 auto, 1 force CUDA-core kernels, 2 force tcgen05 (debug / parity tests)
+
+
+def set_conv_impl(mode: int) -> None:
+    global _CONV_IMPL
+    assert mode in (0, 1, 2)
+    _CONV_IMPL = mode
+
+
+def get_conv_impl() -> int:
+    return _CONV_IMPL
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _dev(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise lib.FfpnError('fusion FPN kernels got a CPU tensor: there is no CPU fallback, move the model and batch to cuda')
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _chk(t: torch.Tensor, name: str):
+    if not t.is_contiguous():
+        raise lib.FfpnError(f'{name} must be contiguous (physical channels-last)')
+
+
+def conv_out_extent(n: int, k: int, s: int, p: int) -> int:
+    return (n + 2 * p - k) // s + 1
+
+
+def make_desc(x_shape, cout: int, kernel: Sequence[int], stride: Sequence[int], pad: Sequence[int], dtype) -> ConvDesc:
+    B, S, W, H, Cin = x_shape
+    d = ConvDesc()
+    d.B, d.S, d.W, d.H = B, S, W, H
+    d.Cin, d.Cout = Cin, cout
+    d.kS, d.kW, d.kH = kernel
+    d.sS, d.sW, d.sH = stride
+    d.pS, d.pW, d.pH = pad
+    d.oS = conv_out_extent(S, kernel[0], stride[0], pad[0])
+    d.oW = conv_out_extent(W, kernel[1], stride[1], pad[1])
+    d.oH = conv_out_extent(H, kernel[2], stride[2], pad[2])
+    d.dtype = lib.dtype_code(dtype)
+    d.impl = _CONV_IMPL
+    return d
+
+
+def _workspace(d: ConvDesc, like: torch.Tensor):
+    n = int(lib.load().ffpn_conv_workspace_bytes(C.byref(d)))
+    if n == 0:
+        return None, 0
+    return torch.empty(n, dtype=torch.uint8, device=like.device), n
+
+
+def new_partial(device, ncols: int, C_: int) -> torch.Tensor:
+    return torch.empty(STAT_ROWS * ncols * C_, dtype=torch.float32, device=device)
+
+
+def conv_fwd(x, w, kernel, stride, pad, in_scale=None, in_shift=None, in_relu=False, want_stats=True):
+    """-> (y, partial, rows).  y raw conv output, partial sums for BatchNorm."""
+    _chk(x, 'x')
+    cout = w.shape[0]
+    d = make_desc(x.shape, cout, kernel, stride, pad, x.dtype)
+    y = torch.empty((d.B, d.oS, d.oW, d.oH, cout), dtype=x.dtype, device=x.device)
+    partial = new_partial(x.device, 2, cout) if want_stats else None
+    rows = C.c_int(0)
+    ws, nws = _workspace(d, x)
+    lib.call('ffpn_conv_fwd', _dev(x), C.byref(d), _ptr(x), _ptr(in_scale), _ptr(in_shift), int(bool(in_relu)), _ptr(w),
+             _ptr(y), _ptr(partial), C.byref(rows), _ptr(ws), nws, _stream(x))
+    return y, partial, rows.value
+
+
+def conv_dgrad(dy, w, x_shape, kernel, stride, pad, addend=None):
+    _chk(dy, 'dy')
+    d = make_desc(x_shape, w.shape[0], kernel, stride, pad, dy.dtype)
+    assert tuple(dy.shape) == (d.B, d.oS, d.oW, d.oH, w.shape[0]), (tuple(dy.shape), (d.B, d.oS, d.oW, d.oH, w.shape[0]))
+    dx = torch.empty(tuple(x_shape), dtype=dy.dtype, device=dy.device)
+    ws, nws = _workspace(d, dy)
+    lib.call('ffpn_conv_dgrad', _dev(dy), C.byref(d), _ptr(dy), _ptr(w), _ptr(addend), _ptr(dx), _ptr(ws), nws, _stream(dy))
+    return dx
+
+
+def conv_wgrad(x, dy, w_shape, kernel, stride, pad, in_scale=None, in_shift=None, in_relu=False):
+    _chk(x, 'x'); _chk(dy, 'dy')
+    d = make_desc(x.shape, w_shape[0], kernel, stride, pad, x.dtype)
+    dw = torch.zeros(tuple(w_shape), dtype=torch.float32, device=x.device)
+    ws, nws = _workspace(d, x)
+    lib.call('ffpn_conv_wgrad', _dev(x), C.byref(d), _ptr(x), _ptr(in_scale), _ptr(in_shift), int(bool(in_relu)), _ptr(dy),
+             _ptr(dw), _ptr(ws), nws, _stream(x))
+    return dw
+
+
+def bn_finalize(partial, rows, count, gamma, beta, running_mean, running_var, momentum, eps, training):
+    """-> (scale, shift, save_mean, save_invstd)"""
+    C_ = gamma.numel()
+    out = torch.empty(4, C_, dtype=torch.float32, device=gamma.device)
+    lib.call('ffpn_bn_finalize', _dev(gamma), _ptr(partial), rows, C_, float(count), _ptr(gamma), _ptr(beta),
+             _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), int(bool(training)), _ptr(out[0]),
+             _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream(gamma))
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_bwd_reduce(dA, y, scale, shift, relu):
+    C_ = y.shape[-1]
+    P = y.numel() // C_
+    partial = new_partial(y.device, 2, C_)
+    rows = C.c_int(0)
+    lib.call('ffpn_bn_bwd_reduce', _dev(y), lib.dtype_code(y.dtype), P, C_, _ptr(dA), _ptr(y), _ptr(scale), _ptr(shift),
+             int(bool(relu)), _ptr(partial), C.byref(rows), _stream(y))
+    return partial, rows.value
+
+
+def bn_bwd_finalize(partial, rows, ncols, ycol, count, gamma, save_mean, save_invstd):
+    """-> (dgamma, dbeta, cA, cP, cQ)"""
+    C_ = gamma.numel()
+    out = torch.empty(5, C_, dtype=torch.float32, device=gamma.device)
+    lib.call('ffpn_bn_bwd_finalize', _dev(gamma), _ptr(partial), rows, ncols, ycol, C_, float(count), _ptr(gamma),
+             _ptr(save_mean), _ptr(save_invstd), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(out[4]),
+             _stream(gamma))
+    return out[0], out[1], out[2], out[3], out[4]
+
+
+def bn_bwd_apply(dA, y, scale, shift, relu, cA, cP, cQ, out=None):
+    C_ = y.shape[-1]
+    P = y.numel() // C_
+    dy = torch.empty_like(y) if out is None else out
+    lib.call('ffpn_bn_bwd_apply', _dev(y), lib.dtype_code(y.dtype), P, C_, _ptr(dA), _ptr(y), _ptr(scale), _ptr(shift),
+             int(bool(relu)), _ptr(cA), _ptr(cP), _ptr(cQ), _ptr(dy), _stream(y))
+    return dy
+
+
+def block_end_fwd(y, a, b, res=None, ra=None, rb=None):
+    C_ = y.shape[-1]
+    z = torch.empty_like(y)
+    lib.call('ffpn_block_end_fwd', _dev(y), lib.dtype_code(y.dtype), y.numel() // C_, C_, _ptr(y), _ptr(a), _ptr(b),
+             _ptr(res), _ptr(ra), _ptr(rb), _ptr(z), _stream(y))
+    return z
+
+
+def block_end_bwd(dz, dzp, z, y, yres, pool):
+    """-> (G, partial, rows, ncols)"""
+    B, S, W, H, C_ = z.shape
+    ncols = 3 if yres is not None else 2
+    G = torch.empty_like(z)
+    partial = new_partial(z.device, ncols, C_)
+    rows = C.c_int(0)
+    k = pool if (pool is not None and dzp is not None) else (0, 0, 0)
+    lib.call('ffpn_block_end_bwd', _dev(z), lib.dtype_code(z.dtype), B, S, W, H, C_, k[0], k[1], k[2], _ptr(dz), _ptr(dzp),
+             _ptr(z), _ptr(y), _ptr(yres), _ptr(G), _ptr(partial), C.byref(rows), _stream(z))
+    return G, partial, rows.value, ncols
+
+
+def maxpool_fwd(z, kernel, want_idx=False):
+    B, S, W, H, C_ = z.shape
+    zp = torch.empty((B, S // kernel[0], W // kernel[1], H // kernel[2], C_), dtype=z.dtype, device=z.device)
+    idx = torch.empty(zp.shape, dtype=torch.int64, device=z.device) if want_idx else None
+    lib.call('ffpn_maxpool_fwd', _dev(z), lib.dtype_code(z.dtype), B, S, W, H, C_, kernel[0], kernel[1], kernel[2], _ptr(z),
+             _ptr(zp), _ptr(idx), _stream(z))
+    return (zp, idx) if want_idx else zp
+
+
+def maxpool_bwd(z, dzp, kernel):
+    B, S, W, H, C_ = z.shape
+    dz = torch.empty_like(z)
+    lib.call('ffpn_maxpool_bwd', _dev(z), lib.dtype_code(z.dtype), B, S, W, H, C_, kernel[0], kernel[1], kernel[2], _ptr(z),
+             _ptr(dzp), _ptr(dz), _stream(z))
+    return dz
+
+
+def proj_tail_fwd(y, a, b, out=None, coff=0):
+    B, S, W, H, C_ = y.shape
+    if out is None:
+        out = torch.empty((B, S, W, 1, C_), dtype=y.dtype, device=y.device)
+    lib.call('ffpn_proj_tail_fwd', _dev(y), lib.dtype_code(y.dtype), B * S * W, H, C_, _ptr(y), _ptr(a), _ptr(b), _ptr(out),
+             out.shape[-1], coff, _stream(y))
+    return out
+
+
+def proj_tail_bwd(dout, y_shape, coff=0):
+    B, S, W, H, C_ = y_shape
+    dA = torch.empty(tuple(y_shape), dtype=dout.dtype, device=dout.device)
+    lib.call('ffpn_proj_tail_bwd', _dev(dout), lib.dtype_code(dout.dtype), B * S * W, H, C_, _ptr(dout), dout.shape[-1], coff,
+             _ptr(dA), _stream(dout))
+    return dA
+
+
+RESIZE_MODES = {None: 0, '2d_max': 1, '2d': 2}
+
+
+def resize2d_fwd(x, So, Wo, mode, out=None, coff=0):
+    """x: (B, Si, Wi, 1, C) -> (B, So, Wo, 1, C) (or a slice of ``out``); returns (out, idx)."""
+    B, Si, Wi, _, C_ = x.shape
+    m = RESIZE_MODES[mode]
+    if out is None:
+        out = torch.empty((B, So, Wo, 1, C_), dtype=x.dtype, device=x.device)
+    idx = torch.empty((B, So, Wo, C_), dtype=torch.int32, device=x.device) if m == 1 else None
+    lib.call('ffpn_resize2d_fwd', _dev(x), lib.dtype_code(x.dtype), m, B, Si, Wi, So, Wo, C_, _ptr(x), _ptr(out),
+             out.shape[-1], coff, _ptr(idx), _stream(x))
+    return out, idx
+
+
+def resize2d_bwd(dout, x_shape, mode, idx, coff=0):
+    B, Si, Wi, _, C_ = x_shape
+    So, Wo = dout.shape[1], dout.shape[2]
+    dx = torch.empty(tuple(x_shape), dtype=dout.dtype, device=dout.device)
+    lib.call('ffpn_resize2d_bwd', _dev(dout), lib.dtype_code(dout.dtype), RESIZE_MODES[mode], B, Si, Wi, So, Wo, C_,
+             _ptr(dout), dout.shape[-1], coff, _ptr(idx), _ptr(dx), _stream(dout))
+    return dx
+
+
+def upsample_fwd(x, fS, fW, out=None, coff=0):
+    B, Si, Wi, _, C_ = x.shape
+    if out is None:
+        out = torch.empty((B, Si * fS, Wi * fW, 1, C_), dtype=x.dtype, device=x.device)
+    lib.call('ffpn_upsample_fwd', _dev(x), lib.dtype_code(x.dtype), B, Si, Wi, fS, fW, C_, _ptr(x), _ptr(out),
+             out.shape[-1], coff, _stream(x))
+    return out
+
+
+def upsample_bwd(dout, x_shape, fS, fW, coff=0):
+    B, Si, Wi, _, C_ = x_shape
+    dx = torch.empty(tuple(x_shape), dtype=dout.dtype, device=dout.device)
+    lib.call('ffpn_upsample_bwd', _dev(dout), lib.dtype_code(dout.dtype), B, Si, Wi, fS, fW, C_, _ptr(dout), dout.shape[-1],
+             coff, _ptr(dx), _stream(dout))
+    return dx
+
+
+def slice_copy(src, soff, dst, doff, C_):
+    P = src.numel() // src.shape[-1]
+    lib.call('ffpn_slice_copy', _dev(src), lib.dtype_code(src.dtype), P, C_, _ptr(src), src.shape[-1], soff, _ptr(dst),
+             dst.shape[-1], doff, _stream(src))
+
+
+def head_fwd(x, w, bias):
+    """x: (B, S, W, 1, C); w: (n, C, 1, 1, 1) fp32 -> logits fp32 (B, n, S, W, 1) in standard layout."""
+    B, S, W, H, C_ = x.shape
+    n = w.shape[0]
+    logits = torch.empty((B, n, S, W, H), dtype=torch.float32, device=x.device)
+    lib.call('ffpn_head_fwd', _dev(x), lib.dtype_code(x.dtype), B, S * W * H, C_, n, _ptr(x), _ptr(w), _ptr(bias),
+             _ptr(logits), _stream(x))
+    return logits
+
+
+def head_bwd(x, w, dlogits, need_dx=True):
+    B, S, W, H, C_ = x.shape
+    n = w.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w)
+    db = torch.empty(n, dtype=torch.float32, device=x.device)
+    lib.call('ffpn_head_bwd', _dev(x), lib.dtype_code(x.dtype), B, S * W * H, C_, n, _ptr(x), _ptr(w), _ptr(dlogits),
+             _ptr(dx), _ptr(dw), _ptr(db), _stream(x))
+    return dx, dw, db
+
+
+def pack_volume(src, dtype):
+    """src fp32 (..., H, W) contiguous -> (..., W, H) of ``dtype``."""
+    H, W = src.shape[-2], src.shape[-1]
+    R = src.numel() // (H * W)
+    dst = torch.empty(tuple(src.shape[:-2]) + (W, H), dtype=dtype, device=src.device)
+    lib.call('ffpn_pack_volume', _dev(src), lib.dtype_code(dtype), R, H, W, _ptr(src), _ptr(dst), _stream(src))
+    return dst
+
+
+def cast(src, dtype):
+    dst = torch.empty(src.shape, dtype=dtype, device=src.device)
+    lib.call('ffpn_cast', _dev(src), lib.dtype_code(dtype), src.numel(), _ptr(src), _ptr(dst), _stream(src))
+    return dst
+
+
+def sgd_step(p, g, mom, lr, momentum, weight_decay, grad_scale, first_step):
+    lib.call('ffpn_sgd_step', _dev(p), p.numel(), _ptr(p), _ptr(g), _ptr(mom), float(lr), float(momentum),
+             float(weight_decay), float(grad_scale), int(bool(first_step)), _stream(p))

@@ -65,7 +65,7 @@ def maxpool_argmax_firstmax(x: np.ndarray, kernel: Sequence[int]) -> Tuple[np.nd
     """nn.MaxPool3d(kernel) (stride=kernel, floor) with PyTorch's tie rule, pure loops.
 
     fusion3D2D.py:87-90.  Tie -> first element in row-major window scan; NaN wins and
-    propagates.  ``x`` is (S, W, H); returns (values, flat indices into
+    propagates, and with several NaNs in a window the LAST one is indexed (checked against torch).  ``x`` is (S, W, H); returns (values, flat indices into
     S*W*H).  Small cases only.
     """
     kS, kW, kH = kernel
@@ -83,7 +83,7 @@ def maxpool_argmax_firstmax(x: np.ndarray, kernel: Sequence[int]) -> Tuple[np.nd
                         for dh in range(kH):
                             ss, ww, hh = s * kS + ds, w * kW + dw, h * kH + dh
                             v = x[ss, ww, hh]
-                            if best is None or v > best or (np.isnan(v) and not np.isnan(best)):
+                            if best is None or v > best or np.isnan(v):      # aten rule: (val > max) || isnan(val)
                                 best, bi = v, (ss * W + ww) * H + hh
                 val[s, w, h] = best
                 idx[s, w, h] = bi
@@ -108,7 +108,7 @@ def adaptive_maxpool2d_argmax(x: np.ndarray, out_size: Sequence[int]) -> Tuple[n
             for ss in range(s0, s1):
                 for ww in range(w0, w1):
                     v = x[ss, ww]
-                    if best is None or v > best or (np.isnan(v) and not np.isnan(best)):
+                    if best is None or v > best or np.isnan(v):      # aten rule: (val > max) || isnan(val)
                         best, bi = v, ss * Wi + ww
             val[s, w] = best
             idx[s, w] = bi

@@ -114,6 +114,8 @@ def main():
     x = torch.randn(1, 1, 4, 6, 8, generator=g)
     x = (x * 2).round() / 2                                   # many ties
     x[0, 0, 1, 2, 3] = float('nan')
+    x[0, 0, 3, 0, 0] = float('nan')
+    x[0, 0, 3, 1, 1] = float('nan')                          # two NaNs in one window: the last is indexed
     for name, k in (('p122', (1, 2, 2)), ('p222', (2, 2, 2))):
         v, i = F.max_pool3d(x, k, return_indices=True)
         ix[f'{name}/x'] = x.numpy()

@@ -1,0 +1,179 @@
+"""Stage- and model-level parity on the B200: the reference-shaped modules (CUDA kernels underneath) against
+the CPU oracle and the committed golden fixtures, same weights, same seeded inputs.
+
+Tolerances: fp32 path -- prediction rel-L2 <= 1e-4, gradients <= 3x the fp32-vs-fp64 floor of
+torch itself (we use 1e-2 global / 3e-2 for conv1-4 stages whose ReLU/pool decisions flip); bf16 path -- loss
+within 2e-2 of fp32, prediction rel-L2 <= 0.15 (PyTorch's own bf16 autocast is at 7.5e-2 on this model)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_fpn_oracle as O
+
+pytestmark = pytest.mark.gpu
+CROPS = ['relative_2d_max', 'relative_2d', 'oct']
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(autouse=True)
+def _exact_mode():
+    import ffpn
+    ffpn.set_compute_dtype(torch.float32)
+    yield
+    ffpn.set_compute_dtype(torch.bfloat16)
+
+
+def _loss(mirror, batch, out):
+    crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                            'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+    return crit(batch, out)[0]
+
+
+def _run(mirror, sd, batch, crop, train=True):
+    model = mirror.build('FPNHybridFusion', crop).cuda()
+    model.load_state_dict(sd, strict=True)
+    model.train(train)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    out = model(cb)
+    return model, cb, out
+
+
+@pytest.mark.parametrize('crop', CROPS)
+def test_model_matches_golden_and_oracle_fp32(mirror, golden_dir, crop):
+    fx = np.load(os.path.join(golden_dir, f'fusion_{crop}.npz'))
+    B, S, H, W, S2, W2 = [int(v) for v in fx['shape']]
+    sd = O.make_state_dict(seed=int(fx['seed_weights']))
+    batch = O.synthetic_batch(B, S, H, W, S2, W2, seed=int(fx['seed_batch']))
+    model, cb, out = _run(mirror, sd, batch, crop)
+    pred = out['prediction']
+    assert tuple(pred.shape) == (B, 1, S, 1, W) and pred.dtype == torch.float32
+    # golden = the unmodified reference in fp64
+    assert rel(pred.cpu(), torch.from_numpy(fx['prediction'])) <= 1e-4
+    loss = _loss(mirror, cb, out)
+    assert abs(loss.item() - float(fx['loss'])) <= 1e-4
+    loss.backward()
+    names = [str(n) for n in fx['grad_names']]
+    grads = dict((k, p.grad) for k, p in model.named_parameters())
+    assert list(grads) == names and all(g is not None for g in grads.values())
+    l2 = np.array([grads[n].double().norm().item() for n in names])
+    tot = np.sqrt((fx['grad_l2'] ** 2).sum())
+    assert abs(np.sqrt((l2 ** 2).sum()) - tot) <= 1e-2 * tot
+    for k in fx.files:
+        if k.startswith('grad/'):
+            g, r = grads[k[5:]].cpu().numpy(), fx[k]
+            denom = max(np.linalg.norm(r), 1e-3 * tot)
+            assert np.linalg.norm(g - r) <= 3e-2 * denom, (k, np.linalg.norm(g - r), denom)
+    # BN running statistics and counters
+    after = model.state_dict()
+    for k in fx.files:
+        if k.startswith('bn/'):
+            np.testing.assert_allclose(after[k[3:]].cpu().numpy(), fx[k], rtol=1e-4, atol=1e-5, err_msg=k)
+
+
+def test_all_gradients_against_oracle_fp32(mirror):
+    sd = O.make_state_dict(seed=21)
+    batch = O.synthetic_batch(2, 8, 64, 32, 20, 48, seed=9, smooth=True)
+    model, cb, out = _run(mirror, sd, batch, 'relative_2d_max')
+    _loss(mirror, cb, out).backward()
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    loss64, pred64, g64 = O.loss_and_grads(sd64, {k: v.double() for k, v in batch.items()})
+    assert rel(out['prediction'].detach().cpu(), pred64) <= 1e-4
+    num = den = 0.0
+    per_stage = {}
+    for k, p in model.named_parameters():
+        d = (p.grad.double().cpu() - g64[k]).norm().item() ** 2
+        n = g64[k].norm().item() ** 2
+        num, den = num + d, den + n
+        st = k.split('.')[1]
+        a = per_stage.setdefault(st, [0.0, 0.0])
+        a[0] += d
+        a[1] += n
+    assert (num / den) ** 0.5 <= 1e-2, (num / den) ** 0.5
+    for st, (d, n) in per_stage.items():
+        assert (d / max(n, 1e-30)) ** 0.5 <= 3e-2, (st, (d / n) ** 0.5)
+
+
+def test_eval_mode_uses_running_stats(mirror):
+    sd = O.make_state_dict(seed=4, randomize_running=True)
+    batch = O.synthetic_batch(1, 4, 64, 16, 4, 16, seed=2)
+    model, cb, out = _run(mirror, sd, batch, 'oct', train=False)
+    ref = O.fpn_hybrid_fusion_forward(sd, batch, 'oct', train=False)['prediction']
+    assert rel(out['prediction'].cpu(), ref) <= 1e-4
+    after = model.state_dict()
+    assert all(torch.equal(after[k].cpu(), sd[k]) for k in sd)          # eval must not touch the buffers
+
+
+def test_odd_depth_496(mirror):
+    """Full axial depth H=496 (not a multiple of 16): pools floor, projection halves with ceil (C3 shape)."""
+    sd = O.make_state_dict(seed=8)
+    batch = O.synthetic_batch(1, 4, 496, 16, 8, 32, seed=3)
+    model, cb, out = _run(mirror, sd, batch, 'relative_2d_max')
+    ref = O.fpn_hybrid_fusion_forward(sd, batch, 'relative_2d_max')['prediction']
+    assert rel(out['prediction'].cpu(), ref) <= 1e-4
+    _loss(mirror, cb, out).backward()
+
+
+def test_bf16_path_close_to_fp32(mirror):
+    import ffpn
+    sd = O.make_state_dict(seed=21)
+    batch = O.synthetic_batch(2, 8, 64, 32, 20, 48, seed=9, smooth=True)
+    loss64, pred64, g64 = O.loss_and_grads({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()},
+                                           {k: v.double() for k, v in batch.items()})
+    ffpn.set_compute_dtype(torch.bfloat16)
+    model, cb, out = _run(mirror, sd, batch, 'relative_2d_max')
+    loss = _loss(mirror, cb, out)
+    loss.backward()
+    assert abs(loss.item() - loss64.item()) <= 2e-2
+    assert rel(out['prediction'].detach().cpu(), pred64) <= 0.15
+    dot = sum((p.grad.double().cpu() * g64[k]).sum().item() for k, p in model.named_parameters())
+    na = sum(p.grad.double().norm().item() ** 2 for p in model.parameters()) ** 0.5
+    nb = sum(g.norm().item() ** 2 for g in g64.values()) ** 0.5
+    assert dot / (na * nb) >= 0.4, dot / (na * nb)       # PyTorch bf16 autocast: 0.45
+
+
+@pytest.mark.parametrize('name', ['FPN', 'FPN2D', 'FPNLateFusion'])
+def test_other_wirings_forward(mirror, name):
+    import torch.nn.functional as F
+    batch = O.synthetic_batch(1, 8, 64, 32, 8, 32, seed=5)
+    model = mirror.build(name, 'oct').cuda().train()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    out = model({k: v.cuda() for k, v in batch.items()})['prediction']
+    oct = batch['image'].permute(0, 1, 2, 4, 3)
+    slo = batch['slo'][:, :, :, 0, :]
+    if name == 'FPN':
+        ref = torch.sigmoid(O.unet3d_body_forward(sd, oct).permute(0, 1, 2, 4, 3))
+    elif name == 'FPN2D':
+        ref = torch.sigmoid(O.unet2d_body_forward(sd, slo).permute(0, 1, 2, 4, 3))
+    else:
+        a = O.unet3d_body_forward(sd, oct, prefix='resensnet3d', use_1x1=False)
+        b = O.unet2d_body_forward(sd, slo, prefix='resensnet2d', output_features=True)
+        ref = torch.sigmoid(F.conv3d(torch.cat([a, b], 1), sd['fusion_module.weight'], sd['fusion_module.bias'])
+                            .permute(0, 1, 2, 4, 3))
+    assert out.shape == ref.shape and rel(out.detach().cpu(), ref) <= 1e-4
+    out.sum().backward()
+    assert all(p.grad is not None for k, p in model.named_parameters() if 'final1' not in k or name != 'FPNLateFusion')
+
+
+def test_training_wrapper_step(mirror):
+    model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+    crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                            'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    wrap = mirror.wrapper.Model(model, crit, None, None, None, [opt])
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 16, 8, 32, seed=1).items()}
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = wrap.training_step(batch, 0)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and wrap.configure_optimizers() == [opt]
+    assert 'Training/Dice' in wrap.logged and len(wrap.logged['Training/BCE']) == 3
+    assert int(model.state_dict()['resensnet.conv1.0.convBlock.0.1.num_batches_tracked']) == 3

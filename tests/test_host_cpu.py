@@ -1,0 +1,168 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol of include/ffpn.h, the
+reference-shaped modules keep the reference's state_dict / constructor / registry contract, seeded
+initialisation reproduces the reference's, and the product refuses to run without CUDA (no fallback)."""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_fpn_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ffpn import lib
+    header = open(os.path.join(REPO, 'include', 'ffpn.h')).read()
+    declared = set(re.findall(r'\b(ffpn_[a-z0-9_]+)\s*\(', header))
+    declared -= {'ffpn_last_error'} - set(lib.EXPORTS)
+    handle = lib.load()
+    assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.ffpn_abi_version() == 1
+    d = lib.ConvDesc()
+    assert handle.ffpn_conv_workspace_bytes(d) >= 0          # pure host call, no GPU needed
+
+
+def test_sass_has_no_foreign_arch():
+    import subprocess
+    from ffpn import lib
+    out = subprocess.run(['cuobjdump', '-lelf', lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_\d+a?', out))
+    assert archs == {'sm_100a'}, archs
+
+
+def test_no_cpu_fallback(mirror):
+    model = mirror.build('FPNHybridFusion')
+    batch = O.synthetic_batch(1, 4, 64, 16, 8, 32)
+    from ffpn.lib import FfpnError
+    with pytest.raises(FfpnError):
+        model(batch)
+
+
+def test_state_dict_contract(mirror, golden_dir):
+    model = mirror.build('FPNHybridFusion')
+    sd = model.state_dict()
+    osd = O.make_state_dict()
+    assert list(sd.keys()) == list(osd.keys())
+    assert all(sd[k].shape == osd[k].shape and sd[k].dtype == osd[k].dtype for k in sd)
+    model.load_state_dict(osd, strict=True)
+    assert sum(p.numel() for p in model.parameters()) == 6142481 and len(list(model.parameters())) == 275
+    assert all(p.requires_grad for p in model.parameters())
+    kinds = {}
+    for m in model.modules():
+        kinds[type(m).__mro__[1].__name__ if type(m).__module__.startswith('models') and type(m).__mro__[1].__module__.startswith('torch') else type(m).__name__] = \
+            kinds.get(type(m).__mro__[1].__name__ if type(m).__module__.startswith('models') and type(m).__mro__[1].__module__.startswith('torch') else type(m).__name__, 0) + 1
+    n = lambda cls: sum(isinstance(m, cls) for m in model.modules())
+    # SURVEY.md App. A leaf-module census
+    assert (n(torch.nn.Conv3d), n(torch.nn.BatchNorm3d), n(torch.nn.Conv2d), n(torch.nn.BatchNorm2d)) == (62, 61, 30, 30)
+    assert (n(torch.nn.ReLU), n(torch.nn.MaxPool3d), n(torch.nn.MaxPool2d)) == (73, 4, 4)
+    # wrapper prefix (pl_model_wrapper.py:123)
+    wrap = mirror.wrapper.Model(model, None, None, None, None, [])
+    assert next(iter(wrap.state_dict())) == 'model.resensnet.conv1.0.convBlock.0.0.weight'
+
+
+def test_seeded_weight_init_matches_reference(mirror, golden_dir):
+    fx = np.load(os.path.join(golden_dir, 'weight_init.npz'))
+    torch.manual_seed(1234)
+    model = mirror.build('FPNHybridFusion')
+    model.apply(mirror.weight_init.weight_init)
+    sd = model.state_dict()
+    assert [str(n) for n in fx['names']] == list(sd.keys())
+    s1 = np.array([v.double().sum().item() for v in sd.values()])
+    s2 = np.array([v.double().abs().sum().item() for v in sd.values()])
+    np.testing.assert_allclose(s1, fx['sum'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(s2, fx['abssum'], rtol=0, atol=1e-9)
+
+
+def test_factory_and_signatures(mirror):
+    fc = mirror.fusion_nets.factory_classes
+    assert sorted(fc) == ['FPN', 'FPN2D', 'FPNClassification', 'FPNHybridFusion', 'FPNHybridFusionRegression',
+                          'FPNLateFusion', 'FPNLateFusionRegression', 'FPNRegression']
+    counts = {'FPN': 4369553, 'FPN2D': 2077745, 'FPNLateFusion': 6447314}
+    for name, c in counts.items():
+        assert sum(p.numel() for p in mirror.build(name).parameters()) == c
+    from models.fpn import fusion3D2D, unets3D, unets2D, components
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(fusion3D2D.ModifiedUnet3D2D.__init__) == ['self', 'config', 'interpolate', 'feature_fusion']
+    assert sig(fusion3D2D.ModifiedUnet3D2DLevel5.forward) == ['self', 'oct', 'slo']
+    assert sig(unets3D.ModifiedUnet3D.__init__) == ['self', 'config', 'original', 'classification']
+    assert sig(unets2D.ModifiedUnet2D.__init__) == ['self', 'config', 'output_features']
+    assert sig(fusion3D2D.unet3dConvX.__init__) == ['self', 'in_size', 'out_size', 'kernel_size', 'stride', 'padding',
+                                                    'is_batchnorm', 'is_residual', 'dropout', 'downsample']
+    assert sig(components.unet3dUp2modified.__init__) == ['self', 'lowlayer_channels', 'currlayer_channels', 'upfactor',
+                                                          'is_deconv', 'is_residual', 'dropout', 'is_batchnorm']
+    assert sig(fusion3D2D.unet3dUp2modified.forward) == ['self', 'inputs1', 'inputs1_b', 'inputs2']
+    m = mirror.build('FPNHybridFusion', crop='relative_2d')
+    assert m.interpolate == '2d' and mirror.build('FPNHybridFusion', crop='oct').interpolate is None
+    assert mirror.build('FPNHybridFusion', crop='relative_2d_max').resensnet.interpolate == '2d_max'
+    body = m.resensnet
+    assert body.channels == [16, 32, 64, 128, 256] and len(body.dropout) == 9 and body.model_name == 'ModifiedUnet3D'
+    with pytest.raises(ValueError):
+        fusion3D2D.ModifiedUnet3D2D(m.config, None, 'mul')
+    assert 'resensnet.final1.0.weight' in mirror.build('FPN2D').state_dict()
+    late = mirror.build('FPNLateFusion')
+    assert late.resensnet3d.use_1x1 is False and 'fusion_module.weight' in late.state_dict()
+    cls = mirror.build('FPNClassification')
+    assert not any(p.requires_grad for p in cls.resensnet.zdimRed1.parameters())
+
+
+def test_config_flags(mirror):
+    cfg = mirror.config
+    for k, v in dict(batch_size=8, virtual_batch_size=1, learning_rate=0.1, number_of_outputs=1, epochs=40,
+                     force_mem_cache_release='ReleaseMemCache', threads=8, base_channels=64).items():
+        assert getattr(cfg, k) == v, k
+    assert cfg.use_complementary is True and cfg.layers == [1, 1, 2, 4] and cfg.number_of_channels == [32, 64, 128, 256]
+
+
+def test_losses_match_oracle(mirror):
+    g = torch.Generator().manual_seed(0)
+    pred = torch.rand(2, 1, 8, 1, 32, generator=g)
+    mask = (torch.rand(2, 1, 8, 1, 32, generator=g) > 0.5).float()
+    crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                            'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+    total, parts = crit({'mask': mask}, {'prediction': pred})
+    assert abs(total.item() - O.mix_loss(pred, mask).item()) < 1e-7
+    assert abs(parts['Dice'].item() - O.dice_loss(pred, mask).item()) < 1e-7
+    with pytest.raises(AssertionError):
+        crit({'mask': mask[:1]}, {'prediction': pred})
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from ffpn.trainer import flatten_parameters, allreduce_mean_
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv3d(2, 3, 1), torch.nn.BatchNorm3d(3))
+    flat_p, flat_g = flatten_parameters(net)
+    g = torch.Generator().manual_seed(100 + rank)
+    for p in net.parameters():
+        p.grad.copy_(torch.randn(p.shape, generator=g))          # rank-local gradients (own BN stats / loss)
+    local = {k: p.grad.clone() for k, p in net.named_parameters()}
+    scale = allreduce_mean_(flat_g)
+    q.put((rank, local, {k: p.grad.clone() * scale for k, p in net.named_parameters()},
+           all(p.data_ptr() >= flat_p.data_ptr() for p in net.parameters())))
+    dist.destroy_process_group()
+
+
+def test_dp_gradient_average_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    want = O.dp_average_gradients([res[0][1], res[1][1]])
+    for r in res:
+        assert r[3]
+        for k in want:
+            assert torch.allclose(r[2][k], want[k], atol=1e-7)
