@@ -8,35 +8,47 @@ namespace {
 constexpr int EW_THREADS = 256;
 
 // ---- finalize: partial sums -> mean / invstd / scale / shift, running stats -------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+// 32 channels per block, 8 row lanes; loads are coalesced across channels and the 8 lane partials are added
+// in a fixed order, so the result is deterministic.
+constexpr int FIN_LANES = 8;
+
+__device__ __forceinline__ void column_sums(const float* __restrict__ partial, int rows, int ncols, int col_a, int col_b,
+                                            int C, int c, int rl, double (*red)[32][2], double& sa, double& sb) {
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int r = rl; r < rows; r += FIN_LANES) {
+      a += (double)partial[((int64_t)r * ncols + col_a) * C + c];
+      b += (double)partial[((int64_t)r * ncols + col_b) * C + c];
+    }
+  }
+  red[rl][threadIdx.x & 31][0] = a;
+  red[rl][threadIdx.x & 31][1] = b;
+  __syncthreads();
+  sa = sb = 0.0;
+  for (int l = 0; l < FIN_LANES; l++) { sa += red[l][threadIdx.x & 31][0]; sb += red[l][threadIdx.x & 31][1]; }
+}
+
+__global__ void __launch_bounds__(32 * FIN_LANES)
+bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, int training, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  // one warp per channel; fixed summation order -> deterministic
-  const int c = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+  __shared__ double red[FIN_LANES][32][2];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
   double mean, var;
   if (training) {
-    double s = 0.0, q = 0.0;
-    for (int r = lane; r < rows; r += 32) {
-      s += (double)partial[((int64_t)r * 2 + 0) * C + c];
-      q += (double)partial[((int64_t)r * 2 + 1) * C + c];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
+    double s, q;
+    column_sums(partial, rows, 2, 0, 1, C, c, rl, red, s, q);
     mean = s / count;
     var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
   } else {
-    mean = (double)running_mean[c];
-    var = (double)running_var[c];
+    mean = c < C ? (double)running_mean[c] : 0.0;
+    var = c < C ? (double)running_var[c] : 1.0;
   }
-  if (lane == 0) {
+  if (rl == 0 && c < C) {
     const double invstd = 1.0 / sqrt(var + (double)eps);
     const float a = (float)((double)gamma[c] * invstd);
     scale[c] = a;
@@ -108,25 +120,18 @@ bn_bwd_reduce_kernel(int64_t P, int C, const T* __restrict__ dA, const T* __rest
 }
 
 // ---- backward pass 2: coefficients ---------------------------------------------------------------------
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int ncols, int ycol, int C,
+__global__ void __launch_bounds__(32 * FIN_LANES)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int ncols, int ycol, int C,
                                        double count, const float* __restrict__ gamma,
                                        const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ cA,
                                        float* __restrict__ cP, float* __restrict__ cQ) {
-  const int c = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int r = lane; r < rows; r += 32) {
-    s1 += (double)partial[((int64_t)r * ncols + 0) * C + c];
-    s2 += (double)partial[((int64_t)r * ncols + ycol) * C + c];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (lane == 0) {
+  __shared__ double red[FIN_LANES][32][2];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  double s1, s2;
+  column_sums(partial, rows, ncols, 0, ycol, C, c, rl, red, s1, s2);
+  if (rl == 0 && c < C) {
     const double mu = (double)save_mean[c], is = (double)save_invstd[c], gm = (double)gamma[c];
     const double dg = is * (s2 - mu * s1);   // sum G * xhat
     const double a = gm * is;
@@ -371,8 +376,7 @@ extern "C" int ffpn_bn_finalize(ffpn_ctx* ctx, const float* stat_partial, int st
                                 float momentum, float eps, int training, float* scale, float* shift, float* save_mean,
                                 float* save_invstd, void* stream) {
   if (training && (stat_partial == nullptr || stat_rows <= 0)) FFPN_FAIL(ctx, "bn_finalize: training needs partial sums");
-  const int wpb = 4;
-  bn_finalize_kernel<<<(C + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+  bn_finalize_kernel<<<(C + 31) / 32, 32 * FIN_LANES, 0, (cudaStream_t)stream>>>(
       stat_partial, stat_rows, C, count, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift,
       save_mean, save_invstd);
   FFPN_CHECK_LAUNCH(ctx, "bn_finalize");
@@ -386,13 +390,13 @@ extern "C" int ffpn_bn_bwd_reduce(ffpn_ctx* ctx, int dtype, int64_t P, int C, co
   if (dtype == FFPN_F32) {
     CHECK_C(ctx, C, 4, "bn_bwd_reduce");
     const int lanes = EW_THREADS / (C / 4);
-    const int g = ffpn_grid_for(P, lanes * 8, min(ctx->num_sms * 8, FFPN_STAT_ROWS));
+    const int g = ffpn_grid_for(P, lanes * 8, min(ctx->num_sms * 4, FFPN_STAT_ROWS));
     bn_bwd_reduce_kernel<float><<<g, EW_THREADS, 0, st>>>(P, C, (const float*)dA, (const float*)y, scale, shift, relu, partial);
     *rows = g;
   } else {
     CHECK_C(ctx, C, 8, "bn_bwd_reduce");
     const int lanes = EW_THREADS / (C / 8);
-    const int g = ffpn_grid_for(P, lanes * 8, min(ctx->num_sms * 8, FFPN_STAT_ROWS));
+    const int g = ffpn_grid_for(P, lanes * 8, min(ctx->num_sms * 4, FFPN_STAT_ROWS));
     bn_bwd_reduce_kernel<bf16><<<g, EW_THREADS, 0, st>>>(P, C, (const bf16*)dA, (const bf16*)y, scale, shift, relu, partial);
     *rows = g;
   }
@@ -403,8 +407,7 @@ extern "C" int ffpn_bn_bwd_reduce(ffpn_ctx* ctx, int dtype, int64_t P, int C, co
 extern "C" int ffpn_bn_bwd_finalize(ffpn_ctx* ctx, const float* partial, int rows, int ncols, int ycol, int C,
                                     double count, const float* gamma, const float* save_mean, const float* save_invstd,
                                     float* dgamma, float* dbeta, float* cA, float* cP, float* cQ, void* stream) {
-  const int wpb = 4;
-  bn_bwd_finalize_kernel<<<(C + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * FIN_LANES, 0, (cudaStream_t)stream>>>(
       partial, rows, ncols, ycol, C, count, gamma, save_mean, save_invstd, dgamma, dbeta, cA, cP, cQ);
   FFPN_CHECK_LAUNCH(ctx, "bn_bwd_finalize");
   return 0;
@@ -454,7 +457,7 @@ extern "C" int ffpn_block_end_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S
   const int vec = dtype == FFPN_F32 ? 4 : 8;
   CHECK_C(ctx, C, vec, "block_end_bwd");
   const int lanes = EW_THREADS / (C / vec);
-  const int g = ffpn_grid_for(P, lanes * 4, min(ctx->num_sms * 8, FFPN_STAT_ROWS));
+  const int g = ffpn_grid_for(P, lanes * 4, min(ctx->num_sms * 4, FFPN_STAT_ROWS));
 #define LAUNCH_BE(T, N) block_end_bwd_kernel<T, N><<<g, EW_THREADS, 0, st>>>((int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const T*)dz, (const T*)dzp, (const T*)z, (const T*)y, (const T*)yres, (T*)G, partial)
   if (dtype == FFPN_F32) { if (yres) LAUNCH_BE(float, 3); else LAUNCH_BE(float, 2); }
   else { if (yres) LAUNCH_BE(bf16, 3); else LAUNCH_BE(bf16, 2); }

@@ -1,12 +1,837 @@
-// tcgen05 / TMEM implicit-GEMM convolution (placeholder until the kernels land: reports "unsupported" so the
-// dispatcher uses the CUDA-core kernels).
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (forward and, through flipped/transposed packed
+// weights, dgrad) for every stride-1 kernel shape on the path.
+//
+// Formulation.  The conv is canonicalised to (slices D with kD taps) x (inner plane Y x X with kY x kX taps,
+// X contiguous).  Positions of the zero-padded inner plane are flattened, i = y*Xp + x, so that for an output
+// row m the input row of tap (dd,dy,dx) is simply m + dd*Lr + dy*Xp + dx: every tap's A operand is the SAME
+// shared-memory tile viewed through a shifted UMMA descriptor start address.  The tile is staged once per
+// K-group by all threads with 16-byte global loads; the producer's BatchNorm scale/shift (+ReLU) and the zero
+// padding are applied in registers on the way in, so the normalised tensor never exists in HBM.  A (and B)
+// use the canonical K-major, no-swizzle UMMA layout: 8-channel (16-byte) chunks in planes, rows 16 bytes apart
+// (SBO = 128 B, LBO = plane stride), which is what makes arbitrary row shifts legal.  Weights are packed per
+// call to bf16 in exactly the smem image ([kgroup][tap][kchunk][cout][8]) and fetched with one
+// cp.async.bulk (UBLKCP) per K-group, completion on an mbarrier.  One elected thread issues
+// tcgen05.mma.cta_group::1.kind::f16 (M=128, N=Cout, K=16) into TMEM accumulators (one 128-row block per
+// column group); tcgen05.commit signals an mbarrier; 8 warps read the accumulators back with tcgen05.ld,
+// round, store channels-last rows and reduce the BatchNorm partial sums.  Two CTAs per SM overlap one CTA's
+// staging/epilogue with the other's MMAs.
 #include "common.cuh"
 
-bool ffpn_tc_fwd_supported(const ffpn_conv_desc*) { return false; }
-bool ffpn_tc_dgrad_supported(const ffpn_conv_desc*) { return false; }
-bool ffpn_tc_wgrad_supported(const ffpn_conv_desc*) { return false; }
-size_t ffpn_tc_workspace_bytes(const ffpn_conv_desc*) { return 0; }
-int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc*, bool, const void*, const float*, const float*, int, const float*,
-                     const void*, void*, float*, int*, void*, size_t, cudaStream_t) { FFPN_FAIL(ctx, "tcgen05 conv not built"); }
-int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc*, const void*, const float*, const float*, int, const void*,
-                       float*, void*, size_t, cudaStream_t) { FFPN_FAIL(ctx, "tcgen05 wgrad not built"); }
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int SCR_STRIDE = 17;                       // per-warp 32x16 transpose scratch, padded
+
+struct TcParams {
+  // canonical geometry (stride-1 convolution)
+  int NB, D, Y, X, oD, oY, oX;
+  int kD, kY, kX, pD, pY, pX;
+  long long inNB, inD, inY, outNB, outD, outY;       // position strides (X stride is 1)
+  int Cin, Cout, Npad;
+  int Xp, tD, L, Lr, nD, nI, Qout;
+  int KG, nkg, colstride, tmem_cols;
+  int rows_alloc, region_rows;
+  int relu, has_aff, has_stats, has_add;
+  unsigned a_bytes, b_bytes;                         // per K-group smem bytes
+  const bf16* x;
+  const float* sc;
+  const float* sh;
+  const bf16* wp;                                    // packed weights
+  const bf16* addend;
+  bf16* y;
+  float* stat;                                       // [gridDim.x][2][Cout]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) lbo[16,30) sbo[32,46) version=1 at
+  // [46,48), base_offset 0, layout_type[61,64) = SWIZZLE_NONE (0).  All in 16-byte units.
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int N_ISSUE = 4;          // warps whose lane 0 issues tcgen05.mma (different accumulator blocks each)
+constexpr int HDR_TAPS = 32;        // byte offset of the tap-offset table in the smem header
+constexpr int HDR_STATS = 160;      // byte offset of the per-CTA statistics accumulators
+
+__device__ __forceinline__ uint4 bn_relu_bf16x8(uint4 v, const float (&s)[8], const float (&h)[8], int relu) {
+  uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    float f0 = fmaf(__uint_as_float(u[q] << 16), s[2 * q], h[2 * q]);
+    float f1 = fmaf(__uint_as_float(u[q] & 0xffff0000u), s[2 * q + 1], h[2 * q + 1]);
+    if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+    __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
+    u[q] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  return make_uint4(u[0], u[1], u[2], u[3]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // header: [0] weights barrier, [8] mma barrier, [16] tmem base, [32] tap offsets, [160..] stats (2*Npad floats)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+  int* tapoff_s = reinterpret_cast<int*>(smem + HDR_TAPS);
+  float* stat_s = reinterpret_cast<float*>(smem + HDR_STATS);
+  const uint32_t hdr = (HDR_STATS + 2 * p.Npad * 4 + 127) & ~127u;
+  float* scr = reinterpret_cast<float*>(smem + hdr);                            // [8 warps][32][SCR_STRIDE]
+  const uint32_t a_off = hdr + 8 * 32 * SCR_STRIDE * 4;
+  uint8_t* a_s = smem + a_off;
+  uint8_t* b_s = a_s + p.a_bytes;
+  const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntaps = p.kD * p.kY * p.kX;
+  const int nkc = p.KG >> 3;
+  const uint32_t plane = (uint32_t)p.rows_alloc * 16u;
+  const int n0 = blockIdx.y * p.Npad;                 // first output channel of this CTA's N-chunk
+  const bf16* wp = p.wp + (size_t)blockIdx.y * p.nkg * (p.b_bytes / 2);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, N_ISSUE);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < ntaps) {
+    const int dx = tid % p.kX, dy = (tid / p.kX) % p.kY, dd = tid / (p.kX * p.kY);
+    tapoff_s[tid] = dd * p.Lr + dy * p.Xp + dx;
+  }
+  for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) stat_s[i] = 0.f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // instruction descriptor: D=f32, A=B=bf16, K-major both, N=Npad, M=128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | (8u << 24);
+  const uint64_t a_desc0 = make_desc(smem_u32(a_s), plane, 128u);
+  const uint64_t b_desc0 = make_desc(smem_u32(b_s), (uint32_t)p.Npad * 16u, 128u);
+
+  // staging role of this thread: one 8-channel chunk, rows r0, r0 + RP, ...
+  const int kc = tid % nkc;
+  const int RP = TC_THREADS / nkc;
+
+  uint32_t n_commit = 0, n_wload = 0;   // completed phases of bar_m / bar_w (uniform across the CTA)
+  const int ntiles = p.NB * p.nD * p.nI;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int it = t % p.nI; t /= p.nI;
+    const int dt = t % p.nD;
+    const int nb = t / p.nD;
+    const int d0 = dt * p.tD, i0 = it * p.L;
+    const int tD_t = min(p.tD, p.oD - d0);
+    const int L_t = min(p.L, p.Qout - i0);
+    const int M_t = (tD_t - 1) * p.Lr + L_t;
+    const int nmb = (M_t + 127) >> 7;
+    const bf16* xb = p.x + (long long)nb * p.inNB * p.Cin;
+
+    for (int kg = 0; kg < p.nkg; kg++) {
+      if (kg > 0) {
+        mbar_wait(bar_m, (n_commit - 1) & 1);     // previous group's MMAs have consumed A and B
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const bool load_w = (p.nkg > 1) || (n_wload == 0);    // resident weights are fetched once per CTA
+      if (load_w && tid == 0) {
+        mbar_expect_tx(bar_w, p.b_bytes);
+        bulk_g2s(smem_u32(b_s), reinterpret_cast<const uint8_t*>(wp) + (size_t)kg * p.b_bytes, p.b_bytes, bar_w);
+      }
+      // ---- stage A: region rows x KG channels; BN scale/shift + ReLU + zero padding applied in registers.
+      //      Row coordinates advance incrementally (no per-element division); loads are issued 4 deep. ----
+      const int cofs = kg * p.KG + kc * 8;
+      float s[8], h[8];
+      if (p.has_aff) {
+        const float4 s0 = *reinterpret_cast<const float4*>(p.sc + cofs), s1 = *reinterpret_cast<const float4*>(p.sc + cofs + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(p.sh + cofs), h1 = *reinterpret_cast<const float4*>(p.sh + cofs + 4);
+        s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+      }
+      int r = tid / nkc;
+      int j = r / p.Lr, ii = r - j * p.Lr;
+      int yp = (i0 + ii) / p.Xp, xp = (i0 + ii) - yp * p.Xp;
+      uint8_t* a_dst = a_s + (size_t)kc * plane;
+      while (r < p.region_rows) {
+        uint4 v[4];
+        int rr[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          rr[u] = r;
+          const int d = d0 + j - p.pD, yy = yp - p.pY, xx = xp - p.pX;
+          ok[u] = (r < p.region_rows) && d >= 0 && d < p.D && yy >= 0 && yy < p.Y && xx >= 0 && xx < p.X;
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok[u]) {
+            const long long pos = (long long)d * p.inD + (long long)yy * p.inY + xx;
+            v[u] = *reinterpret_cast<const uint4*>(xb + pos * p.Cin + cofs);
+          }
+          // advance to the next row of this thread
+          r += RP; ii += RP; xp += RP;
+          if (ii >= p.Lr) {
+            while (ii >= p.Lr) { ii -= p.Lr; j++; }
+            yp = (i0 + ii) / p.Xp; xp = (i0 + ii) - yp * p.Xp;
+          } else {
+            while (xp >= p.Xp) { xp -= p.Xp; yp++; }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (rr[u] < p.region_rows) {
+            if (p.has_aff && ok[u]) v[u] = bn_relu_bf16x8(v[u], s, h, p.relu);
+            *reinterpret_cast<uint4*>(a_dst + (size_t)rr[u] * 16) = v[u];
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to UMMA
+      __syncthreads();
+      // ---- MMA issue: lane 0 of warps 0..3, each for its own accumulator blocks ----
+      if (warp < N_ISSUE && lane == 0) {
+        if (load_w) mbar_wait(bar_w, n_wload & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t kstep_a = 2u * (plane >> 4), kstep_b = 2u * (uint32_t)p.Npad;
+        for (int mb = warp; mb < nmb; mb += N_ISSUE) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(mb * p.colstride);
+          uint32_t acc = kg != 0 ? 1u : 0u;
+          for (int tap = 0; tap < ntaps; tap++) {
+            uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mb * 128 + tapoff_s[tap]);
+            uint64_t bd = b_desc0 + (uint64_t)(uint32_t)(tap * nkc * p.Npad);
+            for (int ks = 0; ks < nkc / 2; ks++) {
+              umma_bf16(d_tmem, ad, bd, idesc, acc);
+              acc = 1u;
+              ad += kstep_a;
+              bd += kstep_b;
+            }
+          }
+        }
+        umma_commit(bar_m);
+      }
+      n_commit++;
+      if (load_w) n_wload++;
+    }
+    // ---- epilogue: TMEM -> registers -> global (+ BatchNorm partial sums) ----
+    mbar_wait(bar_m, (n_commit - 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* myscr = scr + warp * 32 * SCR_STRIDE;
+    const int nchunks = p.Npad >> 4;
+    for (int mb = warp >> 2; mb < nmb; mb += 2) {
+      const int m = mb * 128 + (warp & 3) * 32 + lane;
+      const int j = m / p.Lr, ii = m - j * p.Lr;
+      const int i = i0 + ii;
+      const int oy = i / p.Xp, ox = i - oy * p.Xp;
+      const bool valid = (m < M_t) && (j < tD_t) && (ii < L_t) && (oy < p.oY) && (ox < p.oX);
+      const long long opos = (long long)nb * p.outNB + (long long)(d0 + j) * p.outD + (long long)oy * p.outY + ox;
+      for (int ch = 0; ch < nchunks; ch++) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mb * p.colstride + ch * 16), raw);
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[q]);
+        const int cbase = n0 + ch * 16;                 // global output channel of this 16-wide chunk
+        if (p.has_add && valid) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.addend + opos * p.Cout + cbase);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; h2++) {
+            if (cbase + h2 * 8 < p.Cout) {
+              const uint4 a4 = ap[h2];
+              const uint32_t u[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                v[h2 * 8 + 2 * q] += __uint_as_float(u[q] << 16);
+                v[h2 * 8 + 2 * q + 1] += __uint_as_float(u[q] & 0xffff0000u);
+              }
+            }
+          }
+        }
+        uint32_t packed[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+          packed[q] = *reinterpret_cast<uint32_t*>(&hh);
+          v[2 * q] = __uint_as_float(packed[q] << 16);           // statistics of the stored (rounded) values
+          v[2 * q + 1] = __uint_as_float(packed[q] & 0xffff0000u);
+        }
+        if (valid) {
+          uint4* yp = reinterpret_cast<uint4*>(p.y + opos * p.Cout + cbase);
+          if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if (cbase + 8 < p.Cout) yp[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+        if (p.has_stats) {
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 16; q++) myscr[lane * SCR_STRIDE + q] = valid ? v[q] : 0.f;
+          __syncwarp();
+          const int c = lane & 15, half = lane >> 4;
+          float sm = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 16; rr++) {
+            const float f = myscr[(half * 16 + rr) * SCR_STRIDE + c];
+            sm += f;
+            s2 = fmaf(f, f, s2);
+          }
+          sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (lane < 16) {
+            atomicAdd(&stat_s[ch * 16 + c], sm);
+            atomicAdd(&stat_s[p.Npad + ch * 16 + c], s2);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();     // TMEM drained and A free before the next tile is staged
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }  // tile loop
+  if (p.has_stats) {
+    for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) {
+      const int which = i / p.Npad, c = i - which * p.Npad;
+      if (n0 + c < p.Cout) p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = stat_s[which * p.Npad + c];
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+// Pack fp32 master weights [Cout][Cin][taps] to the bf16 smem image [nchunk][kg][tap][kc][n (Npad)][8].
+// transposed: the operator applied is the dgrad conv: n <-> ci, k <-> co, taps flipped.
+__global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ntaps,
+                                    int Kc, int Nc, int Npad, int KG, int nchunks, int transposed) {
+  // Kc = reduction channels of the packed operator, Nc = its output channels, Npad = channels per N-chunk
+  const int nkc = KG >> 3;
+  const int nkg = Kc / KG;
+  const int64_t total = (int64_t)nchunks * nkg * ntaps * nkc * Npad * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int e = (int)(r % 8); r /= 8;
+    int n = (int)(r % Npad); r /= Npad;
+    const int kc = (int)(r % nkc); r /= nkc;
+    const int tap = (int)(r % ntaps); r /= ntaps;
+    const int kg = (int)(r % nkg);
+    n += (int)(r / nkg) * Npad;
+    const int k = kg * KG + kc * 8 + e;
+    float v = 0.f;
+    if (n < Nc) {
+      if (!transposed) v = w[((int64_t)n * Cin + k) * ntaps + tap];
+      else v = w[((int64_t)k * Cin + n) * ntaps + (ntaps - 1 - tap)];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+struct Plan {
+  TcParams p;
+  size_t smem;
+  int grid;
+  int nchunks;
+  bool ok;
+};
+
+Plan make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
+  Plan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.ok = false;
+  TcParams& p = pl.p;
+  if (d->dtype != FFPN_BF16) return pl;
+  if (d->sS != 1 || d->sW != 1 || d->sH != 1) return pl;
+  // logical conv as seen by the kernel (dgrad: roles swapped, pads k-1-p)
+  int64_t S = transposed ? d->oS : d->S, W = transposed ? d->oW : d->W, H = transposed ? d->oH : d->H;
+  int64_t oS = transposed ? d->S : d->oS, oW = transposed ? d->W : d->oW, oH = transposed ? d->H : d->oH;
+  int pS = transposed ? d->kS - 1 - d->pS : d->pS, pW = transposed ? d->kW - 1 - d->pW : d->pW,
+      pH = transposed ? d->kH - 1 - d->pH : d->pH;
+  const int Cin = transposed ? d->Cout : d->Cin, Cout = transposed ? d->Cin : d->Cout;
+  if (Cin % 16 != 0 || Cout % 8 != 0 || Cin < 16) return pl;
+  const int64_t B = d->B;
+  int kS = d->kS, kW = d->kW, kH = d->kH;
+  if (H == 1 && oH == 1 && kH == 1 && (kW > 1)) {
+    // en-face / 2-D maps: (S, W) becomes the inner plane
+    p.NB = 1; p.D = (int)B; p.kD = 1; p.pD = 0; p.oD = (int)B;
+    p.Y = (int)S; p.kY = kS; p.pY = pS; p.oY = (int)oS;
+    p.X = (int)W; p.kX = kW; p.pX = pW; p.oX = (int)oW;
+    p.inD = S * W; p.inY = W; p.inNB = 0;
+    p.outD = oS * oW; p.outY = oW; p.outNB = 0;
+  } else if (kW == 1 && kH == 1) {
+    if (kS == 1) {                                    // 1x1x1: a plain GEMM over all positions
+      p.NB = 1; p.D = 1; p.kD = 1; p.pD = 0; p.oD = 1;
+      p.Y = 1; p.kY = 1; p.pY = 0; p.oY = 1;
+      const int64_t P = B * S * W * H;
+      if (P >= (1ll << 31)) return pl;
+      p.X = (int)P; p.kX = 1; p.pX = 0; p.oX = (int)P;
+      p.inD = p.inY = p.inNB = p.outD = p.outY = p.outNB = 0;
+    } else {                                          // taps across slices only
+      p.NB = (int)B; p.D = (int)S; p.kD = kS; p.pD = pS; p.oD = (int)oS;
+      p.Y = 1; p.kY = 1; p.pY = 0; p.oY = 1;
+      p.X = (int)(W * H); p.kX = 1; p.pX = 0; p.oX = (int)(W * H);
+      p.inNB = S * W * H; p.inD = W * H; p.inY = 0;
+      p.outNB = oS * W * H; p.outD = W * H; p.outY = 0;
+    }
+  } else if (kS == 1) {                               // taps inside the (W, H) plane
+    p.NB = 1; p.D = (int)(B * S); p.kD = 1; p.pD = 0; p.oD = (int)(B * S);
+    p.Y = (int)W; p.kY = kW; p.pY = pW; p.oY = (int)oW;
+    p.X = (int)H; p.kX = kH; p.pX = pH; p.oX = (int)oH;
+    p.inD = W * H; p.inY = H; p.inNB = 0;
+    p.outD = oW * oH; p.outY = oH; p.outNB = 0;
+  } else {
+    return pl;
+  }
+  p.Cin = Cin; p.Cout = Cout;
+  {                                                   // N-chunks of at most 256 output channels (blockIdx.y)
+    const int npad = (Cout + 15) & ~15;
+    pl.nchunks = (npad + 255) / 256;
+    p.Npad = (((npad + pl.nchunks - 1) / pl.nchunks) + 15) & ~15;
+  }
+  p.Xp = p.X + 2 * p.pX;
+  p.Qout = (p.oY - 1) * p.Xp + p.oX;
+  const int ntaps = p.kD * p.kY * p.kX;
+  const int maxinner = (p.kY - 1) * p.Xp + (p.kX - 1);
+  p.colstride = p.Npad < 32 ? 32 : p.Npad;
+  // K-group: largest of Cin(<=64)/64/32/16 whose weight image fits 72 KB
+  int KG = 64;
+  while (KG > 16 && (Cin % KG != 0 || (size_t)ntaps * KG * p.Npad * 2 > 72 * 1024)) KG >>= 1;
+  if (Cin % KG != 0) return pl;
+  if ((size_t)ntaps * KG * p.Npad * 2 > 200 * 1024) return pl;
+  p.KG = KG; p.nkg = Cin / KG;
+  p.b_bytes = (unsigned)((size_t)ntaps * KG * p.Npad * 2);
+  const uint32_t hdr = (HDR_STATS + 2 * p.Npad * 4 + 127) & ~127u;
+  const size_t fixed = hdr + 8 * 32 * SCR_STRIDE * 4 + p.b_bytes;
+  // Tile size: bounded by the TMEM columns and shared memory of the target occupancy.  Several CTAs per SM is
+  // what overlaps one CTA's staging / epilogue with another's MMAs, so small-N layers aim for 4 CTAs per SM.
+  if (ntaps > 27) return pl;
+  const int budgets[3][2] = {{4, 128}, {2, 256}, {1, 512}};
+  for (int bi = 0; bi < 3; bi++) {
+    const int per_sm = budgets[bi][0];
+    int nmb_max = budgets[bi][1] / p.colstride;
+    if (nmb_max > 8) nmb_max = 8;
+    if (nmb_max < (bi == 0 ? 4 : (bi == 1 ? 2 : 1))) continue;
+    const size_t smem_cap = (size_t)(227 * 1024) / per_sm - 1024;
+    for (; nmb_max >= (bi == 2 ? 1 : 2); nmb_max--) {
+      const int max_rows = nmb_max * 128;
+      int tD, L, Lr;
+      if (p.kD > 1) {
+        L = p.X < 128 ? p.X : 128; Lr = L;
+        tD = max_rows / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+      } else if (p.Qout >= max_rows) {
+        const int nt = (p.Qout + max_rows - 1) / max_rows;
+        L = (((p.Qout + nt - 1) / nt) + 127) & ~127; if (L > max_rows) L = max_rows;
+        Lr = L + maxinner; tD = 1;
+      } else {
+        L = p.Qout; Lr = L + maxinner;
+        tD = (max_rows - L) / Lr + 1; if (tD > p.oD) tD = p.oD;
+      }
+      const int M_total = (tD - 1) * Lr + L;
+      const int nmb = (M_total + 127) / 128;
+      const int maxoff = (p.kD - 1) * Lr + maxinner;
+      int rows_alloc = nmb * 128 + maxoff;
+      const int region = (tD + p.kD - 1) * Lr;
+      if (rows_alloc < region) rows_alloc = region;
+      const size_t a_bytes = (size_t)rows_alloc * KG * 2;
+      const size_t smem = fixed + a_bytes;
+      if (smem > smem_cap) continue;
+      p.tD = tD; p.L = L; p.Lr = Lr;
+      p.rows_alloc = rows_alloc; p.region_rows = region;
+      p.a_bytes = (unsigned)a_bytes;
+      int cols = nmb * p.colstride, tc = 32;
+      while (tc < cols) tc <<= 1;
+      p.tmem_cols = tc;
+      p.nD = (p.oD + tD - 1) / tD;
+      p.nI = (p.Qout + L - 1) / L;
+      pl.smem = smem;
+      const int ntiles = p.NB * p.nD * p.nI;
+      pl.grid = ntiles < per_sm * num_sms ? ntiles : per_sm * num_sms;
+      pl.ok = ((uint64_t)rows_alloc * 16 < (1u << 18)) && tc <= 512;
+      return pl;
+    }
+  }
+  return pl;
+}
+
+
+// =====================================================================================================
+// wgrad on tcgen05:  dW[tap][ci][co] = sum_rows  f(x)[row + off(tap)][ci] * dy[row][co]
+// Both operands are staged in the same planar layout as the forward A tile ([8-channel chunk][row][16 B]) but are
+// read as MN-major operands (positions = K): A = x planes (M = channel chunks at SBO = plane stride, 8-row
+// K groups at LBO = 128 B), shifted by the tap's row offset; B = dy planes.  For narrow layers the kX row
+// shifts are materialised as extra planes so that one MMA (M = 128 lanes = (shift, channel)) serves kX taps.
+// Accumulators stay in TMEM across ALL tiles of a CTA (no per-tile epilogue); smem is double buffered so the
+// staging of tile i+1 overlaps the MMAs of tile i; the final TMEM tile is atomically added into fp32 dW.
+struct WgParams {
+  int NB, D, Y, X, oD, oY, oX, kD, kY, kX, pD, pY, pX;
+  long long inNB, inD, inY, outNB, outD, outY;
+  int Cin, Cout, Xp, Qout, tD, L, Lr, nD, nI;
+  int ci_t, co_t, nci, nco, nkcx, nkcy;
+  int nshift, ngroups, ntaps;
+  int goff[27];
+  int Kpad, rows_x, colstride, tmem_cols;
+  unsigned xbuf_bytes, ybuf_bytes;
+  int relu, has_aff;
+  const bf16* x;
+  const bf16* dy;
+  const float* sc;
+  const float* sh;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);          // [0], [8]: one per smem buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+  uint8_t* xs[2] = {smem + 128, smem + 128 + p.xbuf_bytes};
+  uint8_t* ys[2] = {smem + 128 + 2 * (size_t)p.xbuf_bytes, smem + 128 + 2 * (size_t)p.xbuf_bytes + p.ybuf_bytes};
+  const uint32_t bar[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t plane_x = (uint32_t)p.rows_x * 16u, plane_y = (uint32_t)p.Kpad * 16u;
+  const int cit = blockIdx.y % p.nci, cot = blockIdx.y / p.nci;
+  const int ci0 = cit * p.ci_t, co0 = cot * p.co_t;
+
+  if (tid == 0) {
+    mbar_init(bar[0], N_ISSUE);
+    mbar_init(bar[1], N_ISSUE);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  // D=f32, A=B=bf16, both MN-major (bits 15,16), N = co_t, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.co_t >> 3) << 17) | (8u << 24);
+
+  const int kcx = tid % p.nkcx, RPX = TC_THREADS / p.nkcx;
+  const int kcy = tid % p.nkcy, RPY = TC_THREADS / p.nkcy;
+  float s[8], h[8];
+  if (p.has_aff) {
+    const int cofs = ci0 + kcx * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { s[q] = p.sc[cofs + q]; h[q] = p.sh[cofs + q]; }
+  }
+  const int xrows_needed = p.rows_x + p.nshift - 1;
+  const int region_rows = (p.tD + p.kD - 1) * p.Lr;
+
+  uint32_t n = 0;
+  const int ntiles = p.NB * p.nD * p.nI;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n++) {
+    const int buf = n & 1;
+    if (n >= 2) {
+      mbar_wait(bar[buf], ((n >> 1) - 1) & 1);       // MMAs that read this buffer two tiles ago are done
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    int t = tile;
+    const int it = t % p.nI; t /= p.nI;
+    const int dt = t % p.nD;
+    const int nb = t / p.nD;
+    const int d0 = dt * p.tD, i0 = it * p.L;
+    const int tD_t = min(p.tD, p.oD - d0);
+    const int L_t = min(p.L, p.Qout - i0);
+    const int M_t = (tD_t - 1) * p.Lr + L_t;
+    // ---- stage x (with the producer's BN+ReLU, zero padding), kX shifted copies when materialised ----
+    {
+      const bf16* xb = p.x + (long long)nb * p.inNB * p.Cin + ci0 + kcx * 8;
+      int r = tid / p.nkcx;
+      int j = r / p.Lr, ii = r - j * p.Lr;
+      int yp = (i0 + ii) / p.Xp, xp = (i0 + ii) - yp * p.Xp;
+      while (r < xrows_needed) {
+        uint4 v[4];
+        int rr[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          rr[u] = r;
+          const int d = d0 + j - p.pD, yy = yp - p.pY, xx = xp - p.pX;
+          ok[u] = (r < region_rows) && d >= 0 && d < p.D && yy >= 0 && yy < p.Y && xx >= 0 && xx < p.X;
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok[u]) v[u] = *reinterpret_cast<const uint4*>(xb + ((long long)d * p.inD + (long long)yy * p.inY + xx) * p.Cin);
+          r += RPX; ii += RPX; xp += RPX;
+          if (ii >= p.Lr) {
+            while (ii >= p.Lr) { ii -= p.Lr; j++; }
+            yp = (i0 + ii) / p.Xp; xp = (i0 + ii) - yp * p.Xp;
+          } else {
+            while (xp >= p.Xp) { xp -= p.Xp; yp++; }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (rr[u] < xrows_needed) {
+            if (p.has_aff && ok[u]) v[u] = bn_relu_bf16x8(v[u], s, h, p.relu);
+            for (int sft = 0; sft < p.nshift; sft++) {
+              const int rd = rr[u] - sft;
+              if (rd >= 0 && rd < p.rows_x)
+                *reinterpret_cast<uint4*>(xs[buf] + (size_t)(sft * p.nkcx + kcx) * plane_x + (size_t)rd * 16) = v[u];
+            }
+          }
+        }
+      }
+    }
+    // ---- stage dy rows (same padded-flat row space as the forward output rows; garbage rows are zero) ----
+    {
+      const bf16* yb = p.dy + co0 + kcy * 8;
+      for (int m = tid / p.nkcy; m < p.Kpad; m += RPY) {
+        const int j = m / p.Lr, ii = m - j * p.Lr;
+        const int i = i0 + ii;
+        const int oy = i / p.Xp, ox = i - oy * p.Xp;
+        const bool valid = (m < M_t) && (j < tD_t) && (ii < L_t) && (oy < p.oY) && (ox < p.oX);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          const long long opos = (long long)nb * p.outNB + (long long)(d0 + j) * p.outD + (long long)oy * p.outY + ox;
+          v = *reinterpret_cast<const uint4*>(yb + opos * p.Cout);
+        }
+        *reinterpret_cast<uint4*>(ys[buf] + (size_t)kcy * plane_y + (size_t)m * 16) = v;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp < N_ISSUE && lane == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // MN-major, no swizzle: SBO = stride between 8-channel chunks (plane), LBO = stride between 8-row K groups
+      const uint64_t a0 = make_desc(smem_u32(xs[buf]), 128u, plane_x);
+      const uint64_t b0 = make_desc(smem_u32(ys[buf]), 128u, plane_y);
+      const int ksteps = p.Kpad >> 4;
+      for (int g = warp; g < p.ngroups; g += N_ISSUE) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.colstride);
+        uint64_t ad = a0 + (uint64_t)(uint32_t)p.goff[g];
+        uint64_t bd = b0;
+        uint32_t acc = n != 0 ? 1u : 0u;
+        for (int ks = 0; ks < ksteps; ks++) {
+          umma_bf16(d_tmem, ad, bd, idesc, acc);
+          acc = 1u;
+          ad += 16; bd += 16;                          // 16 rows = 256 bytes = 16 descriptor units
+        }
+      }
+      umma_commit(bar[buf]);
+    }
+  }
+  // ---- drain: wait for the last MMAs on both buffers, then TMEM -> atomicAdd into dW ----
+  if (n >= 1) { const uint32_t uses = (n + 1) >> 1; mbar_wait(bar[0], (uses - 1) & 1); }
+  if (n >= 2) { const uint32_t uses = n >> 1; mbar_wait(bar[1], (uses - 1) & 1); }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (n >= 1) {
+    const int L128 = (warp & 3) * 32 + lane;           // TMEM lane = (shift, chunk, channel-in-chunk)
+    const int q = L128 >> 3, e = L128 & 7;
+    const int sft = q / p.nkcx, c = q - sft * p.nkcx;
+    const bool lane_ok = q < p.nshift * p.nkcx;
+    const int ci = ci0 + c * 8 + e;
+    const int nch = p.co_t >> 4;
+    for (int w = warp >> 2; w < p.ngroups * nch; w += 2) {
+      const int g = w / nch, ch = w - g * nch;
+      uint32_t raw[16];
+      tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * p.colstride + ch * 16), raw);
+      if (lane_ok && ci < p.Cin) {
+        const int tap = g * p.nshift + sft;
+        if (tap < p.ntaps) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const int co = co0 + ch * 16 + k;
+            if (co < p.Cout) atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.ntaps + tap, __uint_as_float(raw[k]));
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+struct WgPlan {
+  WgParams p;
+  size_t smem;
+  dim3 grid;
+  bool ok;
+};
+
+WgPlan make_wgrad_plan(const ffpn_conv_desc* d, int num_sms) {
+  WgPlan w;
+  memset(&w, 0, sizeof(w));
+  Plan f = make_plan(d, false, num_sms);          // canonical geometry (also validates dtype / stride / channels)
+  if (!f.ok || d->Cout % 16 != 0) return w;
+  WgParams& p = w.p;
+  const TcParams& c = f.p;
+  p.NB = c.NB; p.D = c.D; p.Y = c.Y; p.X = c.X; p.oD = c.oD; p.oY = c.oY; p.oX = c.oX;
+  p.kD = c.kD; p.kY = c.kY; p.kX = c.kX; p.pD = c.pD; p.pY = c.pY; p.pX = c.pX;
+  p.inNB = c.inNB; p.inD = c.inD; p.inY = c.inY; p.outNB = c.outNB; p.outD = c.outD; p.outY = c.outY;
+  p.Cin = d->Cin; p.Cout = d->Cout; p.Xp = c.Xp; p.Qout = c.Qout;
+  p.ntaps = p.kD * p.kY * p.kX;
+  if (p.ntaps > 27) return w;
+  p.ci_t = p.Cin < 128 ? p.Cin : 128;
+  if (p.Cin % p.ci_t != 0) return w;
+  p.nci = p.Cin / p.ci_t;
+  p.nkcx = p.ci_t / 8;
+  // materialise the kX row shifts as extra planes when they fit the 16 chunks of an M=128 operand
+  p.nshift = (p.kX > 1 && p.nkcx * p.kX <= 16) ? p.kX : 1;
+  const int ngroups = p.ntaps / p.nshift;
+  p.ngroups = ngroups;
+  const int maxinner = (p.kY - 1) * p.Xp + (p.kX - 1);
+  // output-channel tile: accumulators of all groups must fit 512 TMEM columns
+  int co_t = 256;
+  while (co_t > 16 && (co_t > p.Cout || ngroups * (co_t < 32 ? 32 : co_t) > 512 || p.Cout % co_t != 0)) co_t >>= 1;
+  if (p.Cout % co_t != 0 || ngroups * (co_t < 32 ? 32 : co_t) > 512) return w;
+  p.co_t = co_t; p.nco = p.Cout / co_t; p.nkcy = co_t / 8;
+  p.colstride = co_t < 32 ? 32 : co_t;
+  int tc = 32;
+  while (tc < ngroups * p.colstride) tc <<= 1;
+  p.tmem_cols = tc;
+  for (int Lmax = 512; Lmax >= 128; Lmax -= 128) {
+    int tD, L, Lr;
+    if (p.kD > 1) {
+      L = p.X < 128 ? p.X : 128; Lr = L;
+      tD = Lmax / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+    } else if (p.Qout >= Lmax) {
+      const int nt = (p.Qout + Lmax - 1) / Lmax;
+      L = (((p.Qout + nt - 1) / nt) + 127) & ~127; if (L > Lmax) L = Lmax;
+      Lr = L + maxinner; tD = 1;
+    } else {
+      L = p.Qout; Lr = L + maxinner;
+      tD = (Lmax - L) / Lr + 1; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+    }
+    const int M_total = (tD - 1) * Lr + L;
+    const int Kpad = (M_total + 15) & ~15;
+    int maxg = 0;
+    for (int g = 0; g < ngroups; g++) {
+      const int tap = g * p.nshift;                       // first tap of the group (dx = 0 when materialised)
+      const int dx = tap % p.kX, dy = (tap / p.kX) % p.kY, dd = tap / (p.kX * p.kY);
+      p.goff[g] = dd * Lr + dy * p.Xp + dx;
+      if (p.goff[g] > maxg) maxg = p.goff[g];
+    }
+    const int rows_x = Kpad + maxg;
+    const size_t xbuf = (size_t)p.nshift * p.nkcx * rows_x * 16, ybuf = (size_t)p.nkcy * Kpad * 16;
+    size_t smem = 128 + 2 * xbuf + 2 * ybuf;
+    // an M=128 operand always reads 16 chunk planes: keep the (ignored) extra ones inside the allocation
+    const size_t reach = 128 + xbuf + (size_t)16 * rows_x * 16;
+    if (reach > smem) smem = reach;
+    if (smem > 224 * 1024 || (uint64_t)rows_x * 16 >= (1u << 18)) continue;
+    p.tD = tD; p.L = L; p.Lr = Lr; p.Kpad = Kpad; p.rows_x = rows_x;
+    p.xbuf_bytes = (unsigned)xbuf; p.ybuf_bytes = (unsigned)ybuf;
+    p.nD = (p.oD + tD - 1) / tD;
+    p.nI = (p.Qout + L - 1) / L;
+    const int ntiles = p.NB * p.nD * p.nI;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 512 / tc) per_sm = 512 / tc;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    int gx = per_sm * num_sms / (p.nci * p.nco);
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    w.grid = dim3(gx, p.nci * p.nco);
+    w.smem = smem;
+    w.ok = true;
+    return w;
+  }
+  return w;
+}
+
+}  // namespace
+
+bool ffpn_tc_wgrad_supported(const ffpn_conv_desc* d) { return make_wgrad_plan(d, 148).ok; }
+
+int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale, const float* in_shift,
+                       int in_relu, const void* dy, float* dw, void*, size_t, cudaStream_t st) {
+  WgPlan w = make_wgrad_plan(d, ctx->num_sms);
+  if (!w.ok) FFPN_FAIL(ctx, "conv_wgrad_tc: geometry not supported");
+  WgParams& p = w.p;
+  p.x = (const bf16*)x; p.dy = (const bf16*)dy; p.sc = in_scale; p.sh = in_shift; p.dw = dw;
+  p.relu = in_relu; p.has_aff = in_scale != nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_wgrad_tc_kernel<<<w.grid, TC_THREADS, w.smem, st>>>(p);
+  FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_tc");
+  return 0;
+}
+
+namespace {
+}  // namespace
+
+bool ffpn_tc_fwd_supported(const ffpn_conv_desc* d) { return make_plan(d, false, 148).ok; }
+bool ffpn_tc_dgrad_supported(const ffpn_conv_desc* d) { return make_plan(d, true, 148).ok; }
+
+size_t ffpn_tc_workspace_bytes(const ffpn_conv_desc* d) {
+  const size_t taps = (size_t)d->kS * d->kW * d->kH;
+  const size_t cin = (d->Cin + 63) & ~63, cout = (d->Cout + 63) & ~63;
+  return taps * cin * cout * 2 + 65536;
+}
+
+int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,
+                     const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
+                     int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Plan pl = make_plan(d, transposed, ctx->num_sms);
+  if (!pl.ok) FFPN_FAIL(ctx, "conv_tc: geometry not supported");
+  TcParams& p = pl.p;
+  const int ntaps = p.kD * p.kY * p.kX;
+  const size_t need = (size_t)pl.nchunks * p.nkg * p.b_bytes;
+  if (ws == nullptr || ws_bytes < need) FFPN_FAIL(ctx, "conv_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+  if (stat_partial != nullptr && pl.grid > FFPN_STAT_ROWS) FFPN_FAIL(ctx, "conv_tc: %d tiles exceed the statistics buffer", pl.grid);
+  {
+    const int64_t total = (int64_t)need / 2;
+    const int g = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
+    pack_weights_kernel<<<g, 256, 0, st>>>(w, (bf16*)ws, d->Cout, d->Cin, ntaps, p.Cin, p.Cout, p.Npad, p.KG, pl.nchunks, transposed ? 1 : 0);
+    FFPN_CHECK_LAUNCH(ctx, "pack_weights");
+  }
+  p.x = (const bf16*)x; p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)ws;
+  p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
+  p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_tc_kernel<<<dim3(pl.grid, pl.nchunks), TC_THREADS, pl.smem, st>>>(p);
+  FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_tc" : "conv_fwd_tc");
+  if (stat_rows) *stat_rows = pl.grid;
+  return 0;
+}
+

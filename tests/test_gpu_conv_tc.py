@@ -1,0 +1,101 @@
+"""tcgen05/TMEM implicit-GEMM convolution (csrc/conv_tc.cu) against torch's fp32 convolution on the same
+bf16-rounded inputs, forward (with the fused BN+ReLU prologue and the BatchNorm partial sums) and dgrad
+(with the fused residual addend).  impl=2 forces the tensor-core kernel and errors if it does not apply.
+Tolerance: rel-L2 <= 1e-2 (bf16 operands incl. the re-rounded prologue output, fp32 accumulate)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def phys(x):
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def logical(p):
+    return p.permute(0, 4, 1, 2, 3)
+
+
+CASES = [
+    # name, Cin, Cout, kernel, pad, (B, S, W, H)
+    ('tiny133', 16, 16, (1, 3, 3), (0, 1, 1), (1, 2, 8, 16)),
+    ('l1_133', 16, 16, (1, 3, 3), (0, 1, 1), (2, 3, 128, 128)),
+    ('l2_133_widen', 16, 32, (1, 3, 3), (0, 1, 1), (2, 3, 64, 64)),
+    ('l3_133', 64, 64, (1, 3, 3), (0, 1, 1), (2, 4, 32, 32)),
+    ('l4_133', 128, 128, (1, 3, 3), (0, 1, 1), (2, 4, 16, 16)),
+    ('l5_133', 256, 256, (1, 3, 3), (0, 1, 1), (2, 3, 8, 8)),
+    ('l1_311', 16, 16, (3, 1, 1), (1, 0, 0), (2, 8, 16, 128)),
+    ('l3_311', 64, 64, (3, 1, 1), (1, 0, 0), (2, 12, 32, 32)),
+    ('l5_311', 256, 256, (3, 1, 1), (1, 0, 0), (2, 8, 8, 8)),
+    ('sc_111', 16, 32, (1, 1, 1), (0, 0, 0), (2, 3, 20, 24)),
+    ('sc_111_big', 128, 256, (1, 1, 1), (0, 0, 0), (1, 4, 8, 8)),
+    ('proj_114', 64, 64, (1, 1, 4), (0, 0, 0), (2, 4, 16, 8)),
+    ('proj_114_l5', 256, 256, (1, 1, 4), (0, 0, 0), (2, 4, 8, 8)),
+    ('dec_331', 96, 32, (3, 3, 1), (1, 1, 0), (2, 16, 24, 1)),
+    ('dec_331_up4', 768, 128, (3, 3, 1), (1, 1, 0), (2, 8, 16, 1)),
+    ('dec_111_up4', 768, 128, (1, 1, 1), (0, 0, 0), (2, 8, 16, 1)),
+    ('enc2d_13', 32, 32, (1, 3, 1), (0, 1, 0), (2, 40, 64, 1)),
+    ('enc2d_31', 64, 64, (3, 1, 1), (1, 0, 0), (2, 40, 32, 1)),
+    ('odd_133', 32, 48, (1, 3, 3), (0, 1, 1), (1, 2, 31, 62)),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_conv_tc(case):
+    from ffpn import ops
+    torch.backends.cudnn.allow_tf32 = False
+    name, cin, cout, k, p, (B, S, W, H) = case
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(len(name) * 131 + cin)
+    x = torch.randn(B, cin, S, W, H, generator=g).cuda()
+    w = (torch.randn(cout, cin, *k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5).cuda()
+    sc = (0.5 + torch.rand(cin, generator=g)).cuda()
+    sh = (0.3 * torch.randn(cin, generator=g)).cuda()
+    xq = x.to(dt).float()
+    s1 = (1, 1, 1)
+    old = ops.get_conv_impl()
+    try:
+        for affine in (False, True):
+            xin = torch.relu(xq * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)) if affine else xq
+            ref = F.conv3d(xin, w.to(dt).float(), None, s1, p)
+            ops.set_conv_impl(2)
+            y, partial, rows = ops.conv_fwd(phys(x).to(dt), w, k, s1, p, sc if affine else None, sh if affine else None, affine)
+            torch.cuda.synchronize()
+            yl = logical(y.float())
+            assert yl.shape == ref.shape
+            assert rel(yl, ref) <= 1e-2, ('fwd', affine, rel(yl, ref))
+            st = partial.view(-1, 2, cout)[:rows].double().sum(0)
+            ys = y.float().double().reshape(-1, cout)
+            assert torch.allclose(st[0], ys.sum(0), rtol=1e-3, atol=1e-3 * ys.abs().sum(0).max().item())
+            assert torch.allclose(st[1], (ys * ys).sum(0), rtol=1e-3)
+            ops.set_conv_impl(1)
+            y2, _, _ = ops.conv_fwd(phys(x).to(dt), w, k, s1, p, sc if affine else None, sh if affine else None, affine)
+            assert rel(y.float(), y2.float()) <= 1e-2
+        dy = torch.randn(ref.shape, generator=g).cuda().to(dt)
+        xr = xq.clone().requires_grad_(True)
+        F.conv3d(xr, w.to(dt).float(), None, s1, p).backward(dy.float())
+        add = torch.randn(B, cin, S, W, H, generator=g).cuda().to(dt)
+        ops.set_conv_impl(2)
+        dx = ops.conv_dgrad(phys(dy), w, tuple(phys(x).shape), k, s1, p)
+        dx2 = ops.conv_dgrad(phys(dy), w, tuple(phys(x).shape), k, s1, p, addend=phys(add))
+        torch.cuda.synchronize()
+        assert rel(logical(dx.float()), xr.grad) <= 1e-2, ('dgrad', rel(logical(dx.float()), xr.grad))
+        assert rel(logical(dx2.float()), xr.grad + add.float()) <= 1e-2
+        # wgrad on tensor cores (fused BN+ReLU prologue on x), against torch autograd
+        for affine in (False, True):
+            xin = torch.relu(xq * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)) if affine else xq
+            wr = w.clone().requires_grad_(True)
+            F.conv3d(xin, wr, None, s1, p).backward(dy.float())
+            ops.set_conv_impl(2)
+            dw = ops.conv_wgrad(phys(x).to(dt), phys(dy), w.shape, k, s1, p, sc if affine else None,
+                                sh if affine else None, affine)
+            torch.cuda.synchronize()
+            assert rel(dw, wr.grad) <= 1e-2, ('wgrad', affine, rel(dw, wr.grad))
+    finally:
+        ops.set_conv_impl(old)
