@@ -6,6 +6,10 @@ int ffpn_conv_fwd_simt(ffpn_ctx*, const ffpn_conv_desc*, const void*, const floa
 int ffpn_conv_dgrad_simt(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const void*, void*, cudaStream_t);
 int ffpn_conv_wgrad_simt(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const void*,
                          float*, cudaStream_t);
+// conv_stem.cu
+bool ffpn_stem_supported(const ffpn_conv_desc* d);
+int ffpn_stem_fwd(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, void*, float*, int*, cudaStream_t);
+int ffpn_stem_wgrad(ffpn_ctx*, const ffpn_conv_desc*, const void*, const void*, float*, cudaStream_t);
 // conv_tc.cu
 bool ffpn_tc_fwd_supported(const ffpn_conv_desc* d);
 bool ffpn_tc_dgrad_supported(const ffpn_conv_desc* d);
@@ -63,6 +67,8 @@ extern "C" int ffpn_conv_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void*
   if (check_desc(ctx, d, "conv_fwd")) return 1;
   if ((in_scale == nullptr) != (in_shift == nullptr)) FFPN_FAIL(ctx, "conv_fwd: in_scale/in_shift must both be set or both null");
   if (stat_partial != nullptr && stat_rows == nullptr) FFPN_FAIL(ctx, "conv_fwd: stat_rows is null");
+  if (d->impl == 0 && in_scale == nullptr && ffpn_stem_supported(d))
+    return ffpn_stem_fwd(ctx, d, x, w, y, stat_partial, stat_rows, (cudaStream_t)stream);
   const bool tc_ok = ffpn_tc_fwd_supported(d);
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_fwd: tcgen05 kernel does not support this geometry");
   if (tc_ok && d->impl != 1)
@@ -85,6 +91,8 @@ extern "C" int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const voi
                                void* stream) {
   if (check_desc(ctx, d, "conv_wgrad")) return 1;
   if ((in_scale == nullptr) != (in_shift == nullptr)) FFPN_FAIL(ctx, "conv_wgrad: in_scale/in_shift must both be set or both null");
+  if (d->impl == 0 && in_scale == nullptr && ffpn_stem_supported(d))
+    return ffpn_stem_wgrad(ctx, d, x, dy, dw, (cudaStream_t)stream);
   const bool tc_ok = ffpn_tc_wgrad_supported(d);
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_wgrad: tcgen05 kernel does not support this geometry");
   if (tc_ok && d->impl != 1)

@@ -10,13 +10,24 @@ constexpr int EW_THREADS = 256;
 // ---- finalize: partial sums -> mean / invstd / scale / shift, running stats -------------------------
 // 32 channels per block, 8 row lanes; loads are coalesced across channels and the 8 lane partials are added
 // in a fixed order, so the result is deterministic.
-constexpr int FIN_LANES = 8;
+constexpr int FIN_LANES = 32;
 
 __device__ __forceinline__ void column_sums(const float* __restrict__ partial, int rows, int ncols, int col_a, int col_b,
                                             int C, int c, int rl, double (*red)[32][2], double& sa, double& sb) {
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int r = rl; r < rows; r += FIN_LANES) {
+    int r = rl;
+    for (; r + 3 * FIN_LANES < rows; r += 4 * FIN_LANES) {        // 8 independent loads in flight
+      float va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        va[u] = partial[((int64_t)(r + u * FIN_LANES) * ncols + col_a) * C + c];
+        vb[u] = partial[((int64_t)(r + u * FIN_LANES) * ncols + col_b) * C + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) { a += (double)va[u]; b += (double)vb[u]; }
+    }
+    for (; r < rows; r += FIN_LANES) {
       a += (double)partial[((int64_t)r * ncols + col_a) * C + c];
       b += (double)partial[((int64_t)r * ncols + col_b) * C + c];
     }

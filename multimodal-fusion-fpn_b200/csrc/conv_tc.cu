@@ -29,6 +29,8 @@ struct TcParams {
   long long inNB, inD, inY, outNB, outD, outY;       // position strides (X stride is 1)
   int Cin, Cout, Npad;
   int Xp, tD, L, Lr, nD, nI, Qout;
+  int sX, nsets, hl;                                 // X stride, residue sets staged separately, left halo slots
+  int packmode;                                      // 0 fwd, 1 dgrad (stride 1), 2 dgrad of an X-strided conv
   int KG, nkg, colstride, tmem_cols;
   int rows_alloc, region_rows;
   int relu, has_aff, has_stats, has_add;
@@ -135,8 +137,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < ntaps) {
+    // tap -> (residue set, row offset): input x = sX*ox + dx - pX = sX*(ox + q) + res, slot = ox + q + hl
     const int dx = tid % p.kX, dy = (tid / p.kX) % p.kY, dd = tid / (p.kX * p.kY);
-    tapoff_s[tid] = dd * p.Lr + dy * p.Xp + dx;
+    const int e = dx - p.pX;
+    const int q = e >= 0 ? e / p.sX : -((-e + p.sX - 1) / p.sX);
+    const int res = e - q * p.sX;
+    const int set = p.nsets == 1 ? 0 : res;
+    tapoff_s[tid] = set * nkc * p.rows_alloc + dd * p.Lr + dy * p.Xp + q + p.hl;
   }
   for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) stat_s[i] = 0.f;
   if (warp == 0) {
@@ -192,10 +199,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
         h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
       }
+      for (int set = 0; set < p.nsets; set++) {
+      // residue of this set: the set index itself, except for a single-set strided conv (1x1x1 stride s: residue 0)
+      const int res = p.nsets == 1 ? (p.sX == 1 ? 0 : ((-p.pX) % p.sX + p.sX) % p.sX) : set;
       int r = tid / nkc;
       int j = r / p.Lr, ii = r - j * p.Lr;
       int yp = (i0 + ii) / p.Xp, xp = (i0 + ii) - yp * p.Xp;
-      uint8_t* a_dst = a_s + (size_t)kc * plane;
+      uint8_t* a_dst = a_s + (size_t)(set * nkc + kc) * plane;
       while (r < p.region_rows) {
         uint4 v[4];
         int rr[4];
@@ -203,7 +213,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           rr[u] = r;
-          const int d = d0 + j - p.pD, yy = yp - p.pY, xx = xp - p.pX;
+          const int d = d0 + j - p.pD, yy = yp - p.pY;
+          const int xx = p.sX == 1 ? xp - p.pX : p.sX * (xp - p.hl) + res;
           ok[u] = (r < p.region_rows) && d >= 0 && d < p.D && yy >= 0 && yy < p.Y && xx >= 0 && xx < p.X;
           v[u] = make_uint4(0u, 0u, 0u, 0u);
           if (ok[u]) {
@@ -227,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           }
         }
       }
+      }  // sets
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to UMMA
       __syncthreads();
       // ---- MMA issue: lane 0 of warps 0..3, each for its own accumulator blocks ----
@@ -341,7 +353,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 // Pack fp32 master weights [Cout][Cin][taps] to the bf16 smem image [nchunk][kg][tap][kc][n (Npad)][8].
 // transposed: the operator applied is the dgrad conv: n <-> ci, k <-> co, taps flipped.
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ntaps,
-                                    int Kc, int Nc, int Npad, int KG, int nchunks, int transposed) {
+                                    int Kc, int Nc, int Npad, int KG, int nchunks, int mode, int sH, int pH, int kH,
+                                    int tmin) {
   // Kc = reduction channels of the packed operator, Nc = its output channels, Npad = channels per N-chunk
   const int nkc = KG >> 3;
   const int nkg = Kc / KG;
@@ -357,8 +370,13 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     const int k = kg * KG + kc * 8 + e;
     float v = 0.f;
     if (n < Nc) {
-      if (!transposed) v = w[((int64_t)n * Cin + k) * ntaps + tap];
-      else v = w[((int64_t)k * Cin + n) * ntaps + (ntaps - 1 - tap)];
+      if (mode == 0) v = w[((int64_t)n * Cin + k) * ntaps + tap];                       // forward
+      else if (mode == 1) v = w[((int64_t)k * Cin + n) * ntaps + (ntaps - 1 - tap)];   // dgrad, stride 1
+      else {                                    // dgrad of a depth-strided (1,1,kH) conv: n = r*Cin + ci
+        const int r = n / Cin, ci = n - r * Cin;
+        const int dx = r + pH - sH * (tap + tmin);
+        if (dx >= 0 && dx < kH) v = w[((int64_t)k * Cin + ci) * kH + dx];
+      }
     }
     out[i] = __float2bfloat16_rn(v);
   }
@@ -378,24 +396,43 @@ Plan make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   pl.ok = false;
   TcParams& p = pl.p;
   if (d->dtype != FFPN_BF16) return pl;
-  if (d->sS != 1 || d->sW != 1 || d->sH != 1) return pl;
+  if (d->sS != 1 || d->sW != 1) return pl;
+  const bool strided = d->sH != 1;
+  if (strided && (d->kS != 1 || d->kW != 1)) return pl;          // only the projection's depth-strided convs
   // logical conv as seen by the kernel (dgrad: roles swapped, pads k-1-p)
   int64_t S = transposed ? d->oS : d->S, W = transposed ? d->oW : d->W, H = transposed ? d->oH : d->H;
   int64_t oS = transposed ? d->S : d->oS, oW = transposed ? d->W : d->oW, oH = transposed ? d->H : d->oH;
   int pS = transposed ? d->kS - 1 - d->pS : d->pS, pW = transposed ? d->kW - 1 - d->pW : d->pW,
       pH = transposed ? d->kH - 1 - d->pH : d->pH;
-  const int Cin = transposed ? d->Cout : d->Cin, Cout = transposed ? d->Cin : d->Cout;
-  if (Cin % 16 != 0 || Cout % 8 != 0 || Cin < 16) return pl;
+  int Cin = transposed ? d->Cout : d->Cin, Cout = transposed ? d->Cin : d->Cout;
   const int64_t B = d->B;
   int kS = d->kS, kW = d->kW, kH = d->kH;
-  if (H == 1 && oH == 1 && kH == 1 && (kW > 1)) {
+  p.sX = 1; p.packmode = transposed ? 1 : 0;
+  int tmin = 0;
+  if (strided && transposed) {
+    // dgrad of an X-strided conv == stride-1 conv over dy whose N = sH * Cin columns are the sH interleaved
+    // input positions:  dx[s*j + r] = sum_t W[dx = r + p - s*(t + tmin)]^T dy[j + t + tmin]
+    const int sH = d->sH;
+    if (d->H % sH != 0 || d->H / sH != d->oH) return pl;
+    tmin = -((d->kH - 1 - d->pH) / sH);                          // ceil((p - (k-1)) / s) for p <= k-1
+    if (d->pH > d->kH - 1) return pl;
+    const int tmax = (sH - 1 + d->pH) / sH;
+    kH = tmax - tmin + 1; pH = -tmin;
+    Cout = sH * d->Cin;
+    H = d->oH; oH = d->oH;                                       // rows of dy in, rows of (sH*Cin)-wide dx out
+    p.packmode = 2;
+  } else if (strided) {
+    p.sX = d->sH;
+  }
+  if (Cin % 16 != 0 || Cout % 8 != 0 || Cin < 16) return pl;
+  if (!strided && H == 1 && oH == 1 && kH == 1 && (kW > 1)) {
     // en-face / 2-D maps: (S, W) becomes the inner plane
     p.NB = 1; p.D = (int)B; p.kD = 1; p.pD = 0; p.oD = (int)B;
     p.Y = (int)S; p.kY = kS; p.pY = pS; p.oY = (int)oS;
     p.X = (int)W; p.kX = kW; p.pX = pW; p.oX = (int)oW;
     p.inD = S * W; p.inY = W; p.inNB = 0;
     p.outD = oS * oW; p.outY = oW; p.outNB = 0;
-  } else if (kW == 1 && kH == 1) {
+  } else if (!strided && kW == 1 && kH == 1) {
     if (kS == 1) {                                    // 1x1x1: a plain GEMM over all positions
       p.NB = 1; p.D = 1; p.kD = 1; p.pD = 0; p.oD = 1;
       p.Y = 1; p.kY = 1; p.pY = 0; p.oY = 1;
@@ -425,10 +462,27 @@ Plan make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
     pl.nchunks = (npad + 255) / 256;
     p.Npad = (((npad + pl.nchunks - 1) / pl.nchunks) + 15) & ~15;
   }
-  p.Xp = p.X + 2 * p.pX;
+  // slots per X line: tap dx reads input x = sX*(ox + q) + res, q = floor((dx - pX) / sX); hl = max(-q), hr = max(q) + hl
+  int qmin = 0, qmax = 0, nres = 0;
+  bool seen[16] = {false};
+  if (p.sX > 16) return pl;
+  for (int dx = 0; dx < p.kX; dx++) {
+    const int e = dx - p.pX;
+    const int q = e >= 0 ? e / p.sX : -((-e + p.sX - 1) / p.sX);
+    const int res = e - q * p.sX;
+    if (dx == 0 || q < qmin) qmin = q;
+    if (dx == 0 || q > qmax) qmax = q;
+    if (!seen[res]) { seen[res] = true; nres++; }
+  }
+  p.hl = qmin < 0 ? -qmin : 0;
+  if (qmin > 0) return pl;
+  p.nsets = nres > 1 ? p.sX : 1;
+  if (p.nsets > 2) return pl;
+  const int hr = qmax + p.hl;
+  p.Xp = p.oX + hr;
   p.Qout = (p.oY - 1) * p.Xp + p.oX;
   const int ntaps = p.kD * p.kY * p.kX;
-  const int maxinner = (p.kY - 1) * p.Xp + (p.kX - 1);
+  const int maxinner = (p.kY - 1) * p.Xp + hr;
   p.colstride = p.Npad < 32 ? 32 : p.Npad;
   // K-group: largest of Cin(<=64)/64/32/16 whose weight image fits 72 KB
   int KG = 64;
@@ -469,7 +523,7 @@ Plan make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
       int rows_alloc = nmb * 128 + maxoff;
       const int region = (tD + p.kD - 1) * Lr;
       if (rows_alloc < region) rows_alloc = region;
-      const size_t a_bytes = (size_t)rows_alloc * KG * 2;
+      const size_t a_bytes = (size_t)p.nsets * rows_alloc * KG * 2;
       const size_t smem = fixed + a_bytes;
       if (smem > smem_cap) continue;
       p.tD = tD; p.L = L; p.Lr = Lr;
@@ -483,7 +537,7 @@ Plan make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
       pl.smem = smem;
       const int ntiles = p.NB * p.nD * p.nI;
       pl.grid = ntiles < per_sm * num_sms ? ntiles : per_sm * num_sms;
-      pl.ok = ((uint64_t)rows_alloc * 16 < (1u << 18)) && tc <= 512;
+      pl.ok = ((uint64_t)p.nsets * (KG / 8) * rows_alloc * 16 < (1u << 18)) && tc <= 512;
       return pl;
     }
   }
@@ -505,6 +559,7 @@ struct WgParams {
   int Cin, Cout, Xp, Qout, tD, L, Lr, nD, nI;
   int ci_t, co_t, nci, nco, nkcx, nkcy;
   int nshift, ngroups, ntaps;
+  int sX, nsets, hl;
   int goff[27];
   int Kpad, rows_x, colstride, tmem_cols;
   unsigned xbuf_bytes, ybuf_bytes;
@@ -573,8 +628,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_
     const int L_t = min(p.L, p.Qout - i0);
     const int M_t = (tD_t - 1) * p.Lr + L_t;
     // ---- stage x (with the producer's BN+ReLU, zero padding), kX shifted copies when materialised ----
-    {
+    for (int set = 0; set < p.nsets; set++) {
+      const int res = p.nsets == 1 ? (p.sX == 1 ? 0 : ((-p.pX) % p.sX + p.sX) % p.sX) : set;
       const bf16* xb = p.x + (long long)nb * p.inNB * p.Cin + ci0 + kcx * 8;
+      uint8_t* xdst = xs[buf] + (size_t)set * p.nshift * p.nkcx * plane_x;
       int r = tid / p.nkcx;
       int j = r / p.Lr, ii = r - j * p.Lr;
       int yp = (i0 + ii) / p.Xp, xp = (i0 + ii) - yp * p.Xp;
@@ -585,7 +642,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           rr[u] = r;
-          const int d = d0 + j - p.pD, yy = yp - p.pY, xx = xp - p.pX;
+          const int d = d0 + j - p.pD, yy = yp - p.pY;
+          const int xx = p.sX == 1 ? xp - p.hl : p.sX * (xp - p.hl) + res;
           ok[u] = (r < region_rows) && d >= 0 && d < p.D && yy >= 0 && yy < p.Y && xx >= 0 && xx < p.X;
           v[u] = make_uint4(0u, 0u, 0u, 0u);
           if (ok[u]) v[u] = *reinterpret_cast<const uint4*>(xb + ((long long)d * p.inD + (long long)yy * p.inY + xx) * p.Cin);
@@ -604,7 +662,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_
             for (int sft = 0; sft < p.nshift; sft++) {
               const int rd = rr[u] - sft;
               if (rd >= 0 && rd < p.rows_x)
-                *reinterpret_cast<uint4*>(xs[buf] + (size_t)(sft * p.nkcx + kcx) * plane_x + (size_t)rd * 16) = v[u];
+                *reinterpret_cast<uint4*>(xdst + (size_t)(sft * p.nkcx + kcx) * plane_x + (size_t)rd * 16) = v[u];
             }
           }
         }
@@ -701,6 +759,7 @@ WgPlan make_wgrad_plan(const ffpn_conv_desc* d, int num_sms) {
   p.kD = c.kD; p.kY = c.kY; p.kX = c.kX; p.pD = c.pD; p.pY = c.pY; p.pX = c.pX;
   p.inNB = c.inNB; p.inD = c.inD; p.inY = c.inY; p.outNB = c.outNB; p.outD = c.outD; p.outY = c.outY;
   p.Cin = d->Cin; p.Cout = d->Cout; p.Xp = c.Xp; p.Qout = c.Qout;
+  p.sX = c.sX; p.nsets = c.nsets; p.hl = c.hl;
   p.ntaps = p.kD * p.kY * p.kX;
   if (p.ntaps > 27) return w;
   p.ci_t = p.Cin < 128 ? p.Cin : 128;
@@ -708,10 +767,16 @@ WgPlan make_wgrad_plan(const ffpn_conv_desc* d, int num_sms) {
   p.nci = p.Cin / p.ci_t;
   p.nkcx = p.ci_t / 8;
   // materialise the kX row shifts as extra planes when they fit the 16 chunks of an M=128 operand
-  p.nshift = (p.kX > 1 && p.nkcx * p.kX <= 16) ? p.kX : 1;
+  p.nshift = (p.sX == 1 && p.kX > 1 && p.nkcx * p.kX <= 16) ? p.kX : 1;
   const int ngroups = p.ntaps / p.nshift;
   p.ngroups = ngroups;
-  const int maxinner = (p.kY - 1) * p.Xp + (p.kX - 1);
+  int hr = 0;
+  for (int dx = 0; dx < p.kX; dx++) {
+    const int e = dx - p.pX;
+    const int q = e >= 0 ? e / p.sX : -((-e + p.sX - 1) / p.sX);
+    if (q + p.hl > hr) hr = q + p.hl;
+  }
+  const int maxinner = (p.kY - 1) * p.Xp + hr;
   // output-channel tile: accumulators of all groups must fit 512 TMEM columns
   int co_t = 256;
   while (co_t > 16 && (co_t > p.Cout || ngroups * (co_t < 32 ? 32 : co_t) > 512 || p.Cout % co_t != 0)) co_t >>= 1;
@@ -736,18 +801,22 @@ WgPlan make_wgrad_plan(const ffpn_conv_desc* d, int num_sms) {
     }
     const int M_total = (tD - 1) * Lr + L;
     const int Kpad = (M_total + 15) & ~15;
-    int maxg = 0;
+    int maxg = 0, gset[27];
     for (int g = 0; g < ngroups; g++) {
       const int tap = g * p.nshift;                       // first tap of the group (dx = 0 when materialised)
       const int dx = tap % p.kX, dy = (tap / p.kX) % p.kY, dd = tap / (p.kX * p.kY);
-      p.goff[g] = dd * Lr + dy * p.Xp + dx;
+      const int e = dx - p.pX;
+      const int q = e >= 0 ? e / p.sX : -((-e + p.sX - 1) / p.sX);
+      gset[g] = p.nsets == 1 ? 0 : e - q * p.sX;
+      p.goff[g] = dd * Lr + dy * p.Xp + q + p.hl;
       if (p.goff[g] > maxg) maxg = p.goff[g];
     }
     const int rows_x = Kpad + maxg;
-    const size_t xbuf = (size_t)p.nshift * p.nkcx * rows_x * 16, ybuf = (size_t)p.nkcy * Kpad * 16;
+    for (int g = 0; g < ngroups; g++) p.goff[g] += gset[g] * p.nshift * p.nkcx * rows_x;   // residue set base (rows)
+    const size_t xbuf = (size_t)p.nsets * p.nshift * p.nkcx * rows_x * 16, ybuf = (size_t)p.nkcy * Kpad * 16;
     size_t smem = 128 + 2 * xbuf + 2 * ybuf;
     // an M=128 operand always reads 16 chunk planes: keep the (ignored) extra ones inside the allocation
-    const size_t reach = 128 + xbuf + (size_t)16 * rows_x * 16;
+    const size_t reach = 128 + xbuf + (size_t)(p.nsets - 1) * p.nshift * p.nkcx * rows_x * 16 + (size_t)16 * rows_x * 16;
     if (reach > smem) smem = reach;
     if (smem > 224 * 1024 || (uint64_t)rows_x * 16 >= (1u << 18)) continue;
     p.tD = tD; p.L = L; p.Lr = Lr; p.Kpad = Kpad; p.rows_x = rows_x;
@@ -817,7 +886,8 @@ int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   {
     const int64_t total = (int64_t)need / 2;
     const int g = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
-    pack_weights_kernel<<<g, 256, 0, st>>>(w, (bf16*)ws, d->Cout, d->Cin, ntaps, p.Cin, p.Cout, p.Npad, p.KG, pl.nchunks, transposed ? 1 : 0);
+    pack_weights_kernel<<<g, 256, 0, st>>>(w, (bf16*)ws, d->Cout, d->Cin, ntaps, p.Cin, p.Cout, p.Npad, p.KG, pl.nchunks,
+                                           p.packmode, d->sH, d->pH, d->kH, -p.pX);
     FFPN_CHECK_LAUNCH(ctx, "pack_weights");
   }
   p.x = (const bf16*)x; p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)ws;

@@ -43,6 +43,14 @@ CASES = [
     ('enc2d_13', 32, 32, (1, 3, 1), (0, 1, 0), (2, 40, 64, 1)),
     ('enc2d_31', 64, 64, (3, 1, 1), (1, 0, 0), (2, 40, 32, 1)),
     ('odd_133', 32, 48, (1, 3, 3), (0, 1, 1), (1, 2, 31, 62)),
+    # projection: depth-strided convs (de-interleaved residue planes) and strided 1x1x1 shortcuts
+    ('proj_s2_l1', 16, 16, (1, 1, 3), (0, 0, 1), (2, 3, 16, 128), (1, 1, 2)),
+    ('proj_s2_l3', 64, 64, (1, 1, 3), (0, 0, 1), (2, 3, 8, 32), (1, 1, 2)),
+    ('proj_s2_62', 32, 32, (1, 1, 3), (0, 0, 1), (1, 2, 4, 62), (1, 1, 2)),
+    ('proj_s2_l4', 128, 128, (1, 1, 3), (0, 0, 1), (2, 4, 16, 16), (1, 1, 2)),
+    ('sc_s16', 16, 16, (1, 1, 1), (0, 0, 0), (2, 3, 8, 128), (1, 1, 16)),
+    ('sc_s8', 32, 32, (1, 1, 1), (0, 0, 0), (2, 3, 8, 64), (1, 1, 8)),
+    ('sc_s2', 128, 128, (1, 1, 1), (0, 0, 0), (2, 3, 8, 16), (1, 1, 2)),
 ]
 
 
@@ -50,7 +58,8 @@ CASES = [
 def test_conv_tc(case):
     from ffpn import ops
     torch.backends.cudnn.allow_tf32 = False
-    name, cin, cout, k, p, (B, S, W, H) = case
+    name, cin, cout, k, p, (B, S, W, H) = case[:6]
+    s1 = case[6] if len(case) > 6 else (1, 1, 1)
     dt = torch.bfloat16
     g = torch.Generator().manual_seed(len(name) * 131 + cin)
     x = torch.randn(B, cin, S, W, H, generator=g).cuda()
@@ -58,7 +67,6 @@ def test_conv_tc(case):
     sc = (0.5 + torch.rand(cin, generator=g)).cuda()
     sh = (0.3 * torch.randn(cin, generator=g)).cuda()
     xq = x.to(dt).float()
-    s1 = (1, 1, 1)
     old = ops.get_conv_impl()
     try:
         for affine in (False, True):

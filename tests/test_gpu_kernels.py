@@ -52,6 +52,9 @@ CONV_CASES = [
     (96, 32, (3, 3, 1), (1, 1, 1), (1, 1, 0), (6, 7, 1)),
     (16, 16, (1, 3, 1), (1, 1, 1), (0, 1, 0), (9, 11, 1)),
     (40, 24, (1, 3, 3), (1, 1, 1), (0, 1, 1), (2, 5, 6)),       # channel counts that are not tile multiples
+    (1, 16, (1, 3, 1), (1, 1, 1), (0, 1, 0), (9, 11, 1)),        # 2-D stem (1,3)
+    (1, 16, (1, 1, 1), (1, 1, 1), (0, 0, 0), (3, 10, 12)),       # stem shortcut
+    (16, 16, (1, 1, 3), (1, 1, 2), (0, 0, 1), (2, 5, 25)),       # odd depth: dgrad falls back to the CUDA-core kernel
 ]
 
 
