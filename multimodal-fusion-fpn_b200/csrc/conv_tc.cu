@@ -111,6 +111,7 @@ __device__ __forceinline__ uint4 bn_relu_bf16x8(uint4 v, const float (&s)[8], co
   return make_uint4(u[0], u[1], u[2], u[3]);
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // header: [0] weights barrier, [8] mma barrier, [16] tmem base, [32] tap offsets, [160..] stats (2*Npad floats)
@@ -164,6 +165,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   // staging role of this thread: one 8-channel chunk, rows r0, r0 + RP, ...
   const int kc = tid % nkc;
   const int RP = TC_THREADS / nkc;
+
+  // narrow layers keep the BatchNorm partial sums of this thread's rows in registers for the whole kernel
+  float rsum[NCH > 0 ? NCH * 16 : 1], rsq[NCH > 0 ? NCH * 16 : 1];
+#pragma unroll
+  for (int i = 0; i < (NCH > 0 ? NCH * 16 : 1); i++) { rsum[i] = 0.f; rsq[i] = 0.f; }
 
   uint32_t n_commit = 0, n_wload = 0;   // completed phases of bar_m / bar_w (uniform across the CTA)
   const int ntiles = p.NB * p.nD * p.nI;
@@ -277,7 +283,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       const int oy = i / p.Xp, ox = i - oy * p.Xp;
       const bool valid = (m < M_t) && (j < tD_t) && (ii < L_t) && (oy < p.oY) && (ox < p.oX);
       const long long opos = (long long)nb * p.outNB + (long long)(d0 + j) * p.outD + (long long)oy * p.outY + ox;
-      for (int ch = 0; ch < nchunks; ch++) {
+#pragma unroll
+      for (int ch = 0; ch < (NCH > 0 ? NCH : 16); ch++) {
+        if (NCH == 0 && ch >= nchunks) break;
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mb * p.colstride + ch * 16), raw);
         float v[16];
@@ -312,7 +320,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           if (cbase + 8 < p.Cout) yp[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
-        if (p.has_stats) {
+        if (NCH > 0) {
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+              rsum[(NCH > 0 ? ch : 0) * 16 + q] += v[q];
+              rsq[(NCH > 0 ? ch : 0) * 16 + q] = fmaf(v[q], v[q], rsq[(NCH > 0 ? ch : 0) * 16 + q]);
+            }
+          }
+        } else if (p.has_stats) {
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 16; q++) myscr[lane * SCR_STRIDE + q] = valid ? v[q] : 0.f;
@@ -338,6 +354,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     __syncthreads();     // TMEM drained and A free before the next tile is staged
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }  // tile loop
+  if (NCH > 0 && p.has_stats) {
+#pragma unroll
+    for (int i = 0; i < (NCH > 0 ? NCH * 16 : 1); i++) {
+      const float a = warp_sum(rsum[i]), b = warp_sum(rsq[i]);
+      if (lane == 0) { atomicAdd(&stat_s[i], a); atomicAdd(&stat_s[p.Npad + i], b); }
+    }
+    __syncthreads();
+  }
   if (p.has_stats) {
     for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) {
       const int which = i / p.Npad, c = i - which * p.Npad;
@@ -571,7 +595,9 @@ struct WgParams {
   float* dw;
 };
 
-__global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+constexpr int WG_THREADS = 512;
+
+__global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);          // [0], [8]: one per smem buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
@@ -600,8 +626,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_
   // D=f32, A=B=bf16, both MN-major (bits 15,16), N = co_t, M = 128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.co_t >> 3) << 17) | (8u << 24);
 
-  const int kcx = tid % p.nkcx, RPX = TC_THREADS / p.nkcx;
-  const int kcy = tid % p.nkcy, RPY = TC_THREADS / p.nkcy;
+  const int kcx = tid % p.nkcx, RPX = WG_THREADS / p.nkcx;
+  const int kcy = tid % p.nkcy, RPY = WG_THREADS / p.nkcy;
   float s[8], h[8];
   if (p.has_aff) {
     const int cofs = ci0 + kcx * 8;
@@ -636,11 +662,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_
       int j = r / p.Lr, ii = r - j * p.Lr;
       int yp = (i0 + ii) / p.Xp, xp = (i0 + ii) - yp * p.Xp;
       while (r < xrows_needed) {
-        uint4 v[4];
-        int rr[4];
-        bool ok[4];
+        uint4 v[8];
+        int rr[8];
+        bool ok[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
           rr[u] = r;
           const int d = d0 + j - p.pD, yy = yp - p.pY;
           const int xx = p.sX == 1 ? xp - p.hl : p.sX * (xp - p.hl) + res;
@@ -656,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
           if (rr[u] < xrows_needed) {
             if (p.has_aff && ok[u]) v[u] = bn_relu_bf16x8(v[u], s, h, p.relu);
             for (int sft = 0; sft < p.nshift; sft++) {
@@ -717,7 +743,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tc_kernel(const __grid_
     const bool lane_ok = q < p.nshift * p.nkcx;
     const int ci = ci0 + c * 8 + e;
     const int nch = p.co_t >> 4;
-    for (int w = warp >> 2; w < p.ngroups * nch; w += 2) {
+    for (int w = warp >> 2; w < p.ngroups * nch; w += WG_THREADS / 128) {
       const int g = w / nch, ch = w - g * nch;
       uint32_t raw[16];
       tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * p.colstride + ch * 16), raw);
@@ -856,7 +882,7 @@ int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_wgrad_tc_kernel<<<w.grid, TC_THREADS, w.smem, st>>>(p);
+  conv_wgrad_tc_kernel<<<w.grid, WG_THREADS, w.smem, st>>>(p);
   FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_tc");
   return 0;
 }
@@ -895,11 +921,16 @@ int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_tc_kernel<<<dim3(pl.grid, pl.nchunks), TC_THREADS, pl.smem, st>>>(p);
+  const dim3 grid(pl.grid, pl.nchunks);
+  // NCH = 1/2 keep the BatchNorm partial sums in registers; measured on B200 the extra 32-64 registers cost one
+  // resident CTA per SM and lose more than the shared-memory transpose they avoid, so the smem path is used.
+  conv_tc_kernel<0><<<grid, TC_THREADS, pl.smem, st>>>(p);
   FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_tc" : "conv_fwd_tc");
   if (stat_rows) *stat_rows = pl.grid;
   return 0;
