@@ -15,6 +15,9 @@
 // column group); tcgen05.commit signals an mbarrier; 8 warps read the accumulators back with tcgen05.ld,
 // round, store channels-last rows and reduce the BatchNorm partial sums.  Two CTAs per SM overlap one CTA's
 // staging/epilogue with the other's MMAs.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -31,6 +34,9 @@ struct TcParams {
   int Xp, tD, L, Lr, nD, nI, Qout;
   int sX, nsets, hl;                                 // X stride, residue sets staged separately, left halo slots
   int packmode;                                      // 0 fwd, 1 dgrad (stride 1), 2 dgrad of an X-strided conv
+  int use_tma, tma_mode, tY;                         // A tiles staged by TMA: 0 lines (C,X,Y,D) 1 slices (C,Xflat,D,NB) 2 flat (C,256,P/256)
+  unsigned tma_bytes;                                // bytes of one unit's TMA loads (expect_tx)
+  int dbg;                                           // FFPN_TC_DEBUG bitmask (timing experiments only): 1 no MMA, 2 no epilogue, 4 no staging
   int KG, nkg, colstride, tmem_cols;
   int rows_alloc, region_rows;
   int relu, has_aff, has_stats, has_add;
@@ -111,30 +117,234 @@ __device__ __forceinline__ uint4 bn_relu_bf16x8(uint4 v, const float (&s)[8], co
   return make_uint4(u[0], u[1], u[2], u[3]);
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;                       // src-size 0 => the 16 bytes are zero-filled (padding)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// Walks the rows r0, r0+RP, ... of a staged tile, tracking (slice j, padded-flat inner index -> yp, xp)
+// incrementally so that no per-element division is needed.
+struct RowWalk {
+  int r, j, ii, yp, xp;
+  __device__ __forceinline__ void init(int r0, int i0, const TcParams& p) {
+    r = r0; j = r / p.Lr; ii = r - j * p.Lr;
+    yp = (i0 + ii) / p.Xp; xp = (i0 + ii) - yp * p.Xp;
+  }
+  __device__ __forceinline__ void advance(int RP, int i0, const TcParams& p) {
+    r += RP; ii += RP; xp += RP;
+    if (ii >= p.Lr) {
+      while (ii >= p.Lr) { ii -= p.Lr; j++; }
+      yp = (i0 + ii) / p.Xp; xp = (i0 + ii) - yp * p.Xp;
+    } else {
+      while (xp >= p.Xp) { xp -= p.Xp; yp++; }
+    }
+  }
+  __device__ __forceinline__ bool source(int d0, int res, const TcParams& p, long long& pos) const {
+    const int d = d0 + j - p.pD, yy = yp - p.pY;
+    const int xx = p.sX == 1 ? xp - p.hl : p.sX * (xp - p.hl) + res;
+    pos = (long long)d * p.inD + (long long)yy * p.inY + xx;
+    return d >= 0 && d < p.D && yy >= 0 && yy < p.Y && xx >= 0 && xx < p.X;
+  }
+};
+
+struct TileCoord {
+  int nb, d0, i0, tD_t, L_t, M_t, nmb;
+  __device__ __forceinline__ void set(int tile, const TcParams& p) {
+    int t = tile;
+    const int it = t % p.nI; t /= p.nI;
+    const int dt = t % p.nD;
+    nb = t / p.nD;
+    d0 = dt * p.tD; i0 = it * p.L;
+    tD_t = min(p.tD, p.oD - d0);
+    L_t = min(p.L, p.Qout - i0);
+    M_t = (tD_t - 1) * p.Lr + L_t;
+    nmb = (M_t + 127) >> 7;
+  }
+};
+
+// Issue the asynchronous copies of one (tile, K-group) straight into the planar A layout (padding zero-filled).
+__device__ __forceinline__ void stage_issue(const TcParams& p, const TileCoord& tc, int kg, uint32_t a_dst, uint32_t plane,
+                                            int tid) {
+  const int nkc = p.KG >> 3, kc = tid % nkc, RP = TC_THREADS / nkc;
+  const bf16* xb = p.x + (long long)tc.nb * p.inNB * p.Cin + kg * p.KG + kc * 8;
+  for (int set = 0; set < p.nsets; set++) {
+    const int res = p.nsets == 1 ? (p.sX == 1 ? 0 : ((-p.pX) % p.sX + p.sX) % p.sX) : set;
+    const uint32_t dst = a_dst + (uint32_t)(set * nkc + kc) * plane;
+    RowWalk w;
+    w.init(tid / nkc, tc.i0, p);
+    while (w.r < p.region_rows) {
+      long long pos;
+      const bool ok = w.source(tc.d0, res, p, pos);
+      cp_async16(dst + (uint32_t)w.r * 16u, ok ? (const void*)(xb + pos * p.Cin) : (const void*)p.x, ok);
+      w.advance(RP, tc.i0, p);
+    }
+  }
+}
+
+// In-place BN scale/shift + ReLU of the valid elements of a staged tile (padding stays zero).
+__device__ __forceinline__ void transform_inplace(const TcParams& p, const TileCoord& tc, int kg, uint8_t* a_buf, uint32_t plane,
+                                                  int tid) {
+  const int nkc = p.KG >> 3, kc = tid % nkc, RP = TC_THREADS / nkc;
+  const int cofs = kg * p.KG + kc * 8;
+  float s[8], h[8];
+  {
+    const float4 s0 = *reinterpret_cast<const float4*>(p.sc + cofs), s1 = *reinterpret_cast<const float4*>(p.sc + cofs + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(p.sh + cofs), h1 = *reinterpret_cast<const float4*>(p.sh + cofs + 4);
+    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+    h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+  }
+  for (int set = 0; set < p.nsets; set++) {
+    const int res = p.nsets == 1 ? (p.sX == 1 ? 0 : ((-p.pX) % p.sX + p.sX) % p.sX) : set;
+    uint8_t* base = a_buf + (size_t)(set * nkc + kc) * plane;
+    RowWalk w;
+    w.init(tid / nkc, tc.i0, p);
+    while (w.r < p.region_rows) {
+      long long pos;
+      if (w.source(tc.d0, res, p, pos)) {
+        uint4* q = reinterpret_cast<uint4*>(base + (size_t)w.r * 16);
+        *q = bn_relu_bf16x8(*q, s, h, p.relu);
+      }
+      w.advance(RP, tc.i0, p);
+    }
+  }
+}
+
+// TMA staging of one (tile, K-group): one 4-D box per 8-channel chunk lands as one plane of the A layout; halo /
+// out-of-image elements are filled by the TMA unit (zero, or NaN when a BN+ReLU transform follows: relu(NaN) = 0).
+__device__ __forceinline__ void stage_issue_tma(const TcParams& p, const CUtensorMap* tmap, const TileCoord& tc, int kg,
+                                                uint32_t a_dst, uint32_t plane, uint32_t bar) {
+  const int nkc = p.KG >> 3;
+  int c1, c2, c3;
+  if (p.tma_mode == 0) { c1 = -p.hl; c2 = tc.i0 / p.Xp - p.pY; c3 = tc.d0; }
+  else if (p.tma_mode == 1) { c1 = tc.i0; c2 = tc.d0 - p.pD; c3 = tc.nb; }
+  else { c1 = 0; c2 = tc.i0 >> 8; c3 = 0; }
+  mbar_expect_tx(bar, p.tma_bytes);
+  for (int kc = 0; kc < nkc; kc++) tma_load_4d(a_dst + (uint32_t)kc * plane, tmap, kg * p.KG + kc * 8, c1, c2, c3, bar);
+}
+
+// In-place BN scale/shift + ReLU over a TMA-staged tile: a flat loop, no coordinates (NaN-filled halo -> 0).
+__device__ __forceinline__ void transform_flat(const TcParams& p, int kg, uint8_t* a_buf, uint32_t plane, int tid) {
+  const int nkc = p.KG >> 3, kc = tid % nkc, RP = TC_THREADS / nkc;
+  const int cofs = kg * p.KG + kc * 8;
+  float s[8], h[8];
+  {
+    const float4 s0 = *reinterpret_cast<const float4*>(p.sc + cofs), s1 = *reinterpret_cast<const float4*>(p.sc + cofs + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(p.sh + cofs), h1 = *reinterpret_cast<const float4*>(p.sh + cofs + 4);
+    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+    h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+  }
+  uint4* base = reinterpret_cast<uint4*>(a_buf + (size_t)kc * plane);
+  for (int r = tid / nkc; r < p.region_rows; r += RP) base[r] = bn_relu_bf16x8(base[r], s, h, 1);
+}
+
+// TMEM accumulators of one tile -> bf16 rows in global memory (+ residual addend, + BatchNorm partial sums).
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, const TileCoord& tc, uint32_t tmem_tile, int n0, float* myscr,
+                                              float* stat_s, int warp, int lane) {
+  const int nchunks = p.Npad >> 4;
+  for (int mb = warp >> 2; mb < tc.nmb; mb += 2) {
+    const int m = mb * 128 + (warp & 3) * 32 + lane;
+    const int j = m / p.Lr, ii = m - j * p.Lr;
+    const int i = tc.i0 + ii;
+    const int oy = i / p.Xp, ox = i - oy * p.Xp;
+    const bool valid = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX);
+    const long long opos = (long long)tc.nb * p.outNB + (long long)(tc.d0 + j) * p.outD + (long long)oy * p.outY + ox;
+    for (int ch = 0; ch < nchunks; ch++) {
+      uint32_t raw[16];
+      tmem_ld16(tmem_tile + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mb * p.colstride + ch * 16), raw);
+      float v[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[q]);
+      const int cbase = n0 + ch * 16;                 // global output channel of this 16-wide chunk
+      if (p.has_add && valid) {
+        const uint4* ap = reinterpret_cast<const uint4*>(p.addend + opos * p.Cout + cbase);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+          if (cbase + h2 * 8 < p.Cout) {
+            const uint4 a4 = ap[h2];
+            const uint32_t u[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              v[h2 * 8 + 2 * q] += __uint_as_float(u[q] << 16);
+              v[h2 * 8 + 2 * q + 1] += __uint_as_float(u[q] & 0xffff0000u);
+            }
+          }
+        }
+      }
+      uint32_t packed[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        packed[q] = *reinterpret_cast<uint32_t*>(&hh);
+        v[2 * q] = __uint_as_float(packed[q] << 16);           // statistics of the stored (rounded) values
+        v[2 * q + 1] = __uint_as_float(packed[q] & 0xffff0000u);
+      }
+      if (valid) {
+        uint4* yp = reinterpret_cast<uint4*>(p.y + opos * p.Cout + cbase);
+        if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        if (cbase + 8 < p.Cout) yp[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+      if (p.has_stats) {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 16; q++) myscr[lane * SCR_STRIDE + q] = valid ? v[q] : 0.f;
+        __syncwarp();
+        const int c = lane & 15, half = lane >> 4;
+        float sm = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) {
+          const float f = myscr[(half * 16 + rr) * SCR_STRIDE + c];
+          sm += f;
+          s2 = fmaf(f, f, s2);
+        }
+        sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+        if (lane < 16) {
+          atomicAdd(&stat_s[ch * 16 + c], sm);
+          atomicAdd(&stat_s[p.Npad + ch * 16 + c], s2);
+        }
+      }
+    }
+  }
+}
+
+// Software pipeline over units u = (tile, K-group) of a persistent CTA:
+//   loads of unit u+1 (cp.async, straight into the other A buffer)  ||  transform + MMAs of unit u  ||
+//   epilogue of the previous tile (other TMEM buffer).
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p,
+                                                             const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // header: [0] weights barrier, [8] mma barrier, [16] tmem base, [32] tap offsets, [160..] stats (2*Npad floats)
+  // header: [0],[8] weight barriers, [16] mma barrier, [24] tmem base, [32] tap offsets, [144],[152] TMA barriers, [160..] stats
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 24);
   int* tapoff_s = reinterpret_cast<int*>(smem + HDR_TAPS);
   float* stat_s = reinterpret_cast<float*>(smem + HDR_STATS);
   const uint32_t hdr = (HDR_STATS + 2 * p.Npad * 4 + 127) & ~127u;
   float* scr = reinterpret_cast<float*>(smem + hdr);                            // [8 warps][32][SCR_STRIDE]
   const uint32_t a_off = hdr + 8 * 32 * SCR_STRIDE * 4;
-  uint8_t* a_s = smem + a_off;
-  uint8_t* b_s = a_s + p.a_bytes;
-  const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1]);
+  uint8_t* a_s[2] = {smem + a_off, smem + a_off + p.a_bytes};
+  uint8_t* b_s[2] = {smem + a_off + 2 * (size_t)p.a_bytes, smem + a_off + 2 * (size_t)p.a_bytes + (p.nkg > 1 ? p.b_bytes : 0)};
+  const uint32_t bar_w[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])}, bar_m = smem_u32(&bars[2]);
+  const uint32_t bar_a[2] = {smem_u32(smem + 144), smem_u32(smem + 152)};
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntaps = p.kD * p.kY * p.kX;
   const int nkc = p.KG >> 3;
   const uint32_t plane = (uint32_t)p.rows_alloc * 16u;
   const int n0 = blockIdx.y * p.Npad;                 // first output channel of this CTA's N-chunk
-  const bf16* wp = p.wp + (size_t)blockIdx.y * p.nkg * (p.b_bytes / 2);
+  const uint8_t* wp = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)blockIdx.y * p.nkg * p.b_bytes;
 
   if (tid == 0) {
-    mbar_init(bar_w, 1);
+    mbar_init(bar_w[0], 1);
+    mbar_init(bar_w[1], 1);
     mbar_init(bar_m, N_ISSUE);
+    mbar_init(bar_a[0], 1);
+    mbar_init(bar_a[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < ntaps) {
@@ -156,211 +366,224 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_half = (uint32_t)(p.tmem_cols >> 1);     // two accumulator buffers (tile parity)
 
   // instruction descriptor: D=f32, A=B=bf16, K-major both, N=Npad, M=128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | (8u << 24);
+  const uint64_t a_desc[2] = {make_desc(smem_u32(a_s[0]), plane, 128u), make_desc(smem_u32(a_s[1]), plane, 128u)};
+  const uint64_t b_desc[2] = {make_desc(smem_u32(b_s[0]), (uint32_t)p.Npad * 16u, 128u),
+                              make_desc(smem_u32(b_s[1]), (uint32_t)p.Npad * 16u, 128u)};
+  float* myscr = scr + warp * 32 * SCR_STRIDE;
+
+  const int ntiles = p.NB * p.nD * p.nI;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nunits = my_tiles * p.nkg;
+  TileCoord tc_cur, tc_prev, tc_next;
+
+  // prologue: unit 0
+  tc_cur.set(blockIdx.x, p);
+  if (p.use_tma) {
+    if (tid == 0) {
+      if (p.dbg & 4) { mbar_expect_tx(bar_a[0], 0); }
+      else stage_issue_tma(p, &tmap, tc_cur, 0, smem_u32(a_s[0]), plane, bar_a[0]);
+    }
+  } else {
+    stage_issue(p, tc_cur, 0, smem_u32(a_s[0]), plane, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_expect_tx(bar_w[0], p.b_bytes);
+    bulk_g2s(smem_u32(b_s[0]), wp, p.b_bytes, bar_w[0]);
+  }
+  tc_prev = tc_cur;
+  for (int u = 0; u < nunits; u++) {
+    const int tl = u / p.nkg, kg = u - tl * p.nkg;
+    const int buf = u & 1;
+    if (u >= 1) {
+      mbar_wait(bar_m, (u - 1) & 1);        // MMAs of unit u-1 done: the other A/B buffers and its TMEM tile are ready
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (u + 1 < nunits) {
+      const int tl1 = (u + 1) / p.nkg, kg1 = (u + 1) - tl1 * p.nkg;
+      tc_next.set(blockIdx.x + tl1 * gridDim.x, p);
+      if (p.use_tma) {
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses to this buffer
+          if (p.dbg & 4) { mbar_expect_tx(bar_a[buf ^ 1], 0); }
+          else stage_issue_tma(p, &tmap, tc_next, kg1, smem_u32(a_s[buf ^ 1]), plane, bar_a[buf ^ 1]);
+        }
+      } else {
+        stage_issue(p, tc_next, kg1, smem_u32(a_s[buf ^ 1]), plane, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      if (p.nkg > 1 && tid == 0) {
+        mbar_expect_tx(bar_w[buf ^ 1], p.b_bytes);
+        bulk_g2s(smem_u32(b_s[buf ^ 1]), wp + (size_t)kg1 * p.b_bytes, p.b_bytes, bar_w[buf ^ 1]);
+      }
+      if (!p.use_tma) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      if (!p.use_tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (p.use_tma) mbar_wait(bar_a[buf], (u >> 1) & 1);   // unit u's boxes have landed
+    else __syncthreads();                                  // unit u's cp.async data visible to every thread
+    if (p.has_aff) {
+      if (p.use_tma) transform_flat(p, kg, a_s[buf], plane, tid);
+      else transform_inplace(p, tc_cur, kg, a_s[buf], plane, tid);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to UMMA
+    __syncthreads();
+    // ---- MMA issue: lane 0 of warps 0..3, each for its own accumulator blocks ----
+    if (warp < N_ISSUE && lane == 0) {
+      if (p.nkg > 1) mbar_wait(bar_w[buf], (u >> 1) & 1);
+      else if (u == 0) mbar_wait(bar_w[0], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t kstep_a = 2u * (plane >> 4), kstep_b = 2u * (uint32_t)p.Npad;
+      const uint64_t bd0 = b_desc[p.nkg > 1 ? buf : 0];
+      for (int mb = warp; mb < ((p.dbg & 1) ? 0 : tc_cur.nmb); mb += N_ISSUE) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(tl & 1) * tmem_half + (uint32_t)(mb * p.colstride);
+        uint32_t acc = kg != 0 ? 1u : 0u;
+        for (int tap = 0; tap < ntaps; tap++) {
+          uint64_t ad = a_desc[buf] + (uint64_t)(uint32_t)(mb * 128 + tapoff_s[tap]);
+          uint64_t bd = bd0 + (uint64_t)(uint32_t)(tap * nkc * p.Npad);
+          for (int ks = 0; ks < nkc / 2; ks++) {
+            umma_bf16(d_tmem, ad, bd, idesc, acc);
+            acc = 1u;
+            ad += kstep_a;
+            bd += kstep_b;
+          }
+        }
+      }
+      umma_commit(bar_m);
+    }
+    // ---- epilogue of the previous tile (its last K-group was unit u-1), overlapping this unit's MMAs ----
+    if (u >= 1 && kg == 0 && !(p.dbg & 2)) {
+      epilogue_tile(p, tc_prev, tmem_base + (uint32_t)((tl - 1) & 1) * tmem_half, n0, myscr, stat_s, warp, lane);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    if (kg == p.nkg - 1) tc_prev = tc_cur;
+    if (u + 1 < nunits) tc_cur = tc_next;
+  }
+  // drain: last tile
+  mbar_wait(bar_m, (nunits - 1) & 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!(p.dbg & 2)) epilogue_tile(p, tc_prev, tmem_base + (uint32_t)((my_tiles - 1) & 1) * tmem_half, n0, myscr, stat_s, warp, lane);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (p.has_stats) {
+    for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) {
+      const int which = i / p.Npad, c = i - which * p.Npad;
+      if (n0 + c < p.Cout) p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = stat_s[which * p.Npad + c];
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+// Single-buffer variant for narrow layers: TMA (or cp.async) -> transform -> MMAs -> epilogue, strictly in sequence inside
+// a CTA, but small enough (<= 56 KB smem, 128 TMEM columns, 64 registers) that FOUR CTAs share an SM and overlap
+// each other's phases.  Measured on B200 this beats the two-stage pipeline above when N <= 32.
+__global__ void __launch_bounds__(TC_THREADS, 4) conv_tc_simple_kernel(const __grid_constant__ TcParams p,
+                                                                       const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 24);
+  int* tapoff_s = reinterpret_cast<int*>(smem + HDR_TAPS);
+  float* stat_s = reinterpret_cast<float*>(smem + HDR_STATS);
+  const uint32_t hdr = (HDR_STATS + 2 * p.Npad * 4 + 127) & ~127u;
+  float* scr = reinterpret_cast<float*>(smem + hdr);
+  const uint32_t a_off = hdr + 8 * 32 * SCR_STRIDE * 4;
+  uint8_t* a_s = smem + a_off;
+  uint8_t* b_s = a_s + p.a_bytes;
+  const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[2]), bar_a = smem_u32(smem + 144);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntaps = p.kD * p.kY * p.kX;
+  const int nkc = p.KG >> 3;
+  const uint32_t plane = (uint32_t)p.rows_alloc * 16u;
+  const int n0 = blockIdx.y * p.Npad;
+  const uint8_t* wp = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)blockIdx.y * p.nkg * p.b_bytes;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, N_ISSUE);
+    mbar_init(bar_a, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < ntaps) {
+    const int dx = tid % p.kX, dy = (tid / p.kX) % p.kY, dd = tid / (p.kX * p.kY);
+    const int e = dx - p.pX;
+    const int q = e >= 0 ? e / p.sX : -((-e + p.sX - 1) / p.sX);
+    const int res = e - q * p.sX;
+    const int set = p.nsets == 1 ? 0 : res;
+    tapoff_s[tid] = set * nkc * p.rows_alloc + dd * p.Lr + dy * p.Xp + q + p.hl;
+  }
+  for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) stat_s[i] = 0.f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | (8u << 24);
   const uint64_t a_desc0 = make_desc(smem_u32(a_s), plane, 128u);
   const uint64_t b_desc0 = make_desc(smem_u32(b_s), (uint32_t)p.Npad * 16u, 128u);
-
-  // staging role of this thread: one 8-channel chunk, rows r0, r0 + RP, ...
-  const int kc = tid % nkc;
-  const int RP = TC_THREADS / nkc;
-
-  // narrow layers keep the BatchNorm partial sums of this thread's rows in registers for the whole kernel
-  float rsum[NCH > 0 ? NCH * 16 : 1], rsq[NCH > 0 ? NCH * 16 : 1];
-#pragma unroll
-  for (int i = 0; i < (NCH > 0 ? NCH * 16 : 1); i++) { rsum[i] = 0.f; rsq[i] = 0.f; }
-
-  uint32_t n_commit = 0, n_wload = 0;   // completed phases of bar_m / bar_w (uniform across the CTA)
+  float* myscr = scr + warp * 32 * SCR_STRIDE;
+  if (tid == 0) {                                      // weights: resident for the whole CTA (nkg == 1 in this variant)
+    mbar_expect_tx(bar_w, p.b_bytes);
+    bulk_g2s(smem_u32(b_s), wp, p.b_bytes, bar_w);
+  }
   const int ntiles = p.NB * p.nD * p.nI;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int t = tile;
-    const int it = t % p.nI; t /= p.nI;
-    const int dt = t % p.nD;
-    const int nb = t / p.nD;
-    const int d0 = dt * p.tD, i0 = it * p.L;
-    const int tD_t = min(p.tD, p.oD - d0);
-    const int L_t = min(p.L, p.Qout - i0);
-    const int M_t = (tD_t - 1) * p.Lr + L_t;
-    const int nmb = (M_t + 127) >> 7;
-    const bf16* xb = p.x + (long long)nb * p.inNB * p.Cin;
-
-    for (int kg = 0; kg < p.nkg; kg++) {
-      if (kg > 0) {
-        mbar_wait(bar_m, (n_commit - 1) & 1);     // previous group's MMAs have consumed A and B
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t n = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n++) {
+    TileCoord tc;
+    tc.set(tile, p);
+    if (p.use_tma) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        stage_issue_tma(p, &tmap, tc, 0, smem_u32(a_s), plane, bar_a);
       }
-      const bool load_w = (p.nkg > 1) || (n_wload == 0);    // resident weights are fetched once per CTA
-      if (load_w && tid == 0) {
-        mbar_expect_tx(bar_w, p.b_bytes);
-        bulk_g2s(smem_u32(b_s), reinterpret_cast<const uint8_t*>(wp) + (size_t)kg * p.b_bytes, p.b_bytes, bar_w);
-      }
-      // ---- stage A: region rows x KG channels; BN scale/shift + ReLU + zero padding applied in registers.
-      //      Row coordinates advance incrementally (no per-element division); loads are issued 4 deep. ----
-      const int cofs = kg * p.KG + kc * 8;
-      float s[8], h[8];
-      if (p.has_aff) {
-        const float4 s0 = *reinterpret_cast<const float4*>(p.sc + cofs), s1 = *reinterpret_cast<const float4*>(p.sc + cofs + 4);
-        const float4 h0 = *reinterpret_cast<const float4*>(p.sh + cofs), h1 = *reinterpret_cast<const float4*>(p.sh + cofs + 4);
-        s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
-        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
-      }
-      for (int set = 0; set < p.nsets; set++) {
-      // residue of this set: the set index itself, except for a single-set strided conv (1x1x1 stride s: residue 0)
-      const int res = p.nsets == 1 ? (p.sX == 1 ? 0 : ((-p.pX) % p.sX + p.sX) % p.sX) : set;
-      int r = tid / nkc;
-      int j = r / p.Lr, ii = r - j * p.Lr;
-      int yp = (i0 + ii) / p.Xp, xp = (i0 + ii) - yp * p.Xp;
-      uint8_t* a_dst = a_s + (size_t)(set * nkc + kc) * plane;
-      while (r < p.region_rows) {
-        uint4 v[4];
-        int rr[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          rr[u] = r;
-          const int d = d0 + j - p.pD, yy = yp - p.pY;
-          const int xx = p.sX == 1 ? xp - p.pX : p.sX * (xp - p.hl) + res;
-          ok[u] = (r < p.region_rows) && d >= 0 && d < p.D && yy >= 0 && yy < p.Y && xx >= 0 && xx < p.X;
-          v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (ok[u]) {
-            const long long pos = (long long)d * p.inD + (long long)yy * p.inY + xx;
-            v[u] = *reinterpret_cast<const uint4*>(xb + pos * p.Cin + cofs);
-          }
-          // advance to the next row of this thread
-          r += RP; ii += RP; xp += RP;
-          if (ii >= p.Lr) {
-            while (ii >= p.Lr) { ii -= p.Lr; j++; }
-            yp = (i0 + ii) / p.Xp; xp = (i0 + ii) - yp * p.Xp;
-          } else {
-            while (xp >= p.Xp) { xp -= p.Xp; yp++; }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (rr[u] < p.region_rows) {
-            if (p.has_aff && ok[u]) v[u] = bn_relu_bf16x8(v[u], s, h, p.relu);
-            *reinterpret_cast<uint4*>(a_dst + (size_t)rr[u] * 16) = v[u];
-          }
-        }
-      }
-      }  // sets
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to UMMA
+      mbar_wait(bar_a, n & 1);
+    } else {
+      stage_issue(p, tc, 0, smem_u32(a_s), plane, tid);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
-      // ---- MMA issue: lane 0 of warps 0..3, each for its own accumulator blocks ----
-      if (warp < N_ISSUE && lane == 0) {
-        if (load_w) mbar_wait(bar_w, n_wload & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t kstep_a = 2u * (plane >> 4), kstep_b = 2u * (uint32_t)p.Npad;
-        for (int mb = warp; mb < nmb; mb += N_ISSUE) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(mb * p.colstride);
-          uint32_t acc = kg != 0 ? 1u : 0u;
-          for (int tap = 0; tap < ntaps; tap++) {
-            uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mb * 128 + tapoff_s[tap]);
-            uint64_t bd = b_desc0 + (uint64_t)(uint32_t)(tap * nkc * p.Npad);
-            for (int ks = 0; ks < nkc / 2; ks++) {
-              umma_bf16(d_tmem, ad, bd, idesc, acc);
-              acc = 1u;
-              ad += kstep_a;
-              bd += kstep_b;
-            }
-          }
-        }
-        umma_commit(bar_m);
-      }
-      n_commit++;
-      if (load_w) n_wload++;
     }
-    // ---- epilogue: TMEM -> registers -> global (+ BatchNorm partial sums) ----
-    mbar_wait(bar_m, (n_commit - 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* myscr = scr + warp * 32 * SCR_STRIDE;
-    const int nchunks = p.Npad >> 4;
-    for (int mb = warp >> 2; mb < nmb; mb += 2) {
-      const int m = mb * 128 + (warp & 3) * 32 + lane;
-      const int j = m / p.Lr, ii = m - j * p.Lr;
-      const int i = i0 + ii;
-      const int oy = i / p.Xp, ox = i - oy * p.Xp;
-      const bool valid = (m < M_t) && (j < tD_t) && (ii < L_t) && (oy < p.oY) && (ox < p.oX);
-      const long long opos = (long long)nb * p.outNB + (long long)(d0 + j) * p.outD + (long long)oy * p.outY + ox;
-#pragma unroll
-      for (int ch = 0; ch < (NCH > 0 ? NCH : 16); ch++) {
-        if (NCH == 0 && ch >= nchunks) break;
-        uint32_t raw[16];
-        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mb * p.colstride + ch * 16), raw);
-        float v[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[q]);
-        const int cbase = n0 + ch * 16;                 // global output channel of this 16-wide chunk
-        if (p.has_add && valid) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.addend + opos * p.Cout + cbase);
-#pragma unroll
-          for (int h2 = 0; h2 < 2; h2++) {
-            if (cbase + h2 * 8 < p.Cout) {
-              const uint4 a4 = ap[h2];
-              const uint32_t u[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                v[h2 * 8 + 2 * q] += __uint_as_float(u[q] << 16);
-                v[h2 * 8 + 2 * q + 1] += __uint_as_float(u[q] & 0xffff0000u);
-              }
-            }
-          }
-        }
-        uint32_t packed[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-          packed[q] = *reinterpret_cast<uint32_t*>(&hh);
-          v[2 * q] = __uint_as_float(packed[q] << 16);           // statistics of the stored (rounded) values
-          v[2 * q + 1] = __uint_as_float(packed[q] & 0xffff0000u);
-        }
-        if (valid) {
-          uint4* yp = reinterpret_cast<uint4*>(p.y + opos * p.Cout + cbase);
-          if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          if (cbase + 8 < p.Cout) yp[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-        }
-        if (NCH > 0) {
-          if (valid) {
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-              rsum[(NCH > 0 ? ch : 0) * 16 + q] += v[q];
-              rsq[(NCH > 0 ? ch : 0) * 16 + q] = fmaf(v[q], v[q], rsq[(NCH > 0 ? ch : 0) * 16 + q]);
-            }
-          }
-        } else if (p.has_stats) {
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 16; q++) myscr[lane * SCR_STRIDE + q] = valid ? v[q] : 0.f;
-          __syncwarp();
-          const int c = lane & 15, half = lane >> 4;
-          float sm = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 16; rr++) {
-            const float f = myscr[(half * 16 + rr) * SCR_STRIDE + c];
-            sm += f;
-            s2 = fmaf(f, f, s2);
-          }
-          sm += __shfl_xor_sync(0xffffffffu, sm, 16);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-          if (lane < 16) {
-            atomicAdd(&stat_s[ch * 16 + c], sm);
-            atomicAdd(&stat_s[p.Npad + ch * 16 + c], s2);
-          }
-        }
-      }
+    if (p.has_aff) {
+      if (p.use_tma) transform_flat(p, 0, a_s, plane, tid);
+      else transform_inplace(p, tc, 0, a_s, plane, tid);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();     // TMEM drained and A free before the next tile is staged
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  }  // tile loop
-  if (NCH > 0 && p.has_stats) {
-#pragma unroll
-    for (int i = 0; i < (NCH > 0 ? NCH * 16 : 1); i++) {
-      const float a = warp_sum(rsum[i]), b = warp_sum(rsq[i]);
-      if (lane == 0) { atomicAdd(&stat_s[i], a); atomicAdd(&stat_s[p.Npad + i], b); }
-    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (warp < N_ISSUE && lane == 0) {
+      if (n == 0) mbar_wait(bar_w, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t kstep_a = 2u * (plane >> 4), kstep_b = 2u * (uint32_t)p.Npad;
+      for (int mb = warp; mb < tc.nmb; mb += N_ISSUE) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(mb * p.colstride);
+        uint32_t acc = 0u;
+        for (int tap = 0; tap < ntaps; tap++) {
+          uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mb * 128 + tapoff_s[tap]);
+          uint64_t bd = b_desc0 + (uint64_t)(uint32_t)(tap * nkc * p.Npad);
+          for (int ks = 0; ks < nkc / 2; ks++) {
+            umma_bf16(d_tmem, ad, bd, idesc, acc);
+            acc = 1u;
+            ad += kstep_a;
+            bd += kstep_b;
+          }
+        }
+      }
+      umma_commit(bar_m);
+    }
+    mbar_wait(bar_m, n & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    epilogue_tile(p, tc, tmem_base, n0, myscr, stat_s, warp, lane);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                   // TMEM drained, A free
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   if (p.has_stats) {
     for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) {
@@ -411,6 +634,7 @@ struct Plan {
   size_t smem;
   int grid;
   int nchunks;
+  bool simple;     // single-buffer kernel, 4 CTAs per SM
   bool ok;
 };
 
@@ -516,45 +740,95 @@ Plan make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   p.KG = KG; p.nkg = Cin / KG;
   p.b_bytes = (unsigned)((size_t)ntaps * KG * p.Npad * 2);
   const uint32_t hdr = (HDR_STATS + 2 * p.Npad * 4 + 127) & ~127u;
-  const size_t fixed = hdr + 8 * 32 * SCR_STRIDE * 4 + p.b_bytes;
+  const size_t fixed = hdr + 8 * 32 * SCR_STRIDE * 4 + (size_t)(p.nkg > 1 ? 2 : 1) * p.b_bytes;
   // Tile size: bounded by the TMEM columns and shared memory of the target occupancy.  Several CTAs per SM is
   // what overlaps one CTA's staging / epilogue with another's MMAs, so small-N layers aim for 4 CTAs per SM.
   if (ntaps > 27) return pl;
-  const int budgets[3][2] = {{4, 128}, {2, 256}, {1, 512}};
+  // {CTAs per SM, TMEM columns per CTA}: two accumulator buffers (tile parity) share the columns
+  // budgets: {CTAs per SM, TMEM columns per CTA, buffers}.  First the single-buffer 4-CTA/SM variant (narrow layers with
+  // resident weights), then the two-stage pipeline with two accumulator buffers sharing the columns.
+  const int budgets[3][3] = {{4, 128, 1}, {2, 256, 2}, {1, 512, 2}};
   for (int bi = 0; bi < 3; bi++) {
-    const int per_sm = budgets[bi][0];
-    int nmb_max = budgets[bi][1] / p.colstride;
+    const int per_sm = budgets[bi][0], nbuf = budgets[bi][2];
+    if (nbuf == 1 && (p.nkg != 1 || p.colstride > 32)) continue;
+    int nmb_max = budgets[bi][1] / nbuf / p.colstride;
     if (nmb_max > 8) nmb_max = 8;
-    if (nmb_max < (bi == 0 ? 4 : (bi == 1 ? 2 : 1))) continue;
+    if (nmb_max < (bi == 2 ? 1 : 2)) continue;
     const size_t smem_cap = (size_t)(227 * 1024) / per_sm - 1024;
     for (; nmb_max >= (bi == 2 ? 1 : 2); nmb_max--) {
       const int max_rows = nmb_max * 128;
-      int tD, L, Lr;
-      if (p.kD > 1) {
-        L = p.X < 128 ? p.X : 128; Lr = L;
-        tD = max_rows / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
-      } else if (p.Qout >= max_rows) {
-        const int nt = (p.Qout + max_rows - 1) / max_rows;
-        L = (((p.Qout + nt - 1) / nt) + 127) & ~127; if (L > max_rows) L = max_rows;
-        Lr = L + maxinner; tD = 1;
-      } else {
-        L = p.Qout; Lr = L + maxinner;
-        tD = (max_rows - L) / Lr + 1; if (tD > p.oD) tD = p.oD;
+      int tD = 1, L = 0, Lr = 0, region = 0, tY = 0, tma_mode = -1;
+      bool tma = false;
+      // ---- tiles that are TMA boxes: whole lines (mode 0), slice runs (mode 1), 256-row blocks (mode 2) ----
+      if (p.sX == 1) {
+        if (p.kD > 1) {
+          L = p.X < 128 ? p.X : 128; Lr = L;
+          tD = max_rows / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+          region = (tD + p.kD - 1) * L;
+          tma = tD + p.kD - 1 <= 256; tma_mode = 1;
+        } else if (p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1) {
+          if (p.X % 256 == 0) {
+            int nblk = max_rows / 256; if (nblk < 1) nblk = 1;
+            if (nblk * 256 > p.X) nblk = p.X / 256;
+            L = nblk * 256; Lr = L; tD = 1; region = L;
+            tma = nblk <= 256 && max_rows >= 256; tma_mode = 2;
+          }
+        } else if (p.Xp <= 256) {
+          tY = max_rows / p.Xp;
+          if (tY >= 1) {
+            if (tY >= p.oY) {
+              tY = p.oY;
+              Lr = (tY + p.kY - 1) * p.Xp;
+              tD = (max_rows - tY * p.Xp) / Lr + 1; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+            } else {
+              Lr = (tY + p.kY - 1) * p.Xp; tD = 1;
+            }
+            L = tY * p.Xp; region = tD * Lr;
+            tma = tY + p.kY - 1 <= 256 && tD <= 256; tma_mode = 0;
+          }
+        }
+      }
+      if (!tma) {
+        tma_mode = -1; tY = 0;
+        if (p.kD > 1) {
+          L = p.X < 128 ? p.X : 128; Lr = L;
+          tD = max_rows / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+        } else if (p.Qout >= max_rows) {
+          const int nt = (p.Qout + max_rows - 1) / max_rows;
+          L = (((p.Qout + nt - 1) / nt) + 127) & ~127; if (L > max_rows) L = max_rows;
+          Lr = L + maxinner; tD = 1;
+        } else {
+          L = p.Qout; Lr = L + maxinner;
+          tD = (max_rows - L) / Lr + 1; if (tD > p.oD) tD = p.oD;
+        }
+        region = (tD + p.kD - 1) * Lr;
       }
       const int M_total = (tD - 1) * Lr + L;
       const int nmb = (M_total + 127) / 128;
       const int maxoff = (p.kD - 1) * Lr + maxinner;
-      int rows_alloc = nmb * 128 + maxoff;
-      const int region = (tD + p.kD - 1) * Lr;
-      if (rows_alloc < region) rows_alloc = region;
-      const size_t a_bytes = (size_t)p.nsets * rows_alloc * KG * 2;
-      const size_t smem = fixed + a_bytes;
+      int rows_alloc;
+      size_t a_bytes;
+      if (tma) {
+        rows_alloc = (region + 7) & ~7;                           // each plane is its own TMA box; 128-byte aligned
+        const int over = nmb * 128 + maxoff - rows_alloc;         // MMA rows read past the last plane
+        a_bytes = (size_t)(KG / 8) * rows_alloc * 16 + (size_t)(over > 0 ? over : 0) * 16;
+      } else {
+        rows_alloc = nmb * 128 + maxoff;
+        if (rows_alloc < region) rows_alloc = region;
+        a_bytes = (size_t)p.nsets * rows_alloc * KG * 2;
+      }
+      a_bytes = (a_bytes + 127) & ~(size_t)127;
+      const size_t smem = fixed + (size_t)nbuf * a_bytes;
       if (smem > smem_cap) continue;
-      p.tD = tD; p.L = L; p.Lr = Lr;
+      pl.simple = nbuf == 1;
+      p.tD = tD; p.L = L; p.Lr = Lr; p.tY = tY;
+      p.use_tma = tma ? 1 : 0; p.tma_mode = tma_mode;
       p.rows_alloc = rows_alloc; p.region_rows = region;
+      p.tma_bytes = (unsigned)((size_t)(KG / 8) * region * 16);
       p.a_bytes = (unsigned)a_bytes;
       int cols = nmb * p.colstride, tc = 32;
       while (tc < cols) tc <<= 1;
+      if (nbuf == 2) tc <<= 1;                        // two accumulator buffers
       p.tmem_cols = tc;
       p.nD = (p.oD + tD - 1) / tD;
       p.nI = (p.Qout + L - 1) / L;
@@ -899,6 +1173,53 @@ size_t ffpn_tc_workspace_bytes(const ffpn_conv_desc* d) {
   return taps * cin * cout * 2 + 65536;
 }
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  // resolved through the runtime so that the library has no link-time dependency on libcuda (it must load on CPU boxes)
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 4-D map over a channels-last activation; one box = one 8-channel plane of a tile.
+bool encode_act_map(CUtensorMap* m, const TcParams& p, const void* x, bool nan_fill) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t cb = (cuuint64_t)p.Cin * 2;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], es[4] = {1, 1, 1, 1};
+  dims[0] = (cuuint64_t)p.Cin; box[0] = 8;
+  if (p.tma_mode == 0) {
+    dims[1] = p.X; dims[2] = p.Y; dims[3] = p.D;
+    strides[0] = cb; strides[1] = (cuuint64_t)p.inY * cb; strides[2] = (cuuint64_t)p.inD * cb;
+    box[1] = p.Xp; box[2] = p.tY + p.kY - 1; box[3] = p.tD;
+    if (p.Y == 1) strides[1] = (cuuint64_t)p.X * cb;              // unused dimension: any valid stride
+  } else if (p.tma_mode == 1) {
+    dims[1] = p.X; dims[2] = p.D; dims[3] = p.NB;
+    strides[0] = cb; strides[1] = (cuuint64_t)p.inD * cb; strides[2] = (cuuint64_t)(p.NB > 1 ? p.inNB : (long long)p.inD * p.D) * cb;
+    box[1] = p.L; box[2] = p.tD + p.kD - 1; box[3] = 1;
+  } else {
+    dims[1] = 256; dims[2] = p.X / 256; dims[3] = 1;
+    strides[0] = cb; strides[1] = 256 * cb; strides[2] = (cuuint64_t)p.X * cb;
+    box[1] = 256; box[2] = p.L / 256; box[3] = 1;
+  }
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+}  // namespace
+
 int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,
                      const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
                      int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -921,16 +1242,21 @@ int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   const dim3 grid(pl.grid, pl.nchunks);
-  // NCH = 1/2 keep the BatchNorm partial sums in registers; measured on B200 the extra 32-64 registers cost one
-  // resident CTA per SM and lose more than the shared-memory transpose they avoid, so the smem path is used.
-  conv_tc_kernel<0><<<grid, TC_THREADS, pl.smem, st>>>(p);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (p.use_tma) {
+    // BN+ReLU prologue: halo filled with NaN so that relu(scale*NaN+shift) = 0; without a prologue: zero fill
+    if ((p.has_aff && !p.relu) || !encode_act_map(&tmap, p, x, p.has_aff != 0)) p.use_tma = 0;
+  }
+  if (pl.simple) conv_tc_simple_kernel<<<grid, TC_THREADS, pl.smem, st>>>(p, tmap);
+  else conv_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(p, tmap);
   FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_tc" : "conv_fwd_tc");
   if (stat_rows) *stat_rows = pl.grid;
   return 0;

@@ -25,6 +25,11 @@ elif kind == 'fwd311':
 elif kind == 'dgrad133':
     w = torch.randn(C, C, 1, 3, 3, device='cuda', generator=g) * 0.1
     fn = lambda: ops.conv_dgrad(x, w, tuple(x.shape), (1, 3, 3), (1, 1, 1), (0, 1, 1))
+elif kind in ('dgrad111', 'dgrad113', 'dgrad131'):
+    k = {'dgrad111': (1, 1, 1), 'dgrad113': (1, 1, 3), 'dgrad131': (1, 3, 1)}[kind]
+    pd = tuple((v - 1) // 2 for v in k)
+    w = torch.randn(C, C, *k, device='cuda', generator=g) * 0.1
+    fn = lambda: ops.conv_dgrad(x, w, tuple(x.shape), k, (1, 1, 1), pd)
 elif kind == 'wgrad133':
     w = torch.randn(C, C, 1, 3, 3, device='cuda', generator=g) * 0.1
     dy = torch.randn_like(x)
@@ -32,14 +37,35 @@ elif kind == 'wgrad133':
 elif kind == 'proj':
     w = torch.randn(C, C, 1, 1, 3, device='cuda', generator=g) * 0.1
     fn = lambda: ops.conv_fwd(x, w, (1, 1, 3), (1, 1, 2), (0, 0, 1), sc, sh, True)
-for _ in range(iters):
+for _ in range(3):
     fn()
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(iters):
-    fn()
-e1.record()
-torch.cuda.synchronize()
-print(f'level {level} {kind}: {e0.elapsed_time(e1) / iters * 1e3:.1f} us per call, '
-      f'{2 * x.numel() * 2 / (e0.elapsed_time(e1) / iters * 1e-3) / 1e9:.0f} GB/s (in+out)')
+if os.environ.get('PROF_NO_GRAPH'):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    per = e0.elapsed_time(e1) / iters
+else:
+    # capture `iters` back-to-back calls in a CUDA graph: pure device time, no Python / launch gaps
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(iters):
+            fn()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    per = e0.elapsed_time(e1) / iters
+print(f'level {level} {kind}: {per * 1e3:.1f} us per call, {2 * x.numel() * 2 / (per * 1e-3) / 1e9:.0f} GB/s (in+out)')
