@@ -22,6 +22,24 @@
 
 namespace {
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  // resolved through the runtime so that the library has no link-time dependency on libcuda (it must load on CPU boxes)
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+
 constexpr int TC_THREADS = 256;
 constexpr int SCR_STRIDE = 17;                       // per-warp 32x16 transpose scratch, padded
 
@@ -1139,12 +1157,364 @@ WgPlan make_wgrad_plan(const ffpn_conv_desc* d, int num_sms) {
   return w;
 }
 
+
+// ---- wgrad, TMA-staged variant -------------------------------------------------------------------------
+// Operand roles: A = dy planes (M = output channels; an M=128 operand always reads 16 chunk planes, the unused ones
+// alias the x buffers that follow in smem and land in ignored TMEM lanes), B = x planes (N = kX shifts x input
+// channels: the kX shifted copies are simply kX TMA loads with shifted X coordinates), K = positions.
+// Both tiles are written by the TMA unit directly in the planar layout; out-of-image elements are zero (dy) or NaN
+// (x, turned into 0 by the in-place BN+ReLU pass).  Rows that no box covers are zeroed once at kernel start.
+struct WgTmaParams {
+  int NB, D, Y, X, oD, oY, oX, kD, kY, kX, pD, pY, pX, hl;
+  int Cin, Cout, Xp, tD, tY, L, Lr, nD, nI;
+  int ci_t, co_t, nci, nco, nkcx, nkcy, nshift, ngroups, ntaps;
+  int goff[27];
+  int Kpad, rows_x, xbox_rows, ybox_rows, ncol, colstride, tmem_cols, tma_mode;
+  unsigned xbuf_bytes, ybuf_bytes, tma_bytes;
+  int has_aff, dbg, nstages;
+  const float* sc;
+  const float* sh;
+  float* dw;
+};
+
+constexpr int WG_STAGES = 3;          // maximum ring depth (p.nstages = 2 or 3)
+constexpr int WG_HDR = 128 + 2 * 256 * 4;  // barriers + tmem slot, then scale/shift of this CTA's input-channel tile
+
+__device__ __forceinline__ void wgrad_tma_issue(const WgTmaParams& p, const CUtensorMap* tmx, const CUtensorMap* tmy, int tile,
+                                                uint32_t xd, uint32_t yd, uint32_t plane_x, uint32_t plane_y, int ci0, int co0,
+                                                uint32_t bar) {
+  int t = tile;
+  const int it = t % p.nI; t /= p.nI;
+  const int dt = t % p.nD;
+  const int nb = t / p.nD;
+  const int d0 = dt * p.tD;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(bar, (p.dbg & 4) ? 0u : p.tma_bytes);
+  if (p.dbg & 4) return;
+  if (p.tma_mode == 0) {
+    const int y0 = it * p.tY;
+    for (int kc = 0; kc < p.nkcx; kc++)            // shift 0 only: the transform pass writes the kX shifted copies
+      tma_load_4d(xd + (uint32_t)kc * plane_x, tmx, ci0 + kc * 8, -p.hl, y0 - p.pY, d0, bar);
+    for (int j = 0; j < p.tD; j++)
+      for (int kc = 0; kc < p.nkcy; kc++)
+        tma_load_4d(yd + (uint32_t)kc * plane_y + (uint32_t)(j * p.Lr) * 16u, tmy, co0 + kc * 8, 0, y0, d0 + j, bar);
+  } else if (p.tma_mode == 1) {
+    const int i0 = it * p.L;
+    for (int kc = 0; kc < p.nkcx; kc++) tma_load_4d(xd + (uint32_t)kc * plane_x, tmx, ci0 + kc * 8, i0, d0 - p.pD, nb, bar);
+    for (int kc = 0; kc < p.nkcy; kc++) tma_load_4d(yd + (uint32_t)kc * plane_y, tmy, co0 + kc * 8, i0, d0, nb, bar);
+  } else {
+    const int b0 = (it * p.L) >> 8;
+    for (int kc = 0; kc < p.nkcx; kc++) tma_load_4d(xd + (uint32_t)kc * plane_x, tmx, ci0 + kc * 8, 0, b0, 0, bar);
+    for (int kc = 0; kc < p.nkcy; kc++) tma_load_4d(yd + (uint32_t)kc * plane_y, tmy, co0 + kc * 8, 0, b0, 0, bar);
+  }
+}
+
+// Three-stage ring: TMA of tile n+1  ||  in-place BN+ReLU of tile n  ||  MMAs of tile n-1 (async, TMEM-resident accumulators).
+__global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tma_kernel(const __grid_constant__ WgTmaParams p,
+                                                                     const __grid_constant__ CUtensorMap tmx,
+                                                                     const __grid_constant__ CUtensorMap tmy) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);          // [0..2] MMA done per stage; [3..5] TMA landed per stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
+  float* sc_s = reinterpret_cast<float*>(smem + 128);
+  float* sh_s = sc_s + 256;
+  const int NST = p.nstages;
+  uint8_t* ybase = smem + WG_HDR;
+  uint8_t* xbase = smem + WG_HDR + NST * (size_t)p.ybuf_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t plane_x = (uint32_t)p.rows_x * 16u, plane_y = (uint32_t)p.Kpad * 16u;
+  const int cit = blockIdx.y % p.nci, cot = blockIdx.y / p.nci;
+  const int ci0 = cit * p.ci_t, co0 = cot * p.co_t;
+  const int nqx = p.nshift * p.nkcx;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_STAGES; i++) { mbar_init(smem_u32(&bars[i]), N_ISSUE); mbar_init(smem_u32(&bars[WG_STAGES + i]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.has_aff) {
+    for (int i = tid; i < p.ci_t; i += WG_THREADS) { sc_s[i] = p.sc[ci0 + i]; sh_s[i] = p.sh[ci0 + i]; }
+  }
+  {  // zero all stages once: rows outside the TMA boxes must be finite (x) / zero (dy) for the K reduction
+    uint4* z = reinterpret_cast<uint4*>(smem + WG_HDR);
+    const int n16 = (int)((NST * ((size_t)p.ybuf_bytes + (size_t)p.xbuf_bytes)) >> 4);
+    for (int i = tid; i < n16; i += WG_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  // D=f32, A=B=bf16, both MN-major, N = ncol, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.ncol >> 3) << 17) | (8u << 24);
+
+  const int ntiles = p.NB * p.nD * p.nI;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (tid == 0)
+    wgrad_tma_issue(p, &tmx, &tmy, blockIdx.x, smem_u32(xbase), smem_u32(ybase), plane_x, plane_y, ci0, co0, smem_u32(&bars[WG_STAGES]));
+  for (int n = 0; n < my_tiles; n++) {
+    const int b = n % NST;
+    if (n + 1 < my_tiles) {
+      const int b1 = (n + 1) % NST, u1 = (n + 1) / NST;
+      if (u1 >= 1) {
+        mbar_wait(smem_u32(&bars[b1]), (u1 - 1) & 1);         // MMAs that read stage b1 (tile n-2) are done
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      if (tid == 0)
+        wgrad_tma_issue(p, &tmx, &tmy, blockIdx.x + (n + 1) * gridDim.x, smem_u32(xbase + (size_t)b1 * p.xbuf_bytes),
+                        smem_u32(ybase + (size_t)b1 * p.ybuf_bytes), plane_x, plane_y, ci0, co0, smem_u32(&bars[WG_STAGES + b1]));
+    }
+    uint8_t* xs = xbase + (size_t)b * p.xbuf_bytes;
+    uint8_t* ys = ybase + (size_t)b * p.ybuf_bytes;
+    mbar_wait(smem_u32(&bars[WG_STAGES + b]), (n / NST) & 1);
+    if ((p.has_aff || p.nshift > 1) && !(p.dbg & 8)) {
+      // chunk plane by chunk plane, consecutive threads on consecutive rows (conflict-free 16-byte accesses):
+      // BN+ReLU in place on the shift-0 plane and the kX-1 shifted copies written from the same registers
+      for (int kc = 0; kc < p.nkcx; kc++) {
+        float s[8], h[8];
+        if (p.has_aff) {
+          const float4 s0 = *reinterpret_cast<const float4*>(sc_s + kc * 8), s1 = *reinterpret_cast<const float4*>(sc_s + kc * 8 + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(sh_s + kc * 8), h1 = *reinterpret_cast<const float4*>(sh_s + kc * 8 + 4);
+          s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+          h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+        }
+        uint4* base = reinterpret_cast<uint4*>(xs + (size_t)kc * plane_x);
+        for (int r = tid; r < p.xbox_rows; r += WG_THREADS) {
+          uint4 v = base[r];
+          if (p.has_aff) { v = bn_relu_bf16x8(v, s, h, 1); base[r] = v; }
+          for (int sft = 1; sft < p.nshift; sft++)
+            if (r >= sft) *reinterpret_cast<uint4*>(xs + (size_t)(sft * p.nkcx + kc) * plane_x + (size_t)(r - sft) * 16) = v;
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp < N_ISSUE && lane == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t a0 = make_desc(smem_u32(ys), 128u, plane_y);
+      const uint64_t b0 = make_desc(smem_u32(xs), 128u, plane_x);
+      const int ksteps = p.Kpad >> 4;
+      for (int g = warp; g < ((p.dbg & 1) ? 0 : p.ngroups); g += N_ISSUE) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.colstride);
+        uint64_t ad = a0;
+        uint64_t bd = b0 + (uint64_t)(uint32_t)p.goff[g];
+        uint32_t acc = n != 0 ? 1u : 0u;
+        for (int ks = 0; ks < ksteps; ks++) {
+          umma_bf16(d_tmem, ad, bd, idesc, acc);
+          acc = 1u;
+          ad += 16; bd += 16;
+        }
+      }
+      umma_commit(smem_u32(&bars[b]));
+    }
+  }
+  // drain: the last use of every stage
+  for (int b = 0; b < NST; b++) {
+    if (my_tiles > b) {
+      const int uses = (my_tiles - b + NST - 1) / NST;
+      mbar_wait(smem_u32(&bars[b]), (uses - 1) & 1);
+    }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const int L128 = (warp & 3) * 32 + lane;           // TMEM lane = output channel within the tile
+    const int co = co0 + L128;
+    const int nch = p.ncol >> 4;
+    for (int w = warp >> 2; w < p.ngroups * nch; w += WG_THREADS / 128) {
+      const int g = w / nch, ch = w - g * nch;
+      uint32_t raw[16];
+      tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * p.colstride + ch * 16), raw);
+      if (L128 < p.co_t && co < p.Cout) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const int nn = ch * 16 + k;
+          const int sft = nn / p.ci_t, ci = ci0 + nn - sft * p.ci_t;
+          const int tap = g * p.nshift + sft;
+          if (tap < p.ntaps && ci < p.Cin) atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.ntaps + tap, __uint_as_float(raw[k]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+struct WgTmaPlan {
+  WgTmaParams p;
+  size_t smem;
+  dim3 grid;
+  bool ok;
+  // tensor-map geometry
+  int xbox[4], ybox[4];
+  long long xdims[4], ydims[4], xstr[3], ystr[3];
+};
+
+WgTmaPlan make_wgrad_tma_plan(const ffpn_conv_desc* d, int num_sms) {
+  WgTmaPlan w;
+  memset(&w, 0, sizeof(w));
+  Plan f = make_plan(d, false, num_sms);
+  if (!f.ok || d->Cout % 16 != 0 || f.p.sX != 1) return w;
+  const TcParams& c = f.p;
+  WgTmaParams& p = w.p;
+  p.NB = c.NB; p.D = c.D; p.Y = c.Y; p.X = c.X; p.oD = c.oD; p.oY = c.oY; p.oX = c.oX;
+  p.kD = c.kD; p.kY = c.kY; p.kX = c.kX; p.pD = c.pD; p.pY = c.pY; p.pX = c.pX; p.hl = c.hl;
+  p.Cin = d->Cin; p.Cout = d->Cout; p.Xp = c.Xp;
+  p.ntaps = p.kD * p.kY * p.kX;
+  if (p.ntaps > 27) return w;
+  const bool flat = (p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1 && p.kD == 1);
+  if (p.kD > 1) p.tma_mode = 1;
+  else if (flat) { if (p.X % 256 != 0) return w; p.tma_mode = 2; }
+  else { if (p.Xp > 256) return w; p.tma_mode = 0; }
+  p.nshift = (p.tma_mode == 0 && p.kX > 1) ? p.kX : 1;
+  p.ngroups = p.ntaps / p.nshift;
+  p.co_t = p.Cout < 128 ? p.Cout : 128;
+  if (p.Cout % p.co_t != 0) return w;
+  p.nco = p.Cout / p.co_t; p.nkcy = p.co_t / 8;
+  int ci_t = 256;
+  while (ci_t > 16 && (ci_t > p.Cin || p.Cin % ci_t != 0 || p.nshift * ci_t > 256 ||
+                       p.ngroups * (p.nshift * ci_t < 32 ? 32 : p.nshift * ci_t) > 512)) ci_t >>= 1;
+  if (p.Cin % ci_t != 0 || p.nshift * ci_t > 256 || p.ngroups * (p.nshift * ci_t < 32 ? 32 : p.nshift * ci_t) > 512) return w;
+  p.ci_t = ci_t; p.nci = p.Cin / ci_t; p.nkcx = ci_t / 8;
+  p.ncol = p.nshift * ci_t;
+  p.colstride = p.ncol < 32 ? 32 : p.ncol;
+  int tc = 32;
+  while (tc < p.ngroups * p.colstride) tc <<= 1;
+  p.tmem_cols = tc;
+  int hr = 0;
+  for (int dx = 0; dx < p.kX; dx++) if (dx - p.pX + p.hl > hr) hr = dx - p.pX + p.hl;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    // prefer deep (3-stage) rings with large tiles; fall back to 2 stages before shrinking the tile below 256 rows
+    static const int cand[8][2] = {{512, 3}, {384, 3}, {512, 2}, {256, 3}, {384, 2}, {256, 2}, {128, 3}, {128, 2}};
+    const int Lmax = cand[attempt][0], nst = cand[attempt][1];
+    int tD = 1, tY = 0, L, Lr, xbox_rows, ybox_rows;
+    if (p.tma_mode == 1) {
+      L = p.X < 128 ? p.X : 128; Lr = L;
+      tD = Lmax / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+      xbox_rows = (tD + p.kD - 1) * L; ybox_rows = tD * L;
+    } else if (p.tma_mode == 2) {
+      int nblk = Lmax / 256; if (nblk < 1) continue;
+      if (nblk * 256 > p.X) nblk = p.X / 256;
+      L = nblk * 256; Lr = L; xbox_rows = L; ybox_rows = L;
+    } else {
+      tY = Lmax / p.Xp; if (tY < 1) continue;
+      if (tY >= p.oY) {
+        tY = p.oY;
+        Lr = (tY + p.kY - 1) * p.Xp;
+        tD = (Lmax - tY * p.Xp) / Lr + 1; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+        if (tD > 1 && (Lr % 8) != 0) tD = 1;             // per-slab dy boxes must start 128-byte aligned
+        if (tD > 64) tD = 64;
+      } else {
+        Lr = (tY + p.kY - 1) * p.Xp; tD = 1;
+      }
+      L = tY * p.Xp; xbox_rows = tD * Lr; ybox_rows = L;
+    }
+    const int M_total = (tD - 1) * Lr + L;
+    const int Kpad = (M_total + 15) & ~15;
+    int maxg = 0;
+    for (int g = 0; g < p.ngroups; g++) {
+      const int tap = g * p.nshift;
+      const int dx = tap % p.kX, dy = (tap / p.kX) % p.kY, dd = tap / (p.kX * p.kY);
+      p.goff[g] = dd * Lr + dy * p.Xp + (p.nshift > 1 ? 0 : dx - p.pX + p.hl);
+      if (p.goff[g] > maxg) maxg = p.goff[g];
+    }
+    int rows_x = Kpad + maxg; if (rows_x < xbox_rows) rows_x = xbox_rows;
+    rows_x = (rows_x + 7) & ~7;
+    const size_t xbuf = (size_t)p.nshift * p.nkcx * rows_x * 16, ybuf = (size_t)p.nkcy * Kpad * 16;
+    size_t smem = WG_HDR + nst * (xbuf + ybuf);
+    const size_t reach = WG_HDR + (nst - 1) * ybuf + (size_t)16 * Kpad * 16;   // dy operand reads 16 chunk planes from the last Y stage
+    p.nstages = nst;
+    if (reach > smem) smem = reach;
+    if (smem > 224 * 1024 || (uint64_t)rows_x * 16 >= (1u << 18)) continue;
+    p.tD = tD; p.tY = tY; p.L = L; p.Lr = Lr; p.Kpad = Kpad; p.rows_x = rows_x;
+    p.xbox_rows = xbox_rows; p.ybox_rows = ybox_rows;
+    p.xbuf_bytes = (unsigned)xbuf; p.ybuf_bytes = (unsigned)ybuf;
+    p.tma_bytes = (unsigned)((size_t)p.nkcx * xbox_rows * 16 + (size_t)p.nkcy * (p.tma_mode == 0 ? tD * ybox_rows : ybox_rows) * 16);
+    p.nD = (p.oD + tD - 1) / tD;
+    if (p.tma_mode == 0) p.nI = (p.oY + tY - 1) / tY;
+    else p.nI = (p.X + L - 1) / L;
+    // tensor maps
+    const long long cbx = (long long)p.Cin * 2, cby = (long long)p.Cout * 2;
+    w.xdims[0] = p.Cin; w.ydims[0] = p.Cout; w.xbox[0] = 8; w.ybox[0] = 8;
+    if (p.tma_mode == 0) {
+      w.xdims[1] = p.X; w.xdims[2] = p.Y; w.xdims[3] = p.D;
+      w.xstr[0] = cbx; w.xstr[1] = (p.Y == 1 ? (long long)p.X : c.inY) * cbx; w.xstr[2] = c.inD * cbx;
+      w.xbox[1] = p.Xp; w.xbox[2] = tY + p.kY - 1; w.xbox[3] = tD;
+      w.ydims[1] = p.oX; w.ydims[2] = p.oY; w.ydims[3] = p.oD;
+      w.ystr[0] = cby; w.ystr[1] = (p.oY == 1 ? (long long)p.oX : c.outY) * cby; w.ystr[2] = c.outD * cby;
+      w.ybox[1] = p.Xp; w.ybox[2] = tY; w.ybox[3] = 1;
+    } else if (p.tma_mode == 1) {
+      w.xdims[1] = p.X; w.xdims[2] = p.D; w.xdims[3] = p.NB;
+      w.xstr[0] = cbx; w.xstr[1] = c.inD * cbx; w.xstr[2] = (p.NB > 1 ? c.inNB : c.inD * p.D) * cbx;
+      w.xbox[1] = L; w.xbox[2] = tD + p.kD - 1; w.xbox[3] = 1;
+      w.ydims[1] = p.oX; w.ydims[2] = p.oD; w.ydims[3] = p.NB;
+      w.ystr[0] = cby; w.ystr[1] = c.outD * cby; w.ystr[2] = (p.NB > 1 ? c.outNB : c.outD * p.oD) * cby;
+      w.ybox[1] = L; w.ybox[2] = tD; w.ybox[3] = 1;
+    } else {
+      w.xdims[1] = 256; w.xdims[2] = p.X / 256; w.xdims[3] = 1;
+      w.xstr[0] = cbx; w.xstr[1] = 256 * cbx; w.xstr[2] = (long long)p.X * cbx;
+      w.xbox[1] = 256; w.xbox[2] = L / 256; w.xbox[3] = 1;
+      w.ydims[1] = 256; w.ydims[2] = p.X / 256; w.ydims[3] = 1;
+      w.ystr[0] = cby; w.ystr[1] = 256 * cby; w.ystr[2] = (long long)p.X * cby;
+      w.ybox[1] = 256; w.ybox[2] = L / 256; w.ybox[3] = 1;
+    }
+    for (int i = 1; i < 4; i++) if (w.xbox[i] > 256 || w.ybox[i] > 256) return w;
+    const int ntiles = p.NB * p.nD * p.nI;
+    int gx = num_sms / (p.nci * p.nco);
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    w.grid = dim3(gx, p.nci * p.nco);
+    w.smem = smem;
+    w.ok = true;
+    return w;
+  }
+  return w;
+}
+
+bool encode_map4(CUtensorMap* m, const void* base, const long long* dims, const long long* str, const int* box, bool nan_fill) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; i++) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
+  for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)str[i];
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 bool ffpn_tc_wgrad_supported(const ffpn_conv_desc* d) { return make_wgrad_plan(d, 148).ok; }
 
 int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale, const float* in_shift,
                        int in_relu, const void* dy, float* dw, void*, size_t, cudaStream_t st) {
+  static bool attr_tma = false;
+  if (!(in_scale != nullptr && !in_relu)) {
+    WgTmaPlan t = make_wgrad_tma_plan(d, ctx->num_sms);
+    CUtensorMap tmx, tmy;
+    if (t.ok && encode_map4(&tmx, x, t.xdims, t.xstr, t.xbox, in_scale != nullptr) &&
+        encode_map4(&tmy, dy, t.ydims, t.ystr, t.ybox, false)) {
+      WgTmaParams& q = t.p;
+      q.sc = in_scale; q.sh = in_shift; q.dw = dw; q.has_aff = in_scale != nullptr;
+      { const char* e = getenv("FFPN_TC_DEBUG"); q.dbg = e ? atoi(e) : 0; }
+      if (!attr_tma) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tma: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+        attr_tma = true;
+      }
+      conv_wgrad_tma_kernel<<<t.grid, WG_THREADS, t.smem, st>>>(q, tmx, tmy);
+      FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_tma");
+      return 0;
+    }
+  }
   WgPlan w = make_wgrad_plan(d, ctx->num_sms);
   if (!w.ok) FFPN_FAIL(ctx, "conv_wgrad_tc: geometry not supported");
   WgParams& p = w.p;
@@ -1174,23 +1544,6 @@ size_t ffpn_tc_workspace_bytes(const ffpn_conv_desc* d) {
 }
 
 namespace {
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode_tiled() {
-  // resolved through the runtime so that the library has no link-time dependency on libcuda (it must load on CPU boxes)
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-
 // 4-D map over a channels-last activation; one box = one 8-channel plane of a tile.
 bool encode_act_map(CUtensorMap* m, const TcParams& p, const void* x, bool nan_fill) {
   EncodeTiledFn enc = get_encode_tiled();
