@@ -15,137 +15,11 @@
 // column group); tcgen05.commit signals an mbarrier; 8 warps read the accumulators back with tcgen05.ld,
 // round, store channels-last rows and reduce the BatchNorm partial sums.  Two CTAs per SM overlap one CTA's
 // staging/epilogue with the other's MMAs.
-#include <cuda.h>
-#include <stdlib.h>
 
-#include "common.cuh"
+
+#include "tc_common.cuh"
 
 namespace {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode_tiled() {
-  // resolved through the runtime so that the library has no link-time dependency on libcuda (it must load on CPU boxes)
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-
-
-constexpr int TC_THREADS = 256;
-constexpr int SCR_STRIDE = 17;                       // per-warp 32x16 transpose scratch, padded
-
-struct TcParams {
-  // canonical geometry (stride-1 convolution)
-  int NB, D, Y, X, oD, oY, oX;
-  int kD, kY, kX, pD, pY, pX;
-  long long inNB, inD, inY, outNB, outD, outY;       // position strides (X stride is 1)
-  int Cin, Cout, Npad;
-  int Xp, tD, L, Lr, nD, nI, Qout;
-  int sX, nsets, hl;                                 // X stride, residue sets staged separately, left halo slots
-  int packmode;                                      // 0 fwd, 1 dgrad (stride 1), 2 dgrad of an X-strided conv
-  int use_tma, tma_mode, tY;                         // A tiles staged by TMA: 0 lines (C,X,Y,D) 1 slices (C,Xflat,D,NB) 2 flat (C,256,P/256)
-  unsigned tma_bytes;                                // bytes of one unit's TMA loads (expect_tx)
-  int dbg;                                           // FFPN_TC_DEBUG bitmask (timing experiments only): 1 no MMA, 2 no epilogue, 4 no staging
-  int KG, nkg, colstride, tmem_cols;
-  int rows_alloc, region_rows;
-  int relu, has_aff, has_stats, has_add;
-  unsigned a_bytes, b_bytes;                         // per K-group smem bytes
-  const bf16* x;
-  const float* sc;
-  const float* sh;
-  const bf16* wp;                                    // packed weights
-  const bf16* addend;
-  bf16* y;
-  float* stat;                                       // [gridDim.x][2][Cout]
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) lbo[16,30) sbo[32,46) version=1 at
-  // [46,48), base_offset 0, layout_type[61,64) = SWIZZLE_NONE (0).  All in 16-byte units.
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-constexpr int N_ISSUE = 4;          // warps whose lane 0 issues tcgen05.mma (different accumulator blocks each)
-constexpr int HDR_TAPS = 32;        // byte offset of the tap-offset table in the smem header
-constexpr int HDR_STATS = 160;      // byte offset of the per-CTA statistics accumulators
-
-__device__ __forceinline__ uint4 bn_relu_bf16x8(uint4 v, const float (&s)[8], const float (&h)[8], int relu) {
-  uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    float f0 = fmaf(__uint_as_float(u[q] << 16), s[2 * q], h[2 * q]);
-    float f1 = fmaf(__uint_as_float(u[q] & 0xffff0000u), s[2 * q + 1], h[2 * q + 1]);
-    if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-    __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
-    u[q] = *reinterpret_cast<uint32_t*>(&hh);
-  }
-  return make_uint4(u[0], u[1], u[2], u[3]);
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;                       // src-size 0 => the 16 bytes are zero-filled (padding)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
 
 // Walks the rows r0, r0+RP, ... of a staged tile, tracking (slice j, padded-flat inner index -> yp, xp)
 // incrementally so that no per-element division is needed.
@@ -647,16 +521,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
   }
 }
 
-struct Plan {
-  TcParams p;
-  size_t smem;
-  int grid;
-  int nchunks;
-  bool simple;     // single-buffer kernel, 4 CTAs per SM
-  bool ok;
-};
 
-Plan make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
+}  // namespace
+
+Plan ffpn_tc_make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   Plan pl;
   memset(&pl, 0, sizeof(pl));
   pl.ok = false;
@@ -861,6 +729,7 @@ Plan make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
 }
 
 
+namespace {
 // =====================================================================================================
 // wgrad on tcgen05:  dW[tap][ci][co] = sum_rows  f(x)[row + off(tap)][ci] * dy[row][co]
 // Both operands are staged in the same planar layout as the forward A tile ([8-channel chunk][row][16 B]) but are
@@ -1069,7 +938,7 @@ struct WgPlan {
 WgPlan make_wgrad_plan(const ffpn_conv_desc* d, int num_sms) {
   WgPlan w;
   memset(&w, 0, sizeof(w));
-  Plan f = make_plan(d, false, num_sms);          // canonical geometry (also validates dtype / stride / channels)
+  Plan f = ffpn_tc_make_plan(d, false, num_sms);          // canonical geometry (also validates dtype / stride / channels)
   if (!f.ok || d->Cout % 16 != 0) return w;
   WgParams& p = w.p;
   const TcParams& c = f.p;
@@ -1360,7 +1229,7 @@ struct WgTmaPlan {
 WgTmaPlan make_wgrad_tma_plan(const ffpn_conv_desc* d, int num_sms) {
   WgTmaPlan w;
   memset(&w, 0, sizeof(w));
-  Plan f = make_plan(d, false, num_sms);
+  Plan f = ffpn_tc_make_plan(d, false, num_sms);
   if (!f.ok || d->Cout % 16 != 0 || f.p.sX != 1) return w;
   const TcParams& c = f.p;
   WgTmaParams& p = w.p;
@@ -1534,8 +1403,8 @@ int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
 namespace {
 }  // namespace
 
-bool ffpn_tc_fwd_supported(const ffpn_conv_desc* d) { return make_plan(d, false, 148).ok; }
-bool ffpn_tc_dgrad_supported(const ffpn_conv_desc* d) { return make_plan(d, true, 148).ok; }
+bool ffpn_tc_fwd_supported(const ffpn_conv_desc* d) { return ffpn_tc_make_plan(d, false, 148).ok; }
+bool ffpn_tc_dgrad_supported(const ffpn_conv_desc* d) { return ffpn_tc_make_plan(d, true, 148).ok; }
 
 size_t ffpn_tc_workspace_bytes(const ffpn_conv_desc* d) {
   const size_t taps = (size_t)d->kS * d->kW * d->kH;
@@ -1573,23 +1442,33 @@ bool encode_act_map(CUtensorMap* m, const TcParams& p, const void* x, bool nan_f
 }
 }  // namespace
 
+void ffpn_tc_pack_weights(const float* w, void* out, const ffpn_conv_desc* d, const TcParams& p, int nchunks, int KG,
+                          cudaStream_t st) {
+  const int ntaps = p.kD * p.kY * p.kX;
+  const int64_t total = (int64_t)nchunks * ntaps * p.Cin * p.Npad;
+  const int g = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
+  pack_weights_kernel<<<g, 256, 0, st>>>(w, (bf16*)out, d->Cout, d->Cin, ntaps, p.Cin, p.Cout, p.Npad, KG, nchunks, p.packmode,
+                                         d->sH, d->pH, d->kH, -p.pX);
+}
+
+int ffpn_conv_fwd_ws(ffpn_ctx*, const ffpn_conv_desc*, bool transposed, const void*, const float*, const float*, int, const float*,
+                     const void* addend, void*, float*, int*, void*, size_t, cudaStream_t);
+
 int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,
                      const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
                      int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
-  Plan pl = make_plan(d, transposed, ctx->num_sms);
+  {
+    const int r = ffpn_conv_fwd_ws(ctx, d, transposed, x, in_scale, in_shift, in_relu, w, addend, y, stat_partial, stat_rows, ws, ws_bytes, st);
+    if (r >= 0) return r;                                 // handled (or failed) by the warp-specialised kernel
+  }
+  Plan pl = ffpn_tc_make_plan(d, transposed, ctx->num_sms);
   if (!pl.ok) FFPN_FAIL(ctx, "conv_tc: geometry not supported");
   TcParams& p = pl.p;
-  const int ntaps = p.kD * p.kY * p.kX;
   const size_t need = (size_t)pl.nchunks * p.nkg * p.b_bytes;
   if (ws == nullptr || ws_bytes < need) FFPN_FAIL(ctx, "conv_tc: workspace too small (%zu < %zu)", ws_bytes, need);
   if (stat_partial != nullptr && pl.grid > FFPN_STAT_ROWS) FFPN_FAIL(ctx, "conv_tc: %d tiles exceed the statistics buffer", pl.grid);
-  {
-    const int64_t total = (int64_t)need / 2;
-    const int g = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
-    pack_weights_kernel<<<g, 256, 0, st>>>(w, (bf16*)ws, d->Cout, d->Cin, ntaps, p.Cin, p.Cout, p.Npad, p.KG, pl.nchunks,
-                                           p.packmode, d->sH, d->pH, d->kH, -p.pX);
-    FFPN_CHECK_LAUNCH(ctx, "pack_weights");
-  }
+  ffpn_tc_pack_weights(w, ws, d, p, pl.nchunks, p.KG, st);
+  FFPN_CHECK_LAUNCH(ctx, "pack_weights");
   p.x = (const bf16*)x; p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)ws;
   p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;

@@ -1,0 +1,660 @@
+// Warp-specialised tcgen05 implicit-GEMM convolution (forward and, through transposed packed weights, dgrad) for the
+// stride-1 shapes of the path.  Same formulation as conv_tc.cu (padded-flat positions, every tap = the same smem tile
+// seen through a shifted UMMA descriptor) but:
+//   * the activation tile is kept ROW-MAJOR in shared memory, [position][channels] with a 32/64/128-byte row pitch in
+//     the matching SWIZZLE_32B/64B/128B K-major layout, so ONE TMA box (inner extent = the whole channel run) stages a
+//     tile.  The hardware swizzle is a function of the absolute smem address, so a descriptor whose start address is
+//     shifted by any number of rows still reads the right data (tools/umma_probe.cu, base_offset 0);
+//   * roles are split over warps and decoupled by mbarriers: warp 0 issues TMA into a ring of stages, six warps apply
+//     the producer's BatchNorm scale/shift + ReLU in place (halo = NaN fill -> 0), warp 1 issues the MMAs (tap-outer,
+//     accumulator-block-inner so consecutive MMAs hit different TMEM tiles), eight warps drain the double-buffered
+//     TMEM accumulators, store channels-last bf16 rows (+ residual addend) and accumulate the BatchNorm partial sums
+//     in registers (N <= 32) or by warp-shuffle transposes.
+#include "ws_common.cuh"
+
+namespace {
+
+constexpr int WS_THREADS = 512;
+constexpr int WS_MAX_STAGES = 6;
+constexpr int WS_NT = 160;            // transform threads: warps 3, 12..15
+constexpr int WS_NEPI = 8;            // epilogue warps 4..11
+constexpr int WS_HDR = 3072;          // barriers, statistics
+
+struct WsParams {
+  int NB, D, Y, X, oD, oY, oX, kD, kY, kX, pD, pY, pX, hl;
+  long long outNB, outD, outY;
+  int Cin, Cout, Npad;
+  int Xp, tD, tY, L, Lr, nD, nI, Qout, tma_mode;
+  int Kc, nkg, pitch, kgu, upt;       // channels per sub-tile (= swizzle row), K-groups, row pitch, K-groups / unit, units / tile
+  int region_rows, sub_bytes, a_unit_bytes, stage_bytes, nstages, niss, nst_ring0, nst_ring1, nbuf;   // issuer warps, stages of ring 0 / 1, TMEM tile buffers
+  int w_resident;
+  unsigned b_unit_bytes, b_total_bytes, tx_bytes;
+  int colstride, tmem_cols;
+  int relu, has_aff, has_stats, has_add, dbg;   // dbg (FFPN_TC_DEBUG, timing experiments): 1 no MMA, 2 no epilogue body, 4 no TMA, 8 no transform body
+  const float* sc;
+  const float* sh;
+  const bf16* wp;
+  const bf16* addend;
+  bf16* y;
+  float* stat;
+  unsigned tapdesc[27];               // per tap: row offset of the A view in descriptor units ((rows * pitch) >> 4)
+  long long* trace;                   // FFPN_WS_TRACE: per-tile clock64 stamps of CTA 0 (debug)
+};
+
+#define WS_TRACE(slot, tl) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (tl) < 64) p.trace[(tl) * 16 + (slot)] = clock64(); } while (0)
+
+// Tile walk of a persistent CTA without divisions: tile = blockIdx.x + n * gridDim.x decomposed as (nb, dt, it).
+struct WsTile {
+  int it, dt, nb, sit, sdt, snb;
+  int d0, i0, tD_t, L_t, M_t, nmb;
+  __device__ __forceinline__ void init(const WsParams& p) {
+    int t = blockIdx.x;
+    it = t % p.nI; t /= p.nI; dt = t % p.nD; nb = t / p.nD;
+    t = gridDim.x;
+    sit = t % p.nI; t /= p.nI; sdt = t % p.nD; snb = t / p.nD;
+    derive(p);
+  }
+  __device__ __forceinline__ bool valid(const WsParams& p) const { return nb < p.NB; }
+  __device__ __forceinline__ void next(const WsParams& p) {
+    it += sit;
+    if (it >= p.nI) { it -= p.nI; dt++; }
+    dt += sdt;
+    if (dt >= p.nD) { dt -= p.nD; nb++; }
+    nb += snb;
+    derive(p);
+  }
+  __device__ __forceinline__ void derive(const WsParams& p) {
+    d0 = dt * p.tD; i0 = it * p.L;
+    tD_t = min(p.tD, p.oD - d0);
+    L_t = min(p.L, p.Qout - i0);
+    M_t = (tD_t - 1) * p.Lr + L_t;
+    nmb = (M_t + 127) >> 7;
+  }
+};
+
+// Position of one unit in the stage rings.  With two MMA issuers the stages are split into two rings (tile parity), so
+// that each issuer only ever waits on barriers whose previous phase it consumed itself.
+struct WsRing {
+  int i0, i1;
+  uint32_t ph0, ph1;
+  __device__ __forceinline__ void init() { i0 = i1 = 0; ph0 = ph1 = 0; }
+  __device__ __forceinline__ int stage(int r, const WsParams& p) const { return r + p.niss * (r ? i1 : i0); }
+  __device__ __forceinline__ uint32_t phase(int r) const { return r ? ph1 : ph0; }
+  __device__ __forceinline__ bool advance(int r, const WsParams& p) {     // true when the ring wrapped
+    if (r) { if (++i1 == p.nst_ring1) { i1 = 0; ph1 ^= 1u; return true; } }
+    else { if (++i0 == p.nst_ring0) { i0 = 0; ph0 ^= 1u; return true; } }
+    return false;
+  }
+};
+
+// NREG: 16-column chunks whose statistics are accumulated in registers (Npad == 16 * NREG); 0 = shuffle per chunk.
+template <int NREG>
+__global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ WsParams p,
+                                                                const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar0 = smem_u32(bars);
+  // full[s] @ 0, ready[s] @ 6, empty[s] @ 12, tfull[b] @ 18, tempty[b] @ 22, wbar @ 26
+  auto FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto READY = [&](int s) { return bar0 + 8u * (uint32_t)(6 + s); };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(12 + s); };
+  auto TFULL = [&](int b) { return bar0 + 8u * (uint32_t)(18 + b); };
+  auto TEMPTY = [&](int b) { return bar0 + 8u * (uint32_t)(22 + b); };
+  const uint32_t WBAR = bar0 + 8u * 26u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 240);
+  float* stat_s = reinterpret_cast<float*>(smem + 1024);
+  uint8_t* w_s = smem + WS_HDR;
+  uint8_t* stage0 = w_s + (p.w_resident ? ((p.b_total_bytes + 1023u) & ~1023u) : 0u);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: role branches become uniform branches
+  const int ntaps = p.kD * p.kY * p.kX;
+  const int n0 = blockIdx.y * p.Npad;
+  const uint8_t* wp = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)blockIdx.y * p.b_total_bytes;
+
+  if (tid == 0) {
+    for (int s = 0; s < WS_MAX_STAGES; s++) {
+      mbar_init(FULL(s), 1);
+      mbar_init(READY(s), WS_NT);
+      mbar_init(EMPTY(s), 1);
+    }
+    for (int b = 0; b < 4; b++) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), WS_NEPI); }
+    mbar_init(WBAR, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 2 * p.Npad; i += WS_THREADS) stat_s[i] = 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t buf_cols = (uint32_t)(p.tmem_cols / p.nbuf);
+
+  if (warp == 0) {
+    // ================= TMA producer (one elected lane) =================
+    if (elect_one()) {
+      if (p.w_resident) {
+        mbar_expect_tx(WBAR, p.b_total_bytes);
+        bulk_g2s(smem_u32(w_s), wp, p.b_total_bytes, WBAR);
+      }
+      WsRing ring;
+      ring.init();
+      bool wrapped0 = false, wrapped1 = false;            // first pass over a ring: its stages are free
+      WsTile tc;
+      int ptl = 0;
+      for (tc.init(p); tc.valid(p); tc.next(p), ptl++) {
+        const int r = p.niss == 2 ? (ptl & 1) : 0;
+        int c1, c2, c3;
+        if (p.tma_mode == 0) { c1 = -p.hl; c2 = tc.it * p.tY - p.pY; c3 = tc.d0; }
+        else if (p.tma_mode == 1) { c1 = tc.i0; c2 = tc.d0 - p.pD; c3 = tc.nb; }
+        else { c1 = 0; c2 = tc.i0 >> 8; c3 = 0; }
+        for (int uk = 0; uk < p.upt; uk++) {
+          const int s = ring.stage(r, p);
+          if (r ? wrapped1 : wrapped0) mbar_wait(EMPTY(s), ring.phase(r) ^ 1u);
+          if (uk == 0) WS_TRACE(0, ptl);
+          const uint32_t dst = smem_u32(stage0) + (uint32_t)s * (uint32_t)p.stage_bytes;
+          mbar_expect_tx(FULL(s), (p.dbg & 4) ? 0u : p.tx_bytes);
+          if (!(p.dbg & 4)) {
+            for (int kgi = 0; kgi < p.kgu; kgi++)
+              tma_load_4d(dst + (uint32_t)(kgi * p.sub_bytes), &tmap, (uk * p.kgu + kgi) * p.Kc, c1, c2, c3, FULL(s));
+            if (!p.w_resident) bulk_g2s(dst + (uint32_t)p.a_unit_bytes, wp + (size_t)uk * p.b_unit_bytes, p.b_unit_bytes, FULL(s));
+          }
+          if (ring.advance(r, p)) { if (r) wrapped1 = true; else wrapped0 = true; }
+        }
+        WS_TRACE(1, ptl);
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ================= MMA issuers: warp-uniform control flow (uniform datapath), one elected lane issues.  With two
+    // issuers warp 1 takes the even tiles and warp 2 the odd ones: one warp's issue overhead hides behind the other's MMAs
+    const int me = warp - 1;
+    if (me < p.niss) {
+      const bool leader = elect_one();
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | (8u << 24);
+      const uint32_t bstep = (2u * (uint32_t)p.Npad * 16u) >> 4;           // one K=16 step of the packed weights
+      const uint32_t btap = ((uint32_t)p.Kc * (uint32_t)p.Npad * 2u) >> 4;  // one (K-group, tap) block
+      const uint32_t mbstep = (128u * (uint32_t)p.pitch) >> 4;             // one 128-row accumulator block of A
+      const uint32_t a_hi = desc_sw_hi((uint32_t)p.pitch);
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, version 1, no swizzle
+      const uint32_t b_lbo = (((uint32_t)p.Npad * 16u) >> 4) << 16;
+      const int nks = p.Kc >> 4;
+      if (p.w_resident) mbar_wait(WBAR, 0);
+      int tl = 0, si = 0;
+      uint32_t ph = 0;
+      WsTile tc;
+      for (tc.init(p); tc.valid(p); tc.next(p), tl++) {
+        if (p.niss == 2 && (tl & 1) != me) continue;
+        const int buf = tl % p.nbuf, use = tl / p.nbuf;
+        if (leader) WS_TRACE(2, tl);
+        if (use >= 1) mbar_wait(TEMPTY(buf), (uint32_t)(use - 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (leader) WS_TRACE(3, tl);
+        const uint32_t d_tile = tmem_base + (uint32_t)buf * buf_cols;
+        const int nmb = (p.dbg & 1) ? 0 : tc.nmb;
+        for (int uk = 0; uk < p.upt; uk++) {
+          const int s = me + p.niss * si;
+          mbar_wait(p.has_aff ? READY(s) : FULL(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (leader && uk == 0) WS_TRACE(4, tl);
+          const uint32_t a_stage = smem_u32(stage0) + (uint32_t)s * (uint32_t)p.stage_bytes;
+          const uint32_t b_lo0 = (((p.w_resident ? smem_u32(w_s) + (uint32_t)uk * p.b_unit_bytes : a_stage + (uint32_t)p.a_unit_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+          for (int kgi = 0; kgi < p.kgu; kgi++) {
+            const uint32_t a_lo0 = (((a_stage + (uint32_t)(kgi * p.sub_bytes)) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t first_k = (uint32_t)(uk | kgi);
+            for (int tap = 0; tap < ntaps; tap++) {
+              const uint32_t a_lo1 = a_lo0 + p.tapdesc[tap];
+              const uint32_t b_lo1 = b_lo0 + (uint32_t)(kgi * ntaps + tap) * btap;
+              for (int ks = 0; ks < nks; ks++) {
+                const uint64_t bd = desc64(b_lo1 + (uint32_t)ks * bstep, b_hi);
+                const uint32_t acc = (first_k | (uint32_t)tap | (uint32_t)ks) != 0 ? 1u : 0u;
+                uint32_t a_lo = a_lo1 + (uint32_t)ks * 2u, dcol = d_tile;
+#pragma unroll 8
+                for (int mb = 0; mb < nmb; mb++) {
+                  if (leader) umma_bf16(dcol, desc64(a_lo, a_hi), bd, idesc, acc);
+                  a_lo += mbstep; dcol += (uint32_t)p.colstride;
+                }
+              }
+            }
+          }
+          if (leader) umma_commit(EMPTY(s));            // stage s may be refilled once these MMAs have read it
+          __syncwarp();
+          if (++si == (me ? p.nst_ring1 : p.nst_ring0)) { si = 0; ph ^= 1u; }
+        }
+        if (leader) { WS_TRACE(5, tl); umma_commit(TFULL(buf)); WS_TRACE(6, tl); }   // accumulators of this tile complete
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + WS_NEPI) {
+    // ================= epilogue =================
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    float ssum[NREG > 0 ? 16 * NREG : 1], ssq[NREG > 0 ? 16 * NREG : 1];
+#pragma unroll
+    for (int i = 0; i < (NREG > 0 ? 16 * NREG : 1); i++) { ssum[i] = 0.f; ssq[i] = 0.f; }
+    const int nch = NREG > 0 ? NREG : (p.Npad >> 4);
+    constexpr int BATCH = NREG == 2 ? 2 : 4;                                        // TMEM loads in flight per thread
+    const uint32_t magicLr = (uint32_t)(0x100000000ull / (uint32_t)p.Lr) + 1u;     // exact quotients for m * Lr < 2^32
+    const uint32_t magicXp = (uint32_t)(0x100000000ull / (uint32_t)p.Xp) + 1u;
+    int tl = 0;
+    WsTile tc;
+    for (tc.init(p); tc.valid(p); tc.next(p), tl++) {
+      const int buf = tl % p.nbuf;
+      if (warp == 4 && lane == 0) WS_TRACE(7, tl);
+      mbar_wait(TFULL(buf), (uint32_t)(tl / p.nbuf) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 4 && lane == 0) WS_TRACE(8, tl);
+      const uint32_t t_tile = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
+      const int my_nmb = (p.dbg & 2) ? 0 : (tc.nmb - half + 1) >> 1;               // accumulator blocks half, half + 2, ...
+      const int nitems = my_nmb * nch;
+      for (int it0 = 0; it0 < nitems; it0 += BATCH) {
+        uint32_t raw[BATCH][16];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+          const int idx = it0 + u;
+          if (idx < nitems) {
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
+            tmem_ld16_nowait(t_tile + (uint32_t)((half + 2 * mbi) * p.colstride + ch * 16), raw[u]);
+          }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+          const int idx = it0 + u;
+          if (idx < nitems) {
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
+            const int m = (half + 2 * mbi) * 128 + quad * 32 + lane;
+            const int j = p.Lr == 1 ? m : (int)__umulhi((uint32_t)m, magicLr), ii = m - j * p.Lr;
+            const int i = tc.i0 + ii;
+            const int oy = p.Xp == 1 ? i : (int)__umulhi((uint32_t)i, magicXp), ox = i - oy * p.Xp;
+            const bool valid = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX);
+            const long long opos = (long long)tc.nb * p.outNB + (long long)(tc.d0 + j) * p.outD + (long long)oy * p.outY + ox;
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[u][q]);
+            const int cbase = n0 + ch * 16;
+            if (p.has_add && valid) {
+              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + opos * p.Cout + cbase);
+#pragma unroll
+              for (int h2 = 0; h2 < 2; h2++) {
+                if (cbase + h2 * 8 < p.Cout) {
+                  const uint4 a4 = ap[h2];
+                  const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                  for (int q = 0; q < 4; q++) {
+                    v[h2 * 8 + 2 * q] += __uint_as_float(w4[q] << 16);
+                    v[h2 * 8 + 2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
+                  }
+                }
+              }
+            }
+            uint32_t packed[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+              packed[q] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            if (valid) {
+              uint4* yp = reinterpret_cast<uint4*>(p.y + opos * p.Cout + cbase);
+              if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              if (cbase + 8 < p.Cout) yp[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+            if (p.has_stats) {
+              // statistics of the stored (rounded) values
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                v[2 * q] = valid ? __uint_as_float(packed[q] << 16) : 0.f;
+                v[2 * q + 1] = valid ? __uint_as_float(packed[q] & 0xffff0000u) : 0.f;
+              }
+              if (NREG > 0) {
+                constexpr int CH = NREG > 0 ? NREG : 1;
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                  ssum[16 * (u % CH) + q] += v[q];
+                  ssq[16 * (u % CH) + q] = fmaf(v[q], v[q], ssq[16 * (u % CH) + q]);
+                }
+              } else {
+                float w2[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) w2[q] = v[q] * v[q];
+                const float a = warp_transpose_sum16(v, lane);
+                const float b = warp_transpose_sum16(w2, lane);
+                if ((lane & 1) == 0) {
+                  const int c = ch * 16 + transpose_sum_channel(lane);
+                  atomicAdd(&stat_s[c], a);
+                  atomicAdd(&stat_s[p.Npad + c], b);
+                }
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (warp == 4 && lane == 0) WS_TRACE(9, tl);
+      if (lane == 0) mbar_arrive(TEMPTY(buf));
+    }
+    if (NREG > 0 && p.has_stats) {
+#pragma unroll
+      for (int ch = 0; ch < (NREG > 0 ? NREG : 1); ch++) {
+        float a[16], b[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) { a[q] = ssum[16 * ch + q]; b[q] = ssq[16 * ch + q]; }
+        const float ta = warp_transpose_sum16(a, lane);
+        const float tb = warp_transpose_sum16(b, lane);
+        if ((lane & 1) == 0) {
+          const int c = ch * 16 + transpose_sum_channel(lane);
+          atomicAdd(&stat_s[c], ta);
+          atomicAdd(&stat_s[p.Npad + c], tb);
+        }
+      }
+    }
+  } else {
+    // ================= in-place BatchNorm scale/shift + ReLU of landed tiles =================
+    if (p.has_aff) {
+      const int tix = warp < 4 ? tid - 96 : tid - 384 + 32;        // 0..159
+      const int cpu = p.kgu * (p.Kc >> 3);                         // 16-byte channel chunks per row of a unit
+      const int rstep = WS_NT / cpu;
+      const bool active = tix < rstep * cpu;
+      const int c = tix % cpu, r0 = tix / cpu;
+      const int kgi = c / (p.Kc >> 3), cc = c % (p.Kc >> 3);
+      const uint32_t cmask = (uint32_t)(p.Kc >> 3) - 1u;
+      float s[8], h[8];
+      WsRing ring;
+      ring.init();
+      bool loaded = false;
+      WsTile tc;
+      int ttl = 0;
+      for (tc.init(p); tc.valid(p); tc.next(p), ttl++) {
+        const int r = p.niss == 2 ? (ttl & 1) : 0;
+        for (int uk = 0; uk < p.upt; uk++) {
+          if (active && (!loaded || p.upt > 1)) {
+            const int cofs = (uk * p.kgu + kgi) * p.Kc + cc * 8;
+            const float4 s0 = *reinterpret_cast<const float4*>(p.sc + cofs), s1 = *reinterpret_cast<const float4*>(p.sc + cofs + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(p.sh + cofs), h1 = *reinterpret_cast<const float4*>(p.sh + cofs + 4);
+            s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+            h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+            loaded = true;
+          }
+          const int st = ring.stage(r, p);
+          mbar_wait(FULL(st), ring.phase(r));
+          if (tix == 0 && uk == 0) WS_TRACE(10, ttl);
+          if (active && !(p.dbg & 8)) {
+            uint8_t* base = stage0 + (size_t)st * p.stage_bytes + (size_t)kgi * p.sub_bytes;
+            const uint32_t abase = smem_u32(base);                       // the swizzle is a function of the absolute address
+            int rr = r0;
+            for (; rr + 3 * rstep < p.region_rows; rr += 4 * rstep) {
+              uint4* q[4];
+              uint4 v[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const uint32_t off = (uint32_t)(rr + u * rstep) * (uint32_t)p.pitch;
+                q[u] = reinterpret_cast<uint4*>(base + off + ((((uint32_t)cc ^ ((abase + off) >> 7)) & cmask) << 4));
+                v[u] = *q[u];
+              }
+#pragma unroll
+              for (int u = 0; u < 4; u++) *q[u] = bn_relu_bf16x8(v[u], s, h, 1);
+            }
+            for (; rr < p.region_rows; rr += rstep) {
+              const uint32_t off = (uint32_t)rr * (uint32_t)p.pitch;
+              uint4* q = reinterpret_cast<uint4*>(base + off + ((((uint32_t)cc ^ ((abase + off) >> 7)) & cmask) << 4));
+              *q = bn_relu_bf16x8(*q, s, h, 1);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(READY(st));
+          if (tix == 0 && uk == p.upt - 1) WS_TRACE(11, ttl);
+          ring.advance(r, p);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (p.has_stats) {
+    for (int i = tid; i < 2 * p.Npad; i += WS_THREADS) {
+      const int which = i / p.Npad, c = i - which * p.Npad;
+      if (n0 + c < p.Cout) p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = stat_s[which * p.Npad + c];
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+struct WsPlan {
+  WsParams p;
+  Plan base;
+  size_t smem;
+  dim3 grid;
+  int nchunks;
+  bool ok;
+  int box[4];
+};
+
+WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
+  WsPlan w;
+  memset(&w, 0, sizeof(w));
+  w.base = ffpn_tc_make_plan(d, transposed, num_sms);
+  if (!w.base.ok) return w;
+  const TcParams& c = w.base.p;
+  if (c.sX != 1 || c.nsets != 1) return w;
+  WsParams& p = w.p;
+  p.NB = c.NB; p.D = c.D; p.Y = c.Y; p.X = c.X; p.oD = c.oD; p.oY = c.oY; p.oX = c.oX;
+  p.kD = c.kD; p.kY = c.kY; p.kX = c.kX; p.pD = c.pD; p.pY = c.pY; p.pX = c.pX; p.hl = c.hl;
+  p.outNB = c.outNB; p.outD = c.outD; p.outY = c.outY;
+  p.Cin = c.Cin; p.Cout = c.Cout; p.Npad = c.Npad; p.Xp = c.Xp; p.Qout = c.Qout;
+  w.nchunks = w.base.nchunks;
+  const int ntaps = p.kD * p.kY * p.kX;
+  if (ntaps > 27 || p.Cin % 16 != 0) return w;
+  const int hr = p.Xp - p.oX;
+  const int maxinner = (p.kY - 1) * p.Xp + hr;
+  static int cs16 = -1;
+  if (cs16 < 0) { const char* e = getenv("FFPN_WS_CS32"); cs16 = (e && atoi(e)) ? 0 : 1; }
+  p.colstride = (p.Npad < 32 && !cs16) ? 32 : p.Npad;
+  p.nbuf = p.colstride <= 64 ? 4 : 2;                    // TMEM tile buffers: deep enough that the MMAs never wait for the epilogue
+  int nmb_cap = (512 / p.nbuf) / p.colstride;
+  if (nmb_cap > 8) nmb_cap = 8;
+  if (nmb_cap < 1) return w;
+  const size_t budget = 227 * 1024 - WS_HDR - 1024;
+  const size_t w_total = (size_t)ntaps * p.Cin * p.Npad * 2;
+  // option list: resident weights with the widest swizzle row, then streamed weights with 64/32/16-channel K-groups
+  struct Opt { int resident, Kc; };
+  Opt opts[4];
+  int nopts = 0;
+  {
+    int kc = 64;
+    while (kc > 16 && p.Cin % kc != 0) kc >>= 1;
+    if (w_total <= 100 * 1024) opts[nopts++] = {1, kc};
+    for (int k2 = 64; k2 >= 16; k2 >>= 1)
+      if (p.Cin % k2 == 0) opts[nopts++] = {0, k2};
+  }
+  for (int oi = 0; oi < nopts; oi++) {
+    for (int want_stages = 3; want_stages >= 2; want_stages--) {
+      const int Kc = opts[oi].Kc, resident = opts[oi].resident;
+      const int nkg = p.Cin / Kc, kgu = resident ? nkg : 1, upt = resident ? 1 : nkg;
+      const int pitch = Kc * 2;
+      const size_t b_unit = (size_t)ntaps * Kc * kgu * p.Npad * 2;
+      if (!resident && b_unit > 120 * 1024) continue;
+      const size_t avail = budget - (resident ? ((w_total + 1023) & ~(size_t)1023) : 0);
+      for (int nmb = nmb_cap; nmb >= 1; nmb--) {
+        const int max_rows = nmb * 128;
+        int tD = 1, tY = 0, L = 0, Lr = 0, region = 0, mode = -1;
+        if (p.kD > 1) {
+          L = p.X < 128 ? p.X : 128; Lr = L;
+          tD = max_rows / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+          region = (tD + p.kD - 1) * L; mode = 1;
+          if (tD + p.kD - 1 > 256 || L > 256) continue;
+        } else if (p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1) {
+          if (p.X % 256 != 0) break;
+          int nblk = max_rows / 256; if (nblk < 1) continue;
+          if (nblk * 256 > p.X) nblk = p.X / 256;
+          L = nblk * 256; Lr = L; tD = 1; region = L; mode = 2;
+          if (nblk > 256) continue;
+        } else {
+          if (p.Xp > 256) break;
+          tY = max_rows / p.Xp;
+          if (tY < 1) continue;
+          if (tY >= p.oY) {
+            tY = p.oY;
+            Lr = (tY + p.kY - 1) * p.Xp;
+            tD = (max_rows - tY * p.Xp) / Lr + 1; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
+          } else {
+            Lr = (tY + p.kY - 1) * p.Xp; tD = 1;
+          }
+          L = tY * p.Xp; region = tD * Lr; mode = 0;
+          if (tY + p.kY - 1 > 256 || tD > 256) continue;
+        }
+        const int M_total = (tD - 1) * Lr + L;
+        const int nmb_t = (M_total + 127) / 128;
+        const int maxoff = (p.kD - 1) * Lr + maxinner;
+        int rows_alloc = nmb_t * 128 + maxoff;
+        if (rows_alloc < region) rows_alloc = region;
+        const size_t sub = ((size_t)rows_alloc * pitch + 1023) & ~(size_t)1023;
+        const size_t a_unit = sub * kgu;
+        const size_t stage = a_unit + (resident ? 0 : ((b_unit + 1023) & ~(size_t)1023));
+        int nst = (int)(avail / stage);
+        if (nst > WS_MAX_STAGES) nst = WS_MAX_STAGES;
+        if (nst < want_stages) continue;
+        if (nst > 4) nst = 4;
+        // two issuer warps need a stage ring each (tile parity): 2 + 2 stages, or 1 + 1 when a tile is one unit
+        p.niss = (nst >= 4 || (nst >= 2 && upt == 1)) ? 2 : 1;
+        p.nst_ring0 = p.niss == 2 ? (nst + 1) / 2 : nst;
+        p.nst_ring1 = p.niss == 2 ? nst / 2 : 0;
+        p.tD = tD; p.tY = tY; p.L = L; p.Lr = Lr; p.tma_mode = mode;
+        p.Kc = Kc; p.nkg = nkg; p.pitch = pitch; p.kgu = kgu; p.upt = upt;
+        p.region_rows = region; p.sub_bytes = (int)sub; p.a_unit_bytes = (int)a_unit; p.stage_bytes = (int)stage; p.nstages = nst;
+        p.w_resident = resident; p.b_unit_bytes = (unsigned)b_unit; p.b_total_bytes = (unsigned)w_total;
+        p.tx_bytes = (unsigned)((size_t)kgu * region * pitch + (resident ? 0 : b_unit));
+        int cols = nmb_t * p.colstride * p.nbuf, tc = 32;
+        while (tc < cols) tc <<= 1;
+        if (tc > 512) continue;
+        p.tmem_cols = tc;
+        for (int t = 0; t < ntaps; t++) {
+          const int dx = t % p.kX, dy = (t / p.kX) % p.kY, dd = t / (p.kX * p.kY);
+          p.tapdesc[t] = (unsigned)((dd * Lr + dy * p.Xp + dx - p.pX + p.hl) * pitch) >> 4;
+        }
+        p.nD = (p.oD + tD - 1) / tD;
+        p.nI = (p.Qout + L - 1) / L;
+        const int ntiles = p.NB * p.nD * p.nI;
+        int gx = num_sms / w.nchunks; if (gx < 1) gx = 1;
+        if (gx > ntiles) gx = ntiles;
+        if (gx > FFPN_STAT_ROWS) gx = FFPN_STAT_ROWS;
+        w.grid = dim3(gx, w.nchunks);
+        w.smem = WS_HDR + (resident ? ((w_total + 1023) & ~(size_t)1023) : 0) + (size_t)nst * stage;
+        w.box[0] = Kc;
+        if (mode == 0) { w.box[1] = p.Xp; w.box[2] = tY + p.kY - 1; w.box[3] = tD; }
+        else if (mode == 1) { w.box[1] = L; w.box[2] = tD + p.kD - 1; w.box[3] = 1; }
+        else { w.box[1] = 256; w.box[2] = L / 256; w.box[3] = 1; }
+        w.ok = true;
+        return w;
+      }
+    }
+  }
+  return w;
+}
+
+bool encode_ws_map(CUtensorMap* m, const WsPlan& w, const void* x, bool nan_fill) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const WsParams& p = w.p;
+  const TcParams& c = w.base.p;
+  const cuuint64_t cb = (cuuint64_t)p.Cin * 2;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], es[4] = {1, 1, 1, 1};
+  dims[0] = (cuuint64_t)p.Cin;
+  if (p.tma_mode == 0) {
+    dims[1] = p.X; dims[2] = p.Y; dims[3] = p.D;
+    strides[0] = cb; strides[1] = (cuuint64_t)(p.Y == 1 ? p.X : c.inY) * cb; strides[2] = (cuuint64_t)c.inD * cb;
+  } else if (p.tma_mode == 1) {
+    dims[1] = p.X; dims[2] = p.D; dims[3] = p.NB;
+    strides[0] = cb; strides[1] = (cuuint64_t)c.inD * cb;
+    strides[2] = (cuuint64_t)(p.NB > 1 ? c.inNB : (long long)c.inD * p.D) * cb;
+  } else {
+    dims[1] = 256; dims[2] = p.X / 256; dims[3] = 1;
+    strides[0] = cb; strides[1] = 256 * cb; strides[2] = (cuuint64_t)p.X * cb;
+  }
+  for (int i = 0; i < 4; i++) box[i] = (cuuint32_t)w.box[i];
+  const CUtensorMapSwizzle sw = p.pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool ws_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFPN_WS"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
+
+}  // namespace
+
+// Returns 0 = launched, 1 = error (message set), -1 = geometry not handled by this kernel (caller falls back).
+int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,
+                     const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
+                     int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ws_enabled()) return -1;
+  if (in_scale != nullptr && !in_relu) return -1;                       // NaN-fill halo needs the ReLU
+  WsPlan pl = make_ws_plan(d, transposed, ctx->num_sms);
+  if (!pl.ok) return -1;
+  WsParams& p = pl.p;
+  const size_t need = (size_t)pl.nchunks * p.b_total_bytes;
+  if (ws == nullptr || ws_bytes < need) return -1;
+  CUtensorMap tmap;
+  if (!encode_ws_map(&tmap, pl, x, in_scale != nullptr)) return -1;
+  {
+    TcParams q = pl.base.p;                                             // geometry + packmode of the shared packer
+    ffpn_tc_pack_weights(w, ws, d, q, pl.nchunks, p.Kc, st);
+    FFPN_CHECK_LAUNCH(ctx, "pack_weights");
+  }
+  p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)ws; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
+  { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_ws: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  {
+    static int verbose = -1;
+    if (verbose < 0) { const char* e = getenv("FFPN_WS_VERBOSE"); verbose = e ? atoi(e) : 0; }
+    if (verbose)
+      fprintf(stderr, "conv_ws %s: Cin %d Cout %d Npad %d taps %dx%dx%d mode %d tD %d tY %d L %d Lr %d rows %d Kc %d kgu %d upt %d resident %d "
+              "stages %d (issuers %d) stage_bytes %d smem %zu tmem %d x%d grid (%u,%u) tiles %d\n", transposed ? "dgrad" : "fwd", p.Cin, p.Cout, p.Npad, p.kD,
+              p.kY, p.kX, p.tma_mode, p.tD, p.tY, p.L, p.Lr, p.region_rows, p.Kc, p.kgu, p.upt, p.w_resident, p.nstages, p.niss, p.stage_bytes,
+              pl.smem, p.tmem_cols, p.nbuf, pl.grid.x, pl.grid.y, p.NB * p.nD * p.nI);
+  }
+  static int trace_mode = -1;
+  if (trace_mode < 0) { const char* e = getenv("FFPN_WS_TRACE"); trace_mode = e ? atoi(e) : 0; }
+  p.trace = nullptr;
+  if (trace_mode) {
+    cudaMalloc(&p.trace, 64 * 16 * sizeof(long long));
+    cudaMemset(p.trace, 0, 64 * 16 * sizeof(long long));
+  }
+  const int nreg = (p.has_stats && p.Npad == 16) ? 1 : (p.has_stats && p.Npad == 32) ? 2 : 0;
+  if (nreg == 1) conv_ws_kernel<1><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
+  else if (nreg == 2) conv_ws_kernel<2><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
+  else conv_ws_kernel<0><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
+  FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_ws" : "conv_fwd_ws");
+  if (trace_mode) {
+    static long long h[64 * 16];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    const long long t0 = h[2];
+    fprintf(stderr, "tile: prod[emptyOK issued] mma[top temptyOK fullOK issued committed] epi[top tfullOK done] xf[fullOK done]  (cycles since MMA top of tile 0)\n");
+    for (int t = 0; t < 64 && h[t * 16 + 2]; t++) {
+      fprintf(stderr, "%2d:", t);
+      for (int k = 0; k < 12; k++) fprintf(stderr, " %7lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+    trace_mode = 0;
+  }
+  if (stat_rows) *stat_rows = (int)pl.grid.x;
+  return 0;
+}
