@@ -1363,8 +1363,16 @@ bool encode_map4(CUtensorMap* m, const void* base, const long long* dims, const 
 
 bool ffpn_tc_wgrad_supported(const ffpn_conv_desc* d) { return make_wgrad_plan(d, 148).ok; }
 
+size_t ffpn_wgrad_ws_workspace_bytes(const ffpn_conv_desc* d);
+int ffpn_conv_wgrad_ws(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const void*, float*, void*, size_t,
+                       cudaStream_t);
+
 int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale, const float* in_shift,
-                       int in_relu, const void* dy, float* dw, void*, size_t, cudaStream_t st) {
+                       int in_relu, const void* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
+  {
+    const int r = ffpn_conv_wgrad_ws(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, ws, ws_bytes, st);
+    if (r >= 0) return r;                                 // handled (or failed) by the warp-specialised kernel
+  }
   static bool attr_tma = false;
   if (!(in_scale != nullptr && !in_relu)) {
     WgTmaPlan t = make_wgrad_tma_plan(d, ctx->num_sms);
@@ -1406,10 +1414,12 @@ namespace {
 bool ffpn_tc_fwd_supported(const ffpn_conv_desc* d) { return ffpn_tc_make_plan(d, false, 148).ok; }
 bool ffpn_tc_dgrad_supported(const ffpn_conv_desc* d) { return ffpn_tc_make_plan(d, true, 148).ok; }
 
+size_t ffpn_wgrad_ws_workspace_bytes(const ffpn_conv_desc* d);
 size_t ffpn_tc_workspace_bytes(const ffpn_conv_desc* d) {
   const size_t taps = (size_t)d->kS * d->kW * d->kH;
   const size_t cin = (d->Cin + 63) & ~63, cout = (d->Cout + 63) & ~63;
-  return taps * cin * cout * 2 + 65536;
+  const size_t pack = taps * cin * cout * 2 + 65536, wg = ffpn_wgrad_ws_workspace_bytes(d);   // packed weights | wgrad partial tiles
+  return pack > wg ? pack : wg;
 }
 
 namespace {

@@ -17,7 +17,11 @@ static __device__ __forceinline__ uint32_t desc_sw_hi(uint32_t pitch) {
   const uint32_t ltype = pitch == 128 ? 2u : pitch == 64 ? 4u : 6u;
   return ((8u * pitch) >> 4) | (1u << 14) | (ltype << 29);
 }
-static __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+static __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));   // pure register pairing, no arithmetic
+  return d;
+}
 
 // Sum v[0..15] over the 32 lanes of a warp with a transpose-reduce (16 shuffles): afterwards lanes with even index hold,
 // in v[0], the total of channel ch = 8*b4 + 4*b3 + 2*b2 + b1 (bN = bit N of the lane index).

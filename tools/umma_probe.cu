@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) probe_kernel(Probe p, float* out, long lo
 
 // Mode 3: hardware MMA rate with a lean, warp-uniform issue loop (8 MMAs unrolled, compile-time accumulator rotation).
 template <int NACC>
-__global__ void __launch_bounds__(128) rate_kernel(int sw, int M, int N, int nmma, int astep, long long* cyc) {
+__global__ void __launch_bounds__(128) rate_kernel(int sw, int M, int N, int nmma, int astep, long long* cyc, int mn = 0, int lboA = 0, int lboB = 0, int swB = 0) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -196,13 +196,20 @@ __global__ void __launch_bounds__(128) rate_kernel(int sw, int M, int N, int nmm
     const uint64_t adesc0 = sw ? ((uint64_t)((abase & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * sw) >> 4) << 32) | (1ull << 46) | (ltype << 61))
                                : ((uint64_t)((abase & 0x3FFFFu) >> 4) | ((uint64_t)((1024 * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46));
     const uint64_t bdesc = (uint64_t)((bbase & 0x3FFFFu) >> 4) | ((uint64_t)((N * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     const uint32_t cs = N < 32 ? 32 : N;
+    uint64_t adesc0m = adesc0, bdescm = bdesc;
+    if (mn) {   // both operands MN-major swizzled: LBO = slab stride, SBO = 8 rows
+      const uint64_t ltB = swB == 128 ? 2ull : swB == 64 ? 4ull : 6ull;
+      adesc0m = (uint64_t)((abase & 0x3FFFFu) >> 4) | ((uint64_t)((uint32_t)lboA >> 4) << 16) | ((uint64_t)((8 * sw) >> 4) << 32) | (1ull << 46) | (ltype << 61);
+      bdescm = (uint64_t)(((abase + 49152u) & 0x3FFFFu) >> 4) | ((uint64_t)((uint32_t)lboB >> 4) << 16) | ((uint64_t)((8 * swB) >> 4) << 32) | (1ull << 46) | (ltB << 61);
+      idesc |= (1u << 15) | (1u << 16);
+    }
     const long long t0 = clock64();
     for (int i = 0; i < nmma; i += 8) {
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        if (pred) umma_bf16(tmem + (uint32_t)((j % NACC) * cs), adesc0 + (uint64_t)(j * astep), bdesc, idesc, i ? 1u : 0u);
+        if (pred) umma_bf16(tmem + (uint32_t)((j % NACC) * cs), adesc0m + (uint64_t)(j * astep), bdescm + (uint64_t)(mn ? j * astep : 0), idesc, i ? 1u : 0u);
       }
     }
     if (pred) umma_commit(smem_u32(&bar));
@@ -338,6 +345,24 @@ int main() {
       printf("  nacc %d: %6.1f", nacc, (double)c / 4096);
     }
     printf("\n");
+  }
+  printf("== mode 3b: MN-major (wgrad) shapes, cycles per MMA ==\n");
+  struct Q { int sw, M, N, astep, lboA, lboB, swB; const char* name; };
+  const Q qs[] = {{32, 64, 48, 32, 32, 130 * 32, 32, "M64 N48 SW32/SW32 (L1: 4 dx slabs x 3 line slabs)"},
+                  {32, 64, 16, 32, 32, 130 * 32, 32, "M64 N16 SW32/SW32"},
+                  {32, 128, 48, 32, 32, 130 * 32, 32, "M128 N48 SW32/SW32"},
+                  {64, 128, 96, 64, 64, 66 * 64, 64, "M128 N96 SW64/SW64 (L2)"},
+                  {128, 128, 192, 128, 128, 34 * 128, 128, "M128 N192 SW128/SW128 (L3)"},
+                  {128, 128, 64, 128, 128, 34 * 128, 128, "M128 N64 SW128/SW128"},
+                  {128, 128, 128, 128, 16384, 16384, 128, "M128 N128 SW128 sub-tile slabs (L4)"},
+                  {128, 128, 256, 128, 16384, 8192, 128, "M128 N256 SW128 sub-tile slabs (L5)"}};
+  for (const Q& q : qs) {
+    rate_kernel<1><<<1, 128, smem>>>(q.sw, q.M, q.N, 4096, q.astep, cyc, 1, q.lboA, q.lboB, q.swB);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+    long long c;
+    cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%-52s: %6.1f\n", q.name, (double)c / 4096);
   }
   return 0;
 }
