@@ -44,53 +44,62 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled from a
+    thread every 10 ms (nvidia-smi -lms takes longer to start than a short timed region lasts); falls back to one
+    nvidia-smi query if NVML is unavailable."""
+    REASONS = (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40), ('sw_power_cap', 0x4))
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.path = gpu_index, None, None
+        self.idx, self.samples, self.reasons, self.max_mhz = gpu_index, [], set(), None
+        self._stop, self._thread, self._nvml = threading.Event(), None, None
+
+    def _poll(self):
+        nv, h = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
-            f = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False)
-            self.path = f.name
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms',
-                                          '100', '-i', str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[self.idx]) if visible and visible.split(',')[self.idx].isdigit() else self.idx
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._nvml = (nv, h)
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nvml = None
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        if self.proc is None:
-            out['reasons'] = ['nvidia-smi unavailable']
-            return out
-        self.proc.terminate()
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            if self.samples:
+                sm = sorted(self.samples)
+                out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(sm),
+                           source='nvml, 10 ms poll during the timed region')
+                return out
         try:
-            self.proc.wait(timeout=5)
+            q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+                 'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+            r = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.idx)],
+                               capture_output=True, text=True, timeout=10).stdout.strip().split(',')
+            out.update(sm_mhz=float(r[0]), sm_max_mhz=float(r[1]), samples=1, source='nvidia-smi, one query after the timed region',
+                       reasons=[n for n, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6])
+                                if v.strip().lower().startswith('active')])
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            with open(self.path) as f:
-                for line in f:
-                    c = [x.strip() for x in line.split(',')]
-                    if len(c) < 9:
-                        continue
-                    try:
-                        sm.append(float(c[1])); mx.append(float(c[2]))
-                    except ValueError:
-                        continue
-                    for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
-                        if v.lower().startswith('active'):
-                            reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out['reasons'] = ['clock query unavailable']
         return out
 
 
@@ -99,7 +108,11 @@ def cpu_reference_rate(steps, warmup, threads=None):
     Each step = forward + Mix loss + backward of ONE sample of the workload shape."""
     import torch
     from oracle import fusion_fpn_oracle as O
-    threads = threads or os.cpu_count()
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count()
+    threads = threads or avail
     torch.set_num_threads(threads)
     w = WORKLOAD
     sd = O.make_state_dict(seed=1234)
@@ -160,6 +173,17 @@ def kernel_roofline(torch, ops, peak_gbs, peak_src, iters=20):
     t = timeit(lambda: ops.conv_fwd(x, wz, (1, 1, 3), (1, 1, 2), (0, 0, 1), sc, sh, True))
     res.append(dict(kernel='projection conv (1,1,3) s(1,1,2) 16->16 level-1', bytes=int(x.numel() * 2 * 1.5), sec=t))
     y = torch.randn_like(x)
+    dw = torch.zeros_like(wt)
+    t = timeit(lambda: ops.conv_wgrad(x, y, wt.shape, (1, 3, 3), (1, 1, 1), (0, 1, 1), sc, sh, True, out=dw))
+    res.append(dict(kernel='conv_wgrad (1,3,3) 16->16 level-1 (BN+ReLU on load, all 9 taps per MMA) + partial-tile reduce', bytes=nbytes, sec=t))
+    t = timeit(lambda: ops.conv_dgrad(y, wt, tuple(x.shape), (1, 3, 3), (1, 1, 1), (0, 1, 1)))
+    res.append(dict(kernel='conv_dgrad (1,3,3) 16->16 level-1', bytes=nbytes, sec=t))
+    for lvl, Cl in ((2, 32), (3, 64)):
+        xl = torch.randn(B, S, W_ >> (lvl - 1), H >> (lvl - 1), Cl, device='cuda', generator=g).to(dt)
+        wl = torch.randn(Cl, Cl, 1, 3, 3, device='cuda', generator=g) * 0.05
+        scl = torch.ones(Cl, device='cuda'); shl = torch.zeros(Cl, device='cuda')
+        t = timeit(lambda: ops.conv_fwd(xl, wl, (1, 3, 3), (1, 1, 1), (0, 1, 1), scl, shl, True))
+        res.append(dict(kernel=f'conv_fwd (1,3,3) {Cl}->{Cl} level-{lvl}', bytes=2 * xl.numel() * 2, sec=t))
     t = timeit(lambda: ops.block_end_fwd(y, sc, sh, x))
     res.append(dict(kernel='block_end_fwd (BN apply + residual + ReLU) level-1', bytes=3 * x.numel() * 2, sec=t))
     t = timeit(lambda: ops.bn_bwd_reduce(y, x, sc, sh, True))
@@ -280,8 +304,13 @@ def main():
         if not args.no_kernel_roofline:
             ks = kernel_roofline(torch, ops, peak, src)
             top = ks[0]
+            traffic = None                                  # dram bytes per launch from the committed ncu --set full capture
+            tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    traffic = json.load(f).get('conv_fwd_l1_dram_bytes_per_launch')
             line['roofline'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['gbs'], 'peak': peak, 'unit': 'GB/s',
-                                'frac': top['frac'], 'traffic': None, 'peak_source': src,
+                                'frac': top['frac'], 'traffic': traffic, 'peak_source': src,
                                 'algorithmic_bytes_per_launch': top['bytes'], 'sec_per_launch': top['sec']}
             line['kernels'] = [{k: r[k] for k in ('kernel', 'gbs', 'frac', 'sec', 'bytes')} for r in ks]
             # whole-step roofline: conv-boundary traffic model of SURVEY.md section 8d (bf16, fwd+bwd = 3 x fwd)

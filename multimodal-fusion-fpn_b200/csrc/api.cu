@@ -1,4 +1,6 @@
 // C-ABI entry points that are not defined next to their kernels: ctx lifetime and the convolution dispatcher.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 int ffpn_conv_fwd_simt(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const float*,
@@ -97,5 +99,8 @@ extern "C" int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const voi
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_wgrad: tcgen05 kernel does not support this geometry");
   if (tc_ok && d->impl != 1)
     return ffpn_conv_wgrad_tc(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, ws, ws_bytes, (cudaStream_t)stream);
+  if (d->dtype == FFPN_BF16 && getenv("FFPN_VERBOSE_FALLBACK"))
+    fprintf(stderr, "conv_wgrad -> CUDA-core kernel: B %lld S %lld W %lld H %lld Cin %d Cout %d k %dx%dx%d s %dx%dx%d p %dx%dx%d\n", (long long)d->B,
+            (long long)d->S, (long long)d->W, (long long)d->H, d->Cin, d->Cout, d->kS, d->kW, d->kH, d->sS, d->sW, d->sH, d->pS, d->pW, d->pH);
   return ffpn_conv_wgrad_simt(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, (cudaStream_t)stream);
 }

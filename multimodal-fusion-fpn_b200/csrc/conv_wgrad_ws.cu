@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
   }
 }
 
-// Sum the per-CTA partial tiles (fixed order) and write dW in the state_dict layout [Cout][Cin][taps].
+// Sum the per-CTA partial tiles (fixed order) and add them to dW in the state_dict layout [Cout][Cin][taps].
 __global__ void wgrad_reduce_kernel(const WgWsParams p, float* __restrict__ dw) {
   const int64_t total = (int64_t)p.Cout * p.Cin * p.ntaps;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -291,7 +291,7 @@ __global__ void wgrad_reduce_kernel(const WgWsParams p, float* __restrict__ dw) 
     int k = 0;
     for (; k + 1 < p.gx; k += 2) { s0 += src[(size_t)k * stride]; s1 += src[(size_t)(k + 1) * stride]; }
     if (k < p.gx) s0 += src[(size_t)k * stride];
-    dw[((size_t)co * p.Cin + ci) * p.ntaps + tap] = s0 + s1;
+    dw[((size_t)co * p.Cin + ci) * p.ntaps + tap] += s0 + s1;       // accumulate contract of ffpn_conv_wgrad (dw zeroed by the caller)
   }
 }
 
@@ -330,15 +330,16 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
   p.M = p.co_t == 16 ? 64 : 128;
   p.sA = p.co_t <= 64 ? (p.M / p.co_t < p.kA ? p.M / p.co_t : p.kA) : 1;
   p.passesA = (p.kA + p.sA - 1) / p.sA;
-  p.ci_t = p.Cin < 256 ? p.Cin : 256;
-  if (p.Cin % p.ci_t != 0) { p.ci_t = 128; if (p.Cin % 128 != 0) p.ci_t = 64; }
+  for (int ci_cand = p.Cin < 256 ? p.Cin : 256; ci_cand >= 16; ci_cand = (ci_cand > 64 ? (ci_cand > 128 ? 128 : 64) : 0)) {
+  if (p.Cin % ci_cand != 0) continue;
+  p.ci_t = ci_cand;
   p.n_ci = p.Cin / p.ci_t;
   p.Cx = p.ci_t < 64 ? p.ci_t : 64; p.nxs = p.ci_t / p.Cx; p.pitch_x = p.Cx * 2;
   p.sB = (p.ci_t <= 64 && p.kB > 1 && p.ci_t * p.kB <= 256) ? p.kB : 1;
   p.passesB = p.kB / p.sB;
   p.N = p.sB * p.ci_t; p.colsN = p.N;
   p.nacc_total = p.passesA * p.passesB;
-  if (p.nacc_total > WG2_MAX_ACC) return w;
+  if (p.nacc_total > WG2_MAX_ACC) continue;
   {
     const int cap = 512 / p.colsN;
     p.npg = (p.nacc_total + cap - 1) / cap;
@@ -413,6 +414,7 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
       w.ok = true;
       return w;
     }
+  }
   }
   return w;
 }

@@ -18,7 +18,7 @@ constexpr int WS_THREADS = 512;
 constexpr int WS_MAX_STAGES = 6;
 constexpr int WS_NT = 160;            // transform threads: warps 3, 12..15
 constexpr int WS_NEPI = 8;            // epilogue warps 4..11
-constexpr int WS_HDR = 3072;          // barriers, statistics
+constexpr int WS_HDR = 1024 + 8 * 2 * 256 * 4;   // barriers, then one statistics slot per epilogue warp (fixed-order sum: deterministic)
 
 struct WsParams {
   int NB, D, Y, X, oD, oY, oX, kD, kY, kX, pD, pY, pX, hl;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     mbar_init(WBAR, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 2 * p.Npad; i += WS_THREADS) stat_s[i] = 0.f;
+  for (int i = tid; i < WS_NEPI * 2 * p.Npad; i += WS_THREADS) stat_s[i] = 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)p.tmem_cols));
@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   } else if (warp >= 4 && warp < 4 + WS_NEPI) {
     // ================= epilogue =================
     const int quad = warp & 3, half = (warp - 4) >> 2;
+    float* my_stat = stat_s + (warp - 4) * 2 * p.Npad;            // this warp's own slot: plain read-modify-write, no atomics
     float ssum[NREG > 0 ? 16 * NREG : 1], ssq[NREG > 0 ? 16 * NREG : 1];
 #pragma unroll
     for (int i = 0; i < (NREG > 0 ? 16 * NREG : 1); i++) { ssum[i] = 0.f; ssq[i] = 0.f; }
@@ -322,8 +323,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                 const float b = warp_transpose_sum16(w2, lane);
                 if ((lane & 1) == 0) {
                   const int c = ch * 16 + transpose_sum_channel(lane);
-                  atomicAdd(&stat_s[c], a);
-                  atomicAdd(&stat_s[p.Npad + c], b);
+                  my_stat[c] += a;
+                  my_stat[p.Npad + c] += b;
                 }
               }
             }
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         const float tb = warp_transpose_sum16(b, lane);
         if ((lane & 1) == 0) {
           const int c = ch * 16 + transpose_sum_channel(lane);
-          atomicAdd(&stat_s[c], ta);
-          atomicAdd(&stat_s[p.Npad + c], tb);
+          my_stat[c] += ta;
+          my_stat[p.Npad + c] += tb;
         }
       }
     }
@@ -415,7 +416,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   if (p.has_stats) {
     for (int i = tid; i < 2 * p.Npad; i += WS_THREADS) {
       const int which = i / p.Npad, c = i - which * p.Npad;
-      if (n0 + c < p.Cout) p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = stat_s[which * p.Npad + c];
+      float t = 0.f;
+#pragma unroll
+      for (int e = 0; e < WS_NEPI; e++) t += stat_s[e * 2 * p.Npad + i];
+      if (n0 + c < p.Cout) p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = t;
     }
   }
   if (warp == 1) {

@@ -25,6 +25,23 @@ def get_compute_dtype() -> torch.dtype:
     return _COMPUTE_DTYPE
 
 
+# ---- gradient sink -------------------------------------------------------------------------------------
+# FusionTrainer keeps all gradients in one flat fp32 buffer that is zeroed once per step.  When it installs the
+# sink (parameter data_ptr -> gradient view), the backward kernels write weight / BatchNorm gradients straight into
+# that buffer and the Functions return None for them, instead of autograd allocating a tensor per parameter and
+# launching one `grad += new` kernel each (~350 tiny launches per step).
+_GRAD_SINK = {}
+
+
+def set_grad_sink(mapping) -> None:
+    global _GRAD_SINK
+    _GRAD_SINK = dict(mapping) if mapping else {}
+
+
+def _sink(t):
+    return _GRAD_SINK.get(t.data_ptr()) if _GRAD_SINK else None
+
+
 # ---- layout helpers ------------------------------------------------------------------------------------
 def to_phys(x: torch.Tensor) -> torch.Tensor:
     """logical (B,C,S,W,H) / (B,C,S,W) -> physical (B,S,W,H,C) contiguous in the compute dtype."""
@@ -151,12 +168,14 @@ class ConvXFunction(torch.autograd.Function):
         if spec.tail == 'mean':
             dA = ops.proj_tail_bwd(dz_p, y_last.shape)
             partial, rows = ops.bn_bwd_reduce(dA, y_last, affs[-1][0], affs[-1][1], True)
-            dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, 2, 1, count, g_last, affs[-1][2], affs[-1][3])
+            dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, 2, 1, count, g_last, affs[-1][2], affs[-1][3],
+                                                     _sink(g_last), _sink(tensors[5 * (k - 1) + 2]))
             dy = ops.bn_bwd_apply(dA, y_last, affs[-1][0], affs[-1][1], True, cA, cP, cQ, out=dA)
             G = None
         else:
             G, partial, rows, ncols = ops.block_end_bwd(dz_p, dzp_p, z, y_last, yd, spec.pool)
-            dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 1, count, g_last, affs[-1][2], affs[-1][3])
+            dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 1, count, g_last, affs[-1][2], affs[-1][3],
+                                                     _sink(g_last), _sink(tensors[5 * (k - 1) + 2]))
             dy = ops.bn_bwd_apply(G, y_last, affs[-1][0], affs[-1][1], False, cA, cP, cQ)
         grads[5 * (k - 1) + 1], grads[5 * (k - 1) + 2] = dg, db
         # shortcut branch
@@ -165,9 +184,9 @@ class ConvXFunction(torch.autograd.Function):
             if yd is not None:
                 wd, gd = tensors[5 * k], tensors[5 * k + 1]
                 dgd, dbd, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 2, yd.numel() // yd.shape[-1], gd,
-                                                           affd[2], affd[3])
+                                                           affd[2], affd[3], _sink(gd), _sink(tensors[5 * k + 2]))
                 dyd = ops.bn_bwd_apply(G, yd, affd[0], affd[1], False, cA, cP, cQ)
-                grads[5 * k] = ops.conv_wgrad(xp, dyd, wd.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0))
+                grads[5 * k] = ops.conv_wgrad(xp, dyd, wd.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0), out=_sink(wd))
                 grads[5 * k + 1], grads[5 * k + 2] = dgd, dbd
                 if spec.need_dx:
                     dx_short = ops.conv_dgrad(dyd, wd, xp.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0))
@@ -182,13 +201,14 @@ class ConvXFunction(torch.autograd.Function):
             else:
                 inp, a_in, b_in = xp, None, None
             grads[5 * i] = ops.conv_wgrad(inp, dy, w.shape, spec.kernels[i], spec.strides[i], spec.pads[i], a_in, b_in,
-                                          i > 0)
+                                          i > 0, out=_sink(w))
             if i > 0:
                 dA = ops.conv_dgrad(dy, w, inp.shape, spec.kernels[i], spec.strides[i], spec.pads[i])
                 cnt = inp.numel() // inp.shape[-1]
                 partial, rows = ops.bn_bwd_reduce(dA, inp, a_in, b_in, True)
                 dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, 2, 1, cnt, tensors[5 * (i - 1) + 1],
-                                                         affs[i - 1][2], affs[i - 1][3])
+                                                         affs[i - 1][2], affs[i - 1][3], _sink(tensors[5 * (i - 1) + 1]),
+                                                         _sink(tensors[5 * (i - 1) + 2]))
                 grads[5 * (i - 1) + 1], grads[5 * (i - 1) + 2] = dg, db
                 dy = ops.bn_bwd_apply(dA, inp, a_in, b_in, True, cA, cP, cQ, out=dA)
             elif spec.need_dx:

@@ -95,14 +95,16 @@ def conv_dgrad(dy, w, x_shape, kernel, stride, pad, addend=None):
     return dx
 
 
-def conv_wgrad(x, dy, w_shape, kernel, stride, pad, in_scale=None, in_shift=None, in_relu=False):
+def conv_wgrad(x, dy, w_shape, kernel, stride, pad, in_scale=None, in_shift=None, in_relu=False, out=None):
+    """dW of the convolution.  The kernels ACCUMULATE into dw: ``out`` (a zero-initialised or partially accumulated
+    fp32 gradient view) receives the sum and None is returned; otherwise a fresh zeroed tensor is used and returned."""
     _chk(x, 'x'); _chk(dy, 'dy')
     d = make_desc(x.shape, w_shape[0], kernel, stride, pad, x.dtype)
-    dw = torch.zeros(tuple(w_shape), dtype=torch.float32, device=x.device)
+    dw = out if out is not None else torch.zeros(tuple(w_shape), dtype=torch.float32, device=x.device)
     ws, nws = _workspace(d, x)
     lib.call('ffpn_conv_wgrad', _dev(x), C.byref(d), _ptr(x), _ptr(in_scale), _ptr(in_shift), int(bool(in_relu)), _ptr(dy),
              _ptr(dw), _ptr(ws), nws, _stream(x))
-    return dw
+    return None if out is not None else dw
 
 
 def bn_finalize(partial, rows, count, gamma, beta, running_mean, running_var, momentum, eps, training):
@@ -125,14 +127,17 @@ def bn_bwd_reduce(dA, y, scale, shift, relu):
     return partial, rows.value
 
 
-def bn_bwd_finalize(partial, rows, ncols, ycol, count, gamma, save_mean, save_invstd):
-    """-> (dgamma, dbeta, cA, cP, cQ)"""
+def bn_bwd_finalize(partial, rows, ncols, ycol, count, gamma, save_mean, save_invstd, dgamma_out=None, dbeta_out=None):
+    """-> (dgamma, dbeta, cA, cP, cQ); dgamma / dbeta are written into the given gradient views instead (and returned
+    as None) when those are supplied."""
     C_ = gamma.numel()
     out = torch.empty(5, C_, dtype=torch.float32, device=gamma.device)
+    dg = dgamma_out if dgamma_out is not None else out[0]
+    db = dbeta_out if dbeta_out is not None else out[1]
     lib.call('ffpn_bn_bwd_finalize', _dev(gamma), _ptr(partial), rows, ncols, ycol, C_, float(count), _ptr(gamma),
-             _ptr(save_mean), _ptr(save_invstd), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(out[4]),
+             _ptr(save_mean), _ptr(save_invstd), _ptr(dg), _ptr(db), _ptr(out[2]), _ptr(out[3]), _ptr(out[4]),
              _stream(gamma))
-    return out[0], out[1], out[2], out[3], out[4]
+    return (None if dgamma_out is not None else dg), (None if dbeta_out is not None else db), out[2], out[3], out[4]
 
 
 def bn_bwd_apply(dA, y, scale, shift, relu, cA, cP, cQ, out=None):

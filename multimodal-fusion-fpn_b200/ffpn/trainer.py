@@ -53,12 +53,24 @@ class FusionTrainer:
         self._graph = None
         self._static: Optional[Dict[str, torch.Tensor]] = None
         self._static_loss = None
+        # gradient sink: backward kernels write straight into flat_g (valid while every parameter is used once per
+        # backward and flat_g is zeroed once per optimisation step; BatchNorm gradients are plain writes)
+        self._sink = {}
+        if self.accumulate == 1:
+            for p in model.parameters():
+                if p.dim() >= 1 and p.grad is not None:
+                    self._sink[p.data_ptr()] = p.grad
 
     # -- pieces ----------------------------------------------------------------------------------------
     def forward_backward(self, batch):
-        out = self.model(batch)
-        loss, _ = self.criterion(batch, out)
-        (loss / self.accumulate if self.accumulate > 1 else loss).backward()
+        from . import functional
+        functional.set_grad_sink(self._sink)
+        try:
+            out = self.model(batch)
+            loss, _ = self.criterion(batch, out)
+            (loss / self.accumulate if self.accumulate > 1 else loss).backward()
+        finally:
+            functional.set_grad_sink(None)
         return loss.detach()
 
     def optimizer_step(self):

@@ -82,6 +82,12 @@ def test_conv_tc(case):
             ys = y.float().double().reshape(-1, cout)
             assert torch.allclose(st[0], ys.sum(0), rtol=1e-3, atol=1e-3 * ys.abs().sum(0).max().item())
             assert torch.allclose(st[1], (ys * ys).sum(0), rtol=1e-3)
+            # run-to-run determinism (also a race detector for the mbarrier pipelines): same call, bitwise-equal output
+            y1, partial1, rows1 = ops.conv_fwd(phys(x).to(dt), w, k, s1, p, sc if affine else None, sh if affine else None, affine)
+            torch.cuda.synchronize()
+            assert torch.equal(y, y1)
+            if s1 == (1, 1, 1) and cin in (16, 32, 64, 128, 256, 768) and name != 'sc_111':
+                assert rows1 == rows and torch.equal(partial[:rows * 2 * cout], partial1[:rows * 2 * cout])
             ops.set_conv_impl(1)
             y2, _, _ = ops.conv_fwd(phys(x).to(dt), w, k, s1, p, sc if affine else None, sh if affine else None, affine)
             assert rel(y.float(), y2.float()) <= 1e-2
@@ -105,5 +111,9 @@ def test_conv_tc(case):
                                 sh if affine else None, affine)
             torch.cuda.synchronize()
             assert rel(dw, wr.grad) <= 1e-2, ('wgrad', affine, rel(dw, wr.grad))
+            if s1 == (1, 1, 1) and cin in (16, 32, 64, 128, 256, 768) and cout in (16, 32, 64, 128, 256) and name != 'sc_111':
+                dw1 = ops.conv_wgrad(phys(x).to(dt), phys(dy), w.shape, k, s1, p, sc if affine else None,
+                                     sh if affine else None, affine)
+                assert torch.equal(dw, dw1)                # fixed-order partial-tile reduction: bitwise reproducible
     finally:
         ops.set_conv_impl(old)

@@ -177,3 +177,50 @@ def test_training_wrapper_step(mirror):
     assert all(np.isfinite(losses)) and wrap.configure_optimizers() == [opt]
     assert 'Training/Dice' in wrap.logged and len(wrap.logged['Training/BCE']) == 3
     assert int(model.state_dict()['resensnet.conv1.0.convBlock.0.1.num_batches_tracked']) == 3
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_trainer_gradient_sink_and_fused_sgd(mirror, dtype):
+    """FusionTrainer (backward kernels writing straight into the flat gradient buffer, fused SGD kernel) against the
+    plain autograd path + torch.optim.SGD on the same weights and batch (train.py:126-133 semantics)."""
+    import ffpn
+    from ffpn.trainer import FusionTrainer
+    ffpn.set_compute_dtype(dtype)
+    sd = O.make_state_dict(seed=5)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 32, 8, 32, seed=3).items()}
+    crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                            'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+    ref = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+    ref.load_state_dict(sd, strict=True)
+    ref.train()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    loss_ref, _ = crit(batch, ref(batch))
+    loss_ref.backward()
+    g_ref = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+    opt.step()
+
+    model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    tr = FusionTrainer(model, crit, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    assert len(tr._sink) > 200                                   # conv weights and BatchNorm affine parameters
+    loss = tr.forward_backward(batch)
+    # fp32: same kernels, same data.  bf16: kernels that still reduce BatchNorm sums with float atomics (strided projection
+    # convs) may differ in the last bit run to run, and bf16 re-rounding amplifies that to ~1e-3 on the loss
+    assert abs(loss.item() - loss_ref.item()) <= (1e-6 if dtype == torch.float32 else 5e-3) * max(1.0, abs(loss_ref.item()))
+    # same kernels on the same data: the sink path must reproduce autograd's gradients up to the summation-order noise
+    # of the kernels that still accumulate with float atomics (CUDA-core fp32 path, stems, strided projection convs);
+    # the warp-specialised tcgen05 wgrad reduces its partial tiles in a fixed order and is bitwise reproducible
+    if dtype == torch.float32:
+        for k, p in model.named_parameters():
+            assert rel(p.grad, g_ref[k]) <= 2e-4, (k, rel(p.grad, g_ref[k]))
+    else:
+        fa = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()]).double()
+        fb = torch.cat([g_ref[k].reshape(-1) for k, _ in model.named_parameters()]).double()
+        assert float((fa * fb).sum() / (fa.norm() * fb.norm())) >= 0.995            # run-to-run bf16 noise only
+        assert all(float(p.grad.abs().sum()) > 0 for k, p in model.named_parameters() if p.dim() > 1)
+    tr.optimizer_step()
+    if dtype == torch.float32:
+        for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            assert rel(p.data, q.data) <= 1e-5, k
+    assert float(tr.flat_g.abs().max()) == 0.0
