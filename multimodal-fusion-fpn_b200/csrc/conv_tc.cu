@@ -511,10 +511,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     if (n < Nc) {
       if (mode == 0) v = w[((int64_t)n * Cin + k) * ntaps + tap];                       // forward
       else if (mode == 1) v = w[((int64_t)k * Cin + n) * ntaps + (ntaps - 1 - tap)];   // dgrad, stride 1
-      else {                                    // dgrad of a depth-strided (1,1,kH) conv: n = r*Cin + ci
+      else if (mode == 2) {                     // dgrad of a depth-strided (1,1,kH) conv: n = r*Cin + ci
         const int r = n / Cin, ci = n - r * Cin;
         const int dx = r + pH - sH * (tap + tmin);
         if (dx >= 0 && dx < kH) v = w[((int64_t)k * Cin + ci) * kH + dx];
+      } else {                                  // pair view of the (1,1,3) s2 p1 conv: 3 forward (k = (h,ci)), 4 dgrad (n = (h,ci))
+        const int c2 = mode == 3 ? k : n, oc = mode == 3 ? n : k;
+        const int hh = c2 / Cin, ci = c2 - hh * Cin;
+        const int tp = mode == 3 ? tap : 1 - tap;
+        const int dx = tp == 0 ? (hh == 1 ? 0 : -1) : (hh == 0 ? 1 : 2);
+        if (dx >= 0) v = w[((int64_t)oc * Cin + ci) * 3 + dx];
       }
     }
     out[i] = __float2bfloat16_rn(v);
@@ -1361,7 +1367,8 @@ bool encode_map4(CUtensorMap* m, const void* base, const long long* dims, const 
 
 }  // namespace
 
-bool ffpn_tc_wgrad_supported(const ffpn_conv_desc* d) { return make_wgrad_plan(d, 148).ok; }
+bool ffpn_wgrad_ws_supported(const ffpn_conv_desc* d);
+bool ffpn_tc_wgrad_supported(const ffpn_conv_desc* d) { return ffpn_wgrad_ws_supported(d) || make_wgrad_plan(d, 148).ok; }
 
 size_t ffpn_wgrad_ws_workspace_bytes(const ffpn_conv_desc* d);
 int ffpn_conv_wgrad_ws(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const void*, float*, void*, size_t,

@@ -29,7 +29,7 @@ struct WgWsParams {
   int region_x, Kpad, xsub_bytes, ysub_bytes, stage_bytes, nstages, tmem_cols;
   unsigned tx_bytes, lboA, lboB;
   unsigned accA[WG2_MAX_ACC], accB[WG2_MAX_ACC];     // per global accumulator: start offsets (descriptor units) of A and B
-  int has_aff, gx, dbg;     // dbg (FFPN_TC_DEBUG, timing experiments): 1 no MMA, 4 no TMA, 8 no transform body
+  int has_aff, gx, dbg, pair_cin;     // pair_cin: real Cin when the plan runs on the pair view of a depth-strided conv (0 = off)     // dbg (FFPN_TC_DEBUG, timing experiments): 1 no MMA, 4 no TMA, 8 no transform body
   const float* sc;
   const float* sh;
   float* part;                                        // [grid.y][grid.x][acc_per_cta][128][colsN]
@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
       const uint32_t cmask = (uint32_t)(p.Cx >> 3) - 1u;
       float s[8], h[8];
       if (active) {
-        const int cofs = ci0 + xs * p.Cx + cc * 8;
+        int cofs = ci0 + xs * p.Cx + cc * 8;
+        if (p.pair_cin) cofs %= p.pair_cin;
         const float4 s0 = *reinterpret_cast<const float4*>(p.sc + cofs), s1 = *reinterpret_cast<const float4*>(p.sc + cofs + 4);
         const float4 h0 = *reinterpret_cast<const float4*>(p.sh + cofs), h1 = *reinterpret_cast<const float4*>(p.sh + cofs + 4);
         s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
@@ -265,11 +266,18 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
 
 // Sum the per-CTA partial tiles (fixed order) and add them to dW in the state_dict layout [Cout][Cin][taps].
 __global__ void wgrad_reduce_kernel(const WgWsParams p, float* __restrict__ dw) {
-  const int64_t total = (int64_t)p.Cout * p.Cin * p.ntaps;
+  const int Cr = p.pair_cin ? p.pair_cin : p.Cin, ntr = p.pair_cin ? 3 : p.ntaps;     // real (state_dict) input channels / taps
+  const int64_t total = (int64_t)p.Cout * Cr * ntr;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int ci = (int)(idx % p.Cin);
-    const int co = (int)((idx / p.Cin) % p.Cout);
-    const int tap = (int)(idx / ((int64_t)p.Cin * p.Cout));
+    const int cir = (int)(idx % Cr);
+    const int co = (int)((idx / Cr) % p.Cout);
+    const int tapr = (int)(idx / ((int64_t)Cr * p.Cout));
+    int ci = cir, tap = tapr;
+    if (p.pair_cin) {                       // dx -> (half h, pair tap t'): 0 -> (1,0), 1 -> (0,1), 2 -> (1,1)
+      const int hh = tapr == 1 ? 0 : 1;
+      tap = tapr == 0 ? 0 : 1;
+      ci = hh * Cr + cir;
+    }
     const int ta = tap % p.kA, tb = tap / p.kA;
     const int cot = co / p.co_t, cco = co - cot * p.co_t, cit = ci / p.ci_t, cci = ci - cit * p.ci_t;
     int passA, lanei;
@@ -287,11 +295,17 @@ __global__ void wgrad_reduce_kernel(const WgWsParams p, float* __restrict__ dw) 
     const int y = (pg * p.n_co + cot) * p.n_ci + cit;
     const float* src = p.part + (((size_t)y * p.gx) * p.acc_per_cta + a) * (size_t)(128 * p.colsN) + (size_t)lanei * p.colsN + col;
     const size_t stride = (size_t)p.acc_per_cta * (128 * p.colsN);
-    float s0 = 0.f, s1 = 0.f;
+    // fixed summation order; eight independent loads in flight (the loop is L2-latency bound otherwise)
+    float acc = 0.f;
     int k = 0;
-    for (; k + 1 < p.gx; k += 2) { s0 += src[(size_t)k * stride]; s1 += src[(size_t)(k + 1) * stride]; }
-    if (k < p.gx) s0 += src[(size_t)k * stride];
-    dw[((size_t)co * p.Cin + ci) * p.ntaps + tap] += s0 + s1;       // accumulate contract of ffpn_conv_wgrad (dw zeroed by the caller)
+    for (; k + 8 <= p.gx; k += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = src[(size_t)(k + u) * stride];
+      acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    for (; k < p.gx; k++) acc += src[(size_t)k * stride];
+    dw[((size_t)co * Cr + cir) * ntr + tapr] += acc;       // accumulate contract of ffpn_conv_wgrad (dw zeroed by the caller)
   }
 }
 
@@ -457,9 +471,17 @@ bool wgws_enabled() {
 
 }  // namespace
 
+bool ffpn_wgrad_ws_supported(const ffpn_conv_desc* d) {
+  ffpn_conv_desc dp;
+  const bool pair = ffpn_make_pair_desc(d, &dp);
+  return d->dtype == FFPN_BF16 && wgws_enabled() && make_wgrad_ws_plan(pair ? &dp : d, 148).ok;
+}
+
 size_t ffpn_wgrad_ws_workspace_bytes(const ffpn_conv_desc* d) {
   if (d->dtype != FFPN_BF16) return 0;
-  WgWsPlan pl = make_wgrad_ws_plan(d, 148);
+  ffpn_conv_desc dp;
+  const bool pair = ffpn_make_pair_desc(d, &dp);
+  WgWsPlan pl = make_wgrad_ws_plan(pair ? &dp : d, 148);
   return pl.ok ? pl.ws_bytes : 0;
 }
 
@@ -468,12 +490,15 @@ int ffpn_conv_wgrad_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
                        int in_relu, const void* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!wgws_enabled()) return -1;
   if (in_scale != nullptr && !in_relu) return -1;
-  WgWsPlan pl = make_wgrad_ws_plan(d, ctx->num_sms);
+  ffpn_conv_desc dp;
+  const bool pair = ffpn_make_pair_desc(d, &dp);
+  WgWsPlan pl = make_wgrad_ws_plan(pair ? &dp : d, ctx->num_sms);
   if (!pl.ok || ws == nullptr || ws_bytes < pl.ws_bytes) return -1;
   CUtensorMap tmx, tmy;
   if (!encode_wg_map(&tmx, pl, x, true, in_scale != nullptr) || !encode_wg_map(&tmy, pl, dy, false, false)) return -1;
   WgWsParams& p = pl.p;
   p.sc = in_scale; p.sh = in_shift; p.has_aff = in_scale != nullptr; p.part = (float*)ws;
+  p.pair_cin = pair ? d->Cin : 0;
   { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   static bool attr_set = false;
   if (!attr_set) {
@@ -492,7 +517,7 @@ int ffpn_conv_wgrad_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
   }
   conv_wgrad_ws_kernel<<<pl.grid, WG2_THREADS, pl.smem, st>>>(p, tmx, tmy);
   FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_ws");
-  const int64_t total = (int64_t)p.Cout * p.Cin * p.ntaps;
+  const int64_t total = pair ? (int64_t)d->Cout * d->Cin * 3 : (int64_t)p.Cout * p.Cin * p.ntaps;
   const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p, dw);
   FFPN_CHECK_LAUNCH(ctx, "wgrad_reduce");

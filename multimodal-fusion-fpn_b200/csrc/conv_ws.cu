@@ -30,6 +30,8 @@ struct WsParams {
   int w_resident;
   unsigned b_unit_bytes, b_total_bytes, tx_bytes;
   int colstride, tmem_cols;
+  int fshift;                         // flat (1x1x1) mode: log2 of the TMA box row unit (256 or 128 positions)
+  int aff_mod;                        // BatchNorm vectors are indexed modulo this (pair view: two positions share them); 0 = off
   int relu, has_aff, has_stats, has_add, dbg;   // dbg (FFPN_TC_DEBUG, timing experiments): 1 no MMA, 2 no epilogue body, 4 no TMA, 8 no transform body
   const float* sc;
   const float* sh;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         int c1, c2, c3;
         if (p.tma_mode == 0) { c1 = -p.hl; c2 = tc.it * p.tY - p.pY; c3 = tc.d0; }
         else if (p.tma_mode == 1) { c1 = tc.i0; c2 = tc.d0 - p.pD; c3 = tc.nb; }
-        else { c1 = 0; c2 = tc.i0 >> 8; c3 = 0; }
+        else { c1 = 0; c2 = tc.i0 >> p.fshift; c3 = 0; }
         for (int uk = 0; uk < p.upt; uk++) {
           const int s = ring.stage(r, p);
           if (r ? wrapped1 : wrapped0) mbar_wait(EMPTY(s), ring.phase(r) ^ 1u);
@@ -371,7 +373,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         const int r = p.niss == 2 ? (ttl & 1) : 0;
         for (int uk = 0; uk < p.upt; uk++) {
           if (active && (!loaded || p.upt > 1)) {
-            const int cofs = (uk * p.kgu + kgi) * p.Kc + cc * 8;
+            int cofs = (uk * p.kgu + kgi) * p.Kc + cc * 8;
+            if (p.aff_mod) cofs %= p.aff_mod;
             const float4 s0 = *reinterpret_cast<const float4*>(p.sc + cofs), s1 = *reinterpret_cast<const float4*>(p.sc + cofs + 4);
             const float4 h0 = *reinterpret_cast<const float4*>(p.sh + cofs), h1 = *reinterpret_cast<const float4*>(p.sh + cofs + 4);
             s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
@@ -492,10 +495,12 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
           region = (tD + p.kD - 1) * L; mode = 1;
           if (tD + p.kD - 1 > 256 || L > 256) continue;
         } else if (p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1) {
-          if (p.X % 256 != 0) break;
-          int nblk = max_rows / 256; if (nblk < 1) continue;
-          if (nblk * 256 > p.X) nblk = p.X / 256;
-          L = nblk * 256; Lr = L; tD = 1; region = L; mode = 2;
+          const int unit = (max_rows >= 256 && p.X % 256 == 0) ? 256 : 128;
+          if (p.X % unit != 0) break;
+          int nblk = max_rows / unit; if (nblk < 1) continue;
+          if (nblk * unit > p.X) nblk = p.X / unit;
+          L = nblk * unit; Lr = L; tD = 1; region = L; mode = 2;
+          p.fshift = unit == 256 ? 8 : 7;
           if (nblk > 256) continue;
         } else {
           if (p.Xp > 256) break;
@@ -551,7 +556,7 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
         w.box[0] = Kc;
         if (mode == 0) { w.box[1] = p.Xp; w.box[2] = tY + p.kY - 1; w.box[3] = tD; }
         else if (mode == 1) { w.box[1] = L; w.box[2] = tD + p.kD - 1; w.box[3] = 1; }
-        else { w.box[1] = 256; w.box[2] = L / 256; w.box[3] = 1; }
+        else { w.box[1] = 1 << p.fshift; w.box[2] = L >> p.fshift; w.box[3] = 1; }
         w.ok = true;
         return w;
       }
@@ -577,8 +582,8 @@ bool encode_ws_map(CUtensorMap* m, const WsPlan& w, const void* x, bool nan_fill
     strides[0] = cb; strides[1] = (cuuint64_t)c.inD * cb;
     strides[2] = (cuuint64_t)(p.NB > 1 ? c.inNB : (long long)c.inD * p.D) * cb;
   } else {
-    dims[1] = 256; dims[2] = p.X / 256; dims[3] = 1;
-    strides[0] = cb; strides[1] = 256 * cb; strides[2] = (cuuint64_t)p.X * cb;
+    dims[1] = 1u << p.fshift; dims[2] = (cuuint64_t)p.X >> p.fshift; dims[3] = 1;
+    strides[0] = cb; strides[1] = ((cuuint64_t)1 << p.fshift) * cb; strides[2] = (cuuint64_t)p.X * cb;
   }
   for (int i = 0; i < 4; i++) box[i] = (cuuint32_t)w.box[i];
   const CUtensorMapSwizzle sw = p.pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -601,7 +606,9 @@ int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
                      int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!ws_enabled()) return -1;
   if (in_scale != nullptr && !in_relu) return -1;                       // NaN-fill halo needs the ReLU
-  WsPlan pl = make_ws_plan(d, transposed, ctx->num_sms);
+  ffpn_conv_desc dp;
+  const bool pair = ffpn_make_pair_desc(d, &dp);                         // depth-strided projection conv -> stride-1 on the pair view
+  WsPlan pl = make_ws_plan(pair ? &dp : d, transposed, ctx->num_sms);
   if (!pl.ok) return -1;
   WsParams& p = pl.p;
   const size_t need = (size_t)pl.nchunks * p.b_total_bytes;
@@ -610,11 +617,13 @@ int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   if (!encode_ws_map(&tmap, pl, x, in_scale != nullptr)) return -1;
   {
     TcParams q = pl.base.p;                                             // geometry + packmode of the shared packer
-    ffpn_tc_pack_weights(w, ws, d, q, pl.nchunks, p.Kc, st);
+    if (pair) q.packmode = transposed ? 4 : 3;
+    ffpn_tc_pack_weights(w, ws, d, q, pl.nchunks, p.Kc, st);                // d: the ORIGINAL descriptor (weight layout)
     FFPN_CHECK_LAUNCH(ctx, "pack_weights");
   }
   p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)ws; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
   { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.aff_mod = (pair && !transposed) ? d->Cin : 0;
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
   static bool attr_set = false;
   if (!attr_set) {

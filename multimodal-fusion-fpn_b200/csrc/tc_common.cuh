@@ -140,6 +140,19 @@ struct Plan {
   bool ok;
 };
 
+// The projection's depth-strided conv (1,1,3) stride (1,1,2) pad (0,0,1) is a stride-1 conv on the PAIR VIEW of its input:
+// x[.., H, C] reinterpreted (for free, it is contiguous) as x'[.., H/2, 2C] (even position | odd position), two taps
+// (pair o-1, pair o) and remapped weights W'[co][(h,ci)][t'] = W[co][ci][dx], (t',h): (0,1)->dx 0, (1,0)->1, (1,1)->2,
+// (0,0)->zero.  Forward, dgrad and wgrad of the strided conv then run on the stride-1 warp-specialised kernels.
+static inline bool ffpn_make_pair_desc(const ffpn_conv_desc* d, ffpn_conv_desc* dp) {
+  if (d->dtype != FFPN_BF16 || d->kS != 1 || d->kW != 1 || d->kH != 3 || d->sS != 1 || d->sW != 1 || d->sH != 2 || d->pS != 0 ||
+      d->pW != 0 || d->pH != 1 || (d->H & 1) || d->oH != d->H / 2)
+    return false;
+  *dp = *d;
+  dp->H = d->H / 2; dp->Cin = 2 * d->Cin; dp->kH = 2; dp->sH = 1; dp->pH = 1;
+  return true;
+}
+
 // canonical geometry + tiling of the staged (no-swizzle) kernels; conv_ws.cu re-tiles on top of the geometry
 Plan ffpn_tc_make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms);
 // fp32 master weights -> bf16 smem image [nchunk][kg][tap][kc][n (Npad)][8] (mode: 0 fwd, 1 dgrad, 2 strided dgrad)

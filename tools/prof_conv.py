@@ -37,6 +37,14 @@ elif kind == 'wgrad133':
 elif kind == 'proj':
     w = torch.randn(C, C, 1, 1, 3, device='cuda', generator=g) * 0.1
     fn = lambda: ops.conv_fwd(x, w, (1, 1, 3), (1, 1, 2), (0, 0, 1), sc, sh, True)
+elif kind == 'proj_dgrad':
+    w = torch.randn(C, C, 1, 1, 3, device='cuda', generator=g) * 0.1
+    dyp = torch.randn(B, S, W, H // 2, C, device='cuda', generator=g).to(torch.bfloat16)
+    fn = lambda: ops.conv_dgrad(dyp, w, tuple(x.shape), (1, 1, 3), (1, 1, 2), (0, 0, 1))
+elif kind == 'proj_wgrad':
+    w = torch.randn(C, C, 1, 1, 3, device='cuda', generator=g) * 0.1
+    dyp = torch.randn(B, S, W, H // 2, C, device='cuda', generator=g).to(torch.bfloat16)
+    fn = lambda: ops.conv_wgrad(x, dyp, w.shape, (1, 1, 3), (1, 1, 2), (0, 0, 1), sc, sh, True)
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
