@@ -1461,6 +1461,9 @@ bool encode_act_map(CUtensorMap* m, const TcParams& p, const void* x, bool nan_f
 
 void ffpn_tc_pack_weights(const float* w, void* out, const ffpn_conv_desc* d, const TcParams& p, int nchunks, int KG,
                           cudaStream_t st) {
+  static int skip = -1;                                   // FFPN_TIMING_SKIP_PACK: timing experiments only (stale images)
+  if (skip < 0) { const char* e = getenv("FFPN_TIMING_SKIP_PACK"); skip = e ? atoi(e) : 0; }
+  if (skip) return;
   const int ntaps = p.kD * p.kY * p.kX;
   const int64_t total = (int64_t)nchunks * ntaps * p.Cin * p.Npad;
   const int g = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);

@@ -266,46 +266,57 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
 
 // Sum the per-CTA partial tiles (fixed order) and add them to dW in the state_dict layout [Cout][Cin][taps].
 __global__ void wgrad_reduce_kernel(const WgWsParams p, float* __restrict__ dw) {
+  // four lanes per output, each summing every fourth partial tile (eight loads in flight), combined with two shuffles in
+  // a fixed order: the loop is L2-latency bound, so the shorter dependent chains matter more than the coalescing
   const int Cr = p.pair_cin ? p.pair_cin : p.Cin, ntr = p.pair_cin ? 3 : p.ntaps;     // real (state_dict) input channels / taps
   const int64_t total = (int64_t)p.Cout * Cr * ntr;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cir = (int)(idx % Cr);
-    const int co = (int)((idx / Cr) % p.Cout);
-    const int tapr = (int)(idx / ((int64_t)Cr * p.Cout));
-    int ci = cir, tap = tapr;
-    if (p.pair_cin) {                       // dx -> (half h, pair tap t'): 0 -> (1,0), 1 -> (0,1), 2 -> (1,1)
-      const int hh = tapr == 1 ? 0 : 1;
-      tap = tapr == 0 ? 0 : 1;
-      ci = hh * Cr + cir;
-    }
-    const int ta = tap % p.kA, tb = tap / p.kA;
-    const int cot = co / p.co_t, cco = co - cot * p.co_t, cit = ci / p.ci_t, cci = ci - cit * p.ci_t;
-    int passA, lanei;
-    if (p.co_t <= 64) {
-      passA = ta / p.sA;
-      const int m = p.sA - 1 - (ta - passA * p.sA);
-      lanei = p.M == 64 ? m * 32 + cco : m * p.Cy + cco;
-    } else {
-      passA = ta; lanei = cco;
-    }
-    const int passB = p.sB > 1 ? 0 : tb;
-    const int col = p.sB > 1 ? tb * p.ci_t + cci : cci;
-    const int g = passB * p.passesA + passA;
-    const int pg = g / p.acc_per_cta, a = g - pg * p.acc_per_cta;
-    const int y = (pg * p.n_co + cot) * p.n_ci + cit;
-    const float* src = p.part + (((size_t)y * p.gx) * p.acc_per_cta + a) * (size_t)(128 * p.colsN) + (size_t)lanei * p.colsN + col;
-    const size_t stride = (size_t)p.acc_per_cta * (128 * p.colsN);
-    // fixed summation order; eight independent loads in flight (the loop is L2-latency bound otherwise)
+  const int sub = threadIdx.x & 3;
+  const int64_t nthr = ((int64_t)gridDim.x * blockDim.x) >> 2;
+  const int64_t rounds = (total + nthr - 1) / nthr;
+  int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  for (int64_t r = 0; r < rounds; r++, idx += nthr) {                 // uniform trip count: the shuffles stay converged
+    const bool live = idx < total;
     float acc = 0.f;
-    int k = 0;
-    for (; k + 8 <= p.gx; k += 8) {
-      float v[8];
+    int cir = 0, co = 0, tapr = 0;
+    if (live) {
+      cir = (int)(idx % Cr);
+      co = (int)((idx / Cr) % p.Cout);
+      tapr = (int)(idx / ((int64_t)Cr * p.Cout));
+      int ci = cir, tap = tapr;
+      if (p.pair_cin) {                     // dx -> (half h, pair tap t'): 0 -> (1,0), 1 -> (0,1), 2 -> (1,1)
+        const int hh = tapr == 1 ? 0 : 1;
+        tap = tapr == 0 ? 0 : 1;
+        ci = hh * Cr + cir;
+      }
+      const int ta = tap % p.kA, tb = tap / p.kA;
+      const int cot = co / p.co_t, cco = co - cot * p.co_t, cit = ci / p.ci_t, cci = ci - cit * p.ci_t;
+      int passA, lanei;
+      if (p.co_t <= 64) {
+        passA = ta / p.sA;
+        const int m = p.sA - 1 - (ta - passA * p.sA);
+        lanei = p.M == 64 ? m * 32 + cco : m * p.Cy + cco;
+      } else {
+        passA = ta; lanei = cco;
+      }
+      const int passB = p.sB > 1 ? 0 : tb;
+      const int col = p.sB > 1 ? tb * p.ci_t + cci : cci;
+      const int g = passB * p.passesA + passA;
+      const int pg = g / p.acc_per_cta, a = g - pg * p.acc_per_cta;
+      const int y = (pg * p.n_co + cot) * p.n_ci + cit;
+      const float* src = p.part + (((size_t)y * p.gx) * p.acc_per_cta + a) * (size_t)(128 * p.colsN) + (size_t)lanei * p.colsN + col;
+      const size_t stride = (size_t)p.acc_per_cta * (128 * p.colsN);
+      int k = sub;
+      for (; k + 28 < p.gx; k += 32) {
+        float v[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = src[(size_t)(k + u) * stride];
-      acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        for (int u = 0; u < 8; u++) v[u] = src[(size_t)(k + 4 * u) * stride];
+        acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      }
+      for (; k < p.gx; k += 4) acc += src[(size_t)k * stride];
     }
-    for (; k < p.gx; k++) acc += src[(size_t)k * stride];
-    dw[((size_t)co * Cr + cir) * ntr + tapr] += acc;       // accumulate contract of ffpn_conv_wgrad (dw zeroed by the caller)
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (live && sub == 0) dw[((size_t)co * Cr + cir) * ntr + tapr] += acc;   // accumulate contract of ffpn_conv_wgrad
   }
 }
 
@@ -518,7 +529,7 @@ int ffpn_conv_wgrad_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
   conv_wgrad_ws_kernel<<<pl.grid, WG2_THREADS, pl.smem, st>>>(p, tmx, tmy);
   FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_ws");
   const int64_t total = pair ? (int64_t)d->Cout * d->Cin * 3 : (int64_t)p.Cout * p.Cin * p.ntaps;
-  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  const int blocks = (int)((total * 4 + 255) / 256 < 1184 ? (total * 4 + 255) / 256 : 1184);
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p, dw);
   FFPN_CHECK_LAUNCH(ctx, "wgrad_reduce");
   return 0;

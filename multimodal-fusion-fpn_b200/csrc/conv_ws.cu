@@ -454,6 +454,11 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   p.outNB = c.outNB; p.outD = c.outD; p.outY = c.outY;
   p.Cin = c.Cin; p.Cout = c.Cout; p.Npad = c.Npad; p.Xp = c.Xp; p.Qout = c.Qout;
   w.nchunks = w.base.nchunks;
+  {  // wide outputs: split N over blockIdx.y so that each CTA streams half the weights and more SMs take part
+    static int nsplit = -1;
+    if (nsplit < 0) { const char* e = getenv("FFPN_WS_NSPLIT"); nsplit = e ? atoi(e) : 128; }
+    if (nsplit > 0 && p.Cout >= 2 * nsplit && p.Cout % nsplit == 0) { p.Npad = nsplit; w.nchunks = p.Cout / nsplit; }
+  }
   const int ntaps = p.kD * p.kY * p.kX;
   if (ntaps > 27 || p.Cin % 16 != 0) return w;
   const int hr = p.Xp - p.oX;
@@ -617,6 +622,7 @@ int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   if (!encode_ws_map(&tmap, pl, x, in_scale != nullptr)) return -1;
   {
     TcParams q = pl.base.p;                                             // geometry + packmode of the shared packer
+    q.Npad = p.Npad;
     if (pair) q.packmode = transposed ? 4 : 3;
     ffpn_tc_pack_weights(w, ws, d, q, pl.nchunks, p.Kc, st);                // d: the ORIGINAL descriptor (weight layout)
     FFPN_CHECK_LAUNCH(ctx, "pack_weights");

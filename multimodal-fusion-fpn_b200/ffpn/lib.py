@@ -119,7 +119,12 @@ def ctx(device_index: int):
     return h
 
 
+_SKIP = set(filter(None, os.environ.get('FFPN_TIMING_SKIP', '').split(',')))   # timing experiments only (results invalid)
+
+
 def call(name: str, device_index: int, *args):
+    if _SKIP and name in _SKIP:
+        return
     lib = load()
     h = ctx(device_index)
     rc = getattr(lib, name)(h, *args)
