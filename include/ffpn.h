@@ -176,6 +176,17 @@ int ffpn_cast(ffpn_ctx* ctx, int dtype, int64_t n, const float* src, void* dst, 
 int ffpn_sgd_step(ffpn_ctx* ctx, int64_t n, float* p, const float* g, float* mom, float lr, float momentum,
                   float weight_decay, float grad_scale, int first_step, void* stream);
 
+/* ---- packed-weight arena (optional, training loops): the tcgen05 kernels consume bf16 weight images that the
+ *      library packs from the fp32 master weights.  Without an arena every conv call packs its own image.  With
+ *      one, the images of a whole step are recorded once (begin .. one forward+backward .. seal) into a caller-owned
+ *      device buffer and afterwards regenerated by ONE kernel per step (ffpn_weight_arena_pack, to be called after
+ *      the weights changed and before the next forward).  Calls whose image is not in the arena fall back to
+ *      per-call packing.  The reference has no counterpart (cuDNN reads fp32 weights directly). ------------------- */
+int ffpn_weight_arena_begin(ffpn_ctx* ctx, void* arena, size_t bytes);
+int ffpn_weight_arena_seal(ffpn_ctx* ctx);
+int ffpn_weight_arena_pack(ffpn_ctx* ctx, void* stream);
+int ffpn_weight_arena_end(ffpn_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,11 +53,15 @@ extern "C" int ffpn_create(ffpn_ctx** out, int device) {
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
   c->err[0] = 0;
+  c->arena_state = 0; c->arena = nullptr; c->arena_bytes = c->arena_used = 0; c->njobs = 0; c->arena_elems = 0; c->d_jobs = nullptr;
   *out = c;
   return 0;
 }
 
-extern "C" void ffpn_destroy(ffpn_ctx* ctx) { delete ctx; }
+extern "C" void ffpn_destroy(ffpn_ctx* ctx) {
+  if (ctx && ctx->d_jobs) cudaFree(ctx->d_jobs);
+  delete ctx;
+}
 extern "C" const char* ffpn_last_error(ffpn_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 extern "C" int64_t ffpn_launch_count(ffpn_ctx* ctx) { return ctx ? ctx->launches : -1; }
 

@@ -491,42 +491,59 @@ __global__ void __launch_bounds__(TC_THREADS, 4) conv_tc_simple_kernel(const __g
 
 // Pack fp32 master weights [Cout][Cin][taps] to the bf16 smem image [nchunk][kg][tap][kc][n (Npad)][8].
 // transposed: the operator applied is the dgrad conv: n <-> ci, k <-> co, taps flipped.
+// Kc = reduction channels of the packed operator, Nc = its output channels, Npad = channels per N-chunk
+__device__ __forceinline__ float pack_value(const float* __restrict__ w, int64_t i, int Cout, int Cin, int ntaps, int Kc, int Nc,
+                                            int Npad, int KG, int mode, int sH, int pH, int kH, int tmin) {
+  const uint32_t nkc = (uint32_t)KG >> 3;
+  const uint32_t nkg = (uint32_t)(Kc / KG);
+  uint32_t r = (uint32_t)i;                   // one image has < 2^31 elements: 32-bit index arithmetic
+  const int e = (int)(r & 7u); r >>= 3;
+  int n = (int)(r % (uint32_t)Npad); r /= (uint32_t)Npad;
+  const int kc = (int)(r % nkc); r /= nkc;
+  const int tap = (int)(r % (uint32_t)ntaps); r /= (uint32_t)ntaps;
+  const int kg = (int)(r % nkg);
+  n += (int)(r / nkg) * Npad;
+  const int k = kg * KG + kc * 8 + e;
+  float v = 0.f;
+  if (n < Nc) {
+    if (mode == 0) v = w[((int64_t)n * Cin + k) * ntaps + tap];                       // forward
+    else if (mode == 1) v = w[((int64_t)k * Cin + n) * ntaps + (ntaps - 1 - tap)];   // dgrad, stride 1
+    else if (mode == 2) {                     // dgrad of a depth-strided (1,1,kH) conv: n = r*Cin + ci
+      const int rr = n / Cin, ci = n - rr * Cin;
+      const int dx = rr + pH - sH * (tap + tmin);
+      if (dx >= 0 && dx < kH) v = w[((int64_t)k * Cin + ci) * kH + dx];
+    } else {                                  // pair view of the (1,1,3) s2 p1 conv: 3 forward (k = (h,ci)), 4 dgrad (n = (h,ci))
+      const int c2 = mode == 3 ? k : n, oc = mode == 3 ? n : k;
+      const int hh = c2 / Cin, ci = c2 - hh * Cin;
+      const int tp = mode == 3 ? tap : 1 - tap;
+      const int dx = tp == 0 ? (hh == 1 ? 0 : -1) : (hh == 0 ? 1 : 2);
+      if (dx >= 0) v = w[((int64_t)oc * Cin + ci) * 3 + dx];
+    }
+  }
+  return v;
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ntaps,
                                     int Kc, int Nc, int Npad, int KG, int nchunks, int mode, int sH, int pH, int kH,
                                     int tmin) {
-  // Kc = reduction channels of the packed operator, Nc = its output channels, Npad = channels per N-chunk
-  const int nkc = KG >> 3;
-  const int nkg = Kc / KG;
-  const int64_t total = (int64_t)nchunks * nkg * ntaps * nkc * Npad * 8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i;
-    const int e = (int)(r % 8); r /= 8;
-    int n = (int)(r % Npad); r /= Npad;
-    const int kc = (int)(r % nkc); r /= nkc;
-    const int tap = (int)(r % ntaps); r /= ntaps;
-    const int kg = (int)(r % nkg);
-    n += (int)(r / nkg) * Npad;
-    const int k = kg * KG + kc * 8 + e;
-    float v = 0.f;
-    if (n < Nc) {
-      if (mode == 0) v = w[((int64_t)n * Cin + k) * ntaps + tap];                       // forward
-      else if (mode == 1) v = w[((int64_t)k * Cin + n) * ntaps + (ntaps - 1 - tap)];   // dgrad, stride 1
-      else if (mode == 2) {                     // dgrad of a depth-strided (1,1,kH) conv: n = r*Cin + ci
-        const int r = n / Cin, ci = n - r * Cin;
-        const int dx = r + pH - sH * (tap + tmin);
-        if (dx >= 0 && dx < kH) v = w[((int64_t)k * Cin + ci) * kH + dx];
-      } else {                                  // pair view of the (1,1,3) s2 p1 conv: 3 forward (k = (h,ci)), 4 dgrad (n = (h,ci))
-        const int c2 = mode == 3 ? k : n, oc = mode == 3 ? n : k;
-        const int hh = c2 / Cin, ci = c2 - hh * Cin;
-        const int tp = mode == 3 ? tap : 1 - tap;
-        const int dx = tp == 0 ? (hh == 1 ? 0 : -1) : (hh == 0 ? 1 : 2);
-        if (dx >= 0) v = w[((int64_t)oc * Cin + ci) * 3 + dx];
-      }
-    }
-    out[i] = __float2bfloat16_rn(v);
-  }
+  const int64_t total = (int64_t)nchunks * ntaps * Kc * Npad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(pack_value(w, i, Cout, Cin, ntaps, Kc, Nc, Npad, KG, mode, sH, pH, kH, tmin));
 }
 
+// All images of the packed-weight arena in one launch: element -> job by binary search on the prefix sums.
+__global__ void pack_all_kernel(const ffpn_pack_job* __restrict__ jobs, int njobs, long long total, bf16* __restrict__ arena) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].prefix <= i) lo = mid; else hi = mid - 1;
+    }
+    const ffpn_pack_job& j = jobs[lo];
+    const long long li = i - j.prefix;
+    arena[j.dst + li] = __float2bfloat16_rn(pack_value(j.w, li, j.Cout, j.Cin, j.ntaps, j.Kc, j.Nc, j.Npad, j.KG, j.mode, j.sH, j.pH, j.kH, j.tmin));
+  }
+}
 
 }  // namespace
 
@@ -1459,16 +1476,69 @@ bool encode_act_map(CUtensorMap* m, const TcParams& p, const void* x, bool nan_f
 }
 }  // namespace
 
-void ffpn_tc_pack_weights(const float* w, void* out, const ffpn_conv_desc* d, const TcParams& p, int nchunks, int KG,
-                          cudaStream_t st) {
-  static int skip = -1;                                   // FFPN_TIMING_SKIP_PACK: timing experiments only (stale images)
-  if (skip < 0) { const char* e = getenv("FFPN_TIMING_SKIP_PACK"); skip = e ? atoi(e) : 0; }
-  if (skip) return;
+const void* ffpn_tc_pack_weights(ffpn_ctx* ctx, const float* w, void* ws, const ffpn_conv_desc* d, const TcParams& p, int nchunks,
+                                 int KG, cudaStream_t st, bool* launched) {
   const int ntaps = p.kD * p.kY * p.kX;
   const int64_t total = (int64_t)nchunks * ntaps * p.Cin * p.Npad;
+  *launched = false;
+  ffpn_pack_job j;
+  j.w = w; j.total = total; j.Cout = d->Cout; j.Cin = d->Cin; j.ntaps = ntaps; j.Kc = p.Cin; j.Nc = p.Cout; j.Npad = p.Npad; j.KG = KG;
+  j.nchunks = nchunks; j.mode = p.packmode; j.sH = d->sH; j.pH = d->pH; j.kH = d->kH; j.tmin = -p.pX;
+  if (ctx->arena_state == 2) {
+    for (int i = 0; i < ctx->njobs; i++) {
+      const ffpn_pack_job& q = ctx->jobs[i];
+      if (q.w == w && q.mode == j.mode && q.KG == KG && q.Npad == j.Npad && q.nchunks == nchunks && q.total == total && q.tmin == j.tmin &&
+          q.Nc == j.Nc && q.Kc == j.Kc)
+        return ctx->arena + (size_t)q.dst * 2;                       // image regenerated by ffpn_weight_arena_pack this step
+    }
+  }
+  void* out = ws;
+  if (ctx->arena_state == 1 && ctx->njobs < FFPN_MAX_PACK_JOBS && ctx->arena_used + (size_t)total * 2 + 1024 <= ctx->arena_bytes) {
+    j.dst = (long long)(ctx->arena_used / 2);
+    j.prefix = ctx->arena_elems;
+    ctx->jobs[ctx->njobs++] = j;
+    out = ctx->arena + ctx->arena_used;
+    ctx->arena_used += ((size_t)total * 2 + 1023) & ~(size_t)1023;   // cp.async.bulk sources stay 16-byte aligned
+    ctx->arena_elems += total;
+  }
   const int g = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
-  pack_weights_kernel<<<g, 256, 0, st>>>(w, (bf16*)out, d->Cout, d->Cin, ntaps, p.Cin, p.Cout, p.Npad, KG, nchunks, p.packmode,
-                                         d->sH, d->pH, d->kH, -p.pX);
+  pack_weights_kernel<<<g, 256, 0, st>>>(w, (bf16*)out, j.Cout, j.Cin, ntaps, j.Kc, j.Nc, j.Npad, KG, nchunks, j.mode, j.sH, j.pH, j.kH,
+                                         j.tmin);
+  *launched = true;
+  return out;
+}
+
+// ---- packed-weight arena (include/ffpn.h) -----------------------------------------------------------------
+extern "C" int ffpn_weight_arena_begin(ffpn_ctx* ctx, void* arena, size_t bytes) {
+  if (!ctx) return 1;
+  if (arena == nullptr || bytes < (1u << 20) || ((uintptr_t)arena & 1023)) FFPN_FAIL(ctx, "weight_arena_begin: need a 1 KiB-aligned buffer of >= 1 MiB");
+  ctx->arena = (char*)arena; ctx->arena_bytes = bytes; ctx->arena_used = 0; ctx->njobs = 0; ctx->arena_elems = 0;
+  ctx->arena_state = 1;
+  return 0;
+}
+extern "C" int ffpn_weight_arena_seal(ffpn_ctx* ctx) {
+  if (!ctx) return 1;
+  if (ctx->arena_state != 1) FFPN_FAIL(ctx, "weight_arena_seal: not recording");
+  if (ctx->d_jobs == nullptr && cudaMalloc(&ctx->d_jobs, sizeof(ffpn_pack_job) * FFPN_MAX_PACK_JOBS) != cudaSuccess)
+    FFPN_FAIL(ctx, "weight_arena_seal: cannot allocate the job table");
+  if (ctx->njobs > 0 && cudaMemcpy(ctx->d_jobs, ctx->jobs, sizeof(ffpn_pack_job) * ctx->njobs, cudaMemcpyHostToDevice) != cudaSuccess)
+    FFPN_FAIL(ctx, "weight_arena_seal: cannot upload the job table");
+  ctx->arena_state = ctx->njobs > 0 ? 2 : 0;
+  return 0;
+}
+extern "C" int ffpn_weight_arena_pack(ffpn_ctx* ctx, void* stream) {
+  if (!ctx) return 1;
+  if (ctx->arena_state != 2) return 0;
+  const long long total = ctx->arena_elems;
+  const int g = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  pack_all_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(ctx->d_jobs, ctx->njobs, total, (bf16*)ctx->arena);
+  FFPN_CHECK_LAUNCH(ctx, "weight_arena_pack");
+  return 0;
+}
+extern "C" int ffpn_weight_arena_end(ffpn_ctx* ctx) {
+  if (!ctx) return 1;
+  ctx->arena_state = 0; ctx->njobs = 0; ctx->arena = nullptr; ctx->arena_bytes = ctx->arena_used = 0; ctx->arena_elems = 0;
+  return 0;
 }
 
 int ffpn_conv_fwd_ws(ffpn_ctx*, const ffpn_conv_desc*, bool transposed, const void*, const float*, const float*, int, const float*,
@@ -1487,9 +1557,10 @@ int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   const size_t need = (size_t)pl.nchunks * p.nkg * p.b_bytes;
   if (ws == nullptr || ws_bytes < need) FFPN_FAIL(ctx, "conv_tc: workspace too small (%zu < %zu)", ws_bytes, need);
   if (stat_partial != nullptr && pl.grid > FFPN_STAT_ROWS) FFPN_FAIL(ctx, "conv_tc: %d tiles exceed the statistics buffer", pl.grid);
-  ffpn_tc_pack_weights(w, ws, d, p, pl.nchunks, p.KG, st);
-  FFPN_CHECK_LAUNCH(ctx, "pack_weights");
-  p.x = (const bf16*)x; p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)ws;
+  bool packed_now = false;
+  const void* wimg = ffpn_tc_pack_weights(ctx, w, ws, d, p, pl.nchunks, p.KG, st, &packed_now);
+  if (packed_now) FFPN_CHECK_LAUNCH(ctx, "pack_weights");
+  p.x = (const bf16*)x; p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)wimg;
   p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
   static bool attr_set = false;

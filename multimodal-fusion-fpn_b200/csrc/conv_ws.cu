@@ -620,14 +620,16 @@ int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   if (ws == nullptr || ws_bytes < need) return -1;
   CUtensorMap tmap;
   if (!encode_ws_map(&tmap, pl, x, in_scale != nullptr)) return -1;
+  const void* wimg;
   {
     TcParams q = pl.base.p;                                             // geometry + packmode of the shared packer
     q.Npad = p.Npad;
     if (pair) q.packmode = transposed ? 4 : 3;
-    ffpn_tc_pack_weights(w, ws, d, q, pl.nchunks, p.Kc, st);                // d: the ORIGINAL descriptor (weight layout)
-    FFPN_CHECK_LAUNCH(ctx, "pack_weights");
+    bool packed_now = false;
+    wimg = ffpn_tc_pack_weights(ctx, w, ws, d, q, pl.nchunks, p.Kc, st, &packed_now);   // d: the ORIGINAL descriptor (weight layout)
+    if (packed_now) FFPN_CHECK_LAUNCH(ctx, "pack_weights");
   }
-  p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)ws; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
+  p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)wimg; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
   { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.aff_mod = (pair && !transposed) ? d->Cin : 0;
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;

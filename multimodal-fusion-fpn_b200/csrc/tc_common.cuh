@@ -155,6 +155,8 @@ static inline bool ffpn_make_pair_desc(const ffpn_conv_desc* d, ffpn_conv_desc* 
 
 // canonical geometry + tiling of the staged (no-swizzle) kernels; conv_ws.cu re-tiles on top of the geometry
 Plan ffpn_tc_make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms);
-// fp32 master weights -> bf16 smem image [nchunk][kg][tap][kc][n (Npad)][8] (mode: 0 fwd, 1 dgrad, 2 strided dgrad)
-void ffpn_tc_pack_weights(const float* w, void* out, const ffpn_conv_desc* d, const TcParams& p, int nchunks, int KG,
-                          cudaStream_t st);
+// fp32 master weights -> bf16 smem image [nchunk][kg][tap][kc][n (Npad)][8] (mode: 0 fwd, 1 dgrad, 2 strided dgrad, 3/4 pair view).
+// Returns the device pointer of the image: `ws` after a per-call packing launch, or the arena slot when the packed-weight
+// arena is replaying (no launch).  *launched tells the caller whether a kernel was enqueued.
+const void* ffpn_tc_pack_weights(ffpn_ctx* ctx, const float* w, void* ws, const ffpn_conv_desc* d, const TcParams& p, int nchunks,
+                                 int KG, cudaStream_t st, bool* launched);

@@ -290,3 +290,20 @@ def cast(src, dtype):
 def sgd_step(p, g, mom, lr, momentum, weight_decay, grad_scale, first_step):
     lib.call('ffpn_sgd_step', _dev(p), p.numel(), _ptr(p), _ptr(g), _ptr(mom), float(lr), float(momentum),
              float(weight_decay), float(grad_scale), int(bool(first_step)), _stream(p))
+
+
+# ---- packed-weight arena (include/ffpn.h: ffpn_weight_arena_*) ---------------------------------------------
+def weight_arena_begin(arena: torch.Tensor):
+    lib.call('ffpn_weight_arena_begin', _dev(arena), _ptr(arena), arena.numel() * arena.element_size())
+
+
+def weight_arena_seal(device_index: int):
+    lib.call('ffpn_weight_arena_seal', device_index)
+
+
+def weight_arena_pack(like: torch.Tensor):
+    lib.call('ffpn_weight_arena_pack', _dev(like), _stream(like))
+
+
+def weight_arena_end(device_index: int):
+    lib.call('ffpn_weight_arena_end', device_index)

@@ -55,6 +55,11 @@ class FusionTrainer:
         self._static_loss = None
         # gradient sink: backward kernels write straight into flat_g (valid while every parameter is used once per
         # backward and flat_g is zeroed once per optimisation step; BatchNorm gradients are plain writes)
+        # packed-weight arena: the first forward+backward records every bf16 weight image, later steps regenerate all of
+        # them with one kernel instead of one tiny packing launch per conv call (~170 per step)
+        self._arena = None
+        self._arena_state = 0          # 0 not started, 1 recording, 2 sealed
+        self._weights_dirty = False    # set by mark_weights_dirty(): repack before the next forward
         self._sink = {}
         if self.accumulate == 1:
             for p in model.parameters():
@@ -63,7 +68,16 @@ class FusionTrainer:
 
     # -- pieces ----------------------------------------------------------------------------------------
     def forward_backward(self, batch):
-        from . import functional
+        from . import functional, ops
+        from .functional import get_compute_dtype
+        if get_compute_dtype() == torch.bfloat16:
+            if self._arena_state == 0:
+                self._arena = torch.empty(96 << 20, dtype=torch.uint8, device=self.flat_p.device)
+                ops.weight_arena_begin(self._arena)
+                self._arena_state = 1
+            elif self._arena_state == 2 and self._weights_dirty:
+                ops.weight_arena_pack(self.flat_p)     # weights were changed behind the trainer's back (load_state_dict, ...)
+                self._weights_dirty = False
         functional.set_grad_sink(self._sink)
         try:
             out = self.model(batch)
@@ -71,13 +85,36 @@ class FusionTrainer:
             (loss / self.accumulate if self.accumulate > 1 else loss).backward()
         finally:
             functional.set_grad_sink(None)
+            if self._arena_state == 1:
+                ops.weight_arena_seal(self.flat_p.device.index if self.flat_p.device.index is not None else 0)
+                self._arena_state = 2
         return loss.detach()
+
+    def mark_weights_dirty(self):
+        """Call after modifying parameters outside optimizer_step() (e.g. load_state_dict): the bf16 weight images of the
+        arena are regenerated before the next forward."""
+        self._weights_dirty = True
+
+    def close(self):
+        """Detach the packed-weight arena from the library context (the context is shared per device)."""
+        if self._arena_state:
+            from . import ops
+            ops.weight_arena_end(self.flat_p.device.index if self.flat_p.device.index is not None else 0)
+            self._arena_state, self._arena = 0, None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def optimizer_step(self):
         from . import ops
         scale = allreduce_mean_(self.flat_g, self.group)
         ops.sgd_step(self.flat_p, self.flat_g, self.mom, self.lr, self.momentum, self.weight_decay, scale,
                      self.steps == 0)
+        if self._arena_state == 2:
+            ops.weight_arena_pack(self.flat_p)         # keep the arena images in step with the weights (eval forwards use them)
         self.steps += 1
         self.flat_g.zero_()
 
@@ -110,6 +147,8 @@ class FusionTrainer:
             if self._fused_opt:
                 from . import ops
                 ops.sgd_step(self.flat_p, self.flat_g, self.mom, self.lr, self.momentum, self.weight_decay, 1.0, False)
+                if self._arena_state == 2:
+                    ops.weight_arena_pack(self.flat_p)
                 self.flat_g.zero_()
         self._first_graph_step = first
         return self
