@@ -69,6 +69,15 @@ size_t ffpn_conv_workspace_bytes(const ffpn_conv_desc* d);
 int ffpn_conv_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale,
                   const float* in_shift, int in_relu, const float* w, void* y, float* stat_partial,
                   int* stat_rows, void* ws, size_t ws_bytes, void* stream);
+/* conv_fwd followed by the BatchNorm statistics finalize of its output (ffpn_bn_finalize) as ONE call: on the tcgen05
+ * path the last CTA of the conv kernel combines the partial sums itself, which removes a latency-bound launch per
+ * conv (fusion3D2D.py:717-732: every conv is followed by a BatchNorm in training mode).  Same arguments as the two calls. */
+int ffpn_conv_fwd_bn(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale, const float* in_shift,
+                     int in_relu, const float* w, void* y, float* stat_partial, int* stat_rows, double count,
+                     const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                     int training, float* scale, float* shift, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes,
+                     void* stream);
+
 /* dgrad: dx = conv_transpose(dy, w) [+ addend]  (gradient w.r.t. f(x), i.e. before the producer's ReLU
  *        mask).  addend (nullable, same shape/dtype as dx) fuses the residual-branch gradient sum of
  *        fusion3D2D.py:724-725's backward. */

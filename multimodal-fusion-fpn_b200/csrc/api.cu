@@ -21,6 +21,14 @@ int ffpn_conv_fwd_tc(ffpn_ctx*, const ffpn_conv_desc*, bool transposed, const vo
                      const float*, const void* addend, void*, float*, int*, void*, size_t, cudaStream_t);
 int ffpn_conv_wgrad_tc(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const void*,
                        float*, void*, size_t, cudaStream_t);
+// conv_ws.cu (fin != nullptr: BatchNorm finalize fused into the kernel)
+struct ffpn_bn_fin;
+int ffpn_conv_fwd_ws_bn(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const float*, void*, float*, int*,
+                        void*, size_t, cudaStream_t, double count, float momentum, float eps, const float* gamma, const float* beta,
+                        float* rmean, float* rvar, float* scale, float* shift, float* smean, float* sinvstd);
+extern "C" int ffpn_bn_finalize(ffpn_ctx* ctx, const float* stat_partial, int stat_rows, int C, double count, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum, float eps, int training,
+                                float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
 
 static int check_desc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const char* who) {
   if (!ctx) return 1;
@@ -53,13 +61,14 @@ extern "C" int ffpn_create(ffpn_ctx** out, int device) {
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
   c->err[0] = 0;
-  c->arena_state = 0; c->arena = nullptr; c->arena_bytes = c->arena_used = 0; c->njobs = 0; c->arena_elems = 0; c->d_jobs = nullptr;
+  c->arena_state = 0; c->arena = nullptr; c->arena_bytes = c->arena_used = 0; c->njobs = 0; c->arena_elems = 0; c->d_jobs = nullptr; c->d_counter = nullptr;
   *out = c;
   return 0;
 }
 
 extern "C" void ffpn_destroy(ffpn_ctx* ctx) {
   if (ctx && ctx->d_jobs) cudaFree(ctx->d_jobs);
+  if (ctx && ctx->d_counter) cudaFree(ctx->d_counter);
   delete ctx;
 }
 extern "C" const char* ffpn_last_error(ffpn_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
@@ -80,6 +89,25 @@ extern "C" int ffpn_conv_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void*
   if (tc_ok && d->impl != 1)
     return ffpn_conv_fwd_tc(ctx, d, false, x, in_scale, in_shift, in_relu, w, nullptr, y, stat_partial, stat_rows, ws, ws_bytes, (cudaStream_t)stream);
   return ffpn_conv_fwd_simt(ctx, d, x, in_scale, in_shift, in_relu, w, y, stat_partial, stat_rows, (cudaStream_t)stream);
+}
+
+extern "C" int ffpn_conv_fwd_bn(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale, const float* in_shift,
+                                int in_relu, const float* w, void* y, float* stat_partial, int* stat_rows, double count,
+                                const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                int training, float* scale, float* shift, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes,
+                                void* stream) {
+  if (check_desc(ctx, d, "conv_fwd_bn")) return 1;
+  if ((in_scale == nullptr) != (in_shift == nullptr)) FFPN_FAIL(ctx, "conv_fwd_bn: in_scale/in_shift must both be set or both null");
+  if (training && (stat_partial == nullptr || stat_rows == nullptr)) FFPN_FAIL(ctx, "conv_fwd_bn: training needs the statistics buffer");
+  if (training && d->impl != 1 && d->dtype == FFPN_BF16 && !(d->impl == 0 && in_scale == nullptr && ffpn_stem_supported(d)) &&
+      ffpn_tc_fwd_supported(d)) {
+    const int r = ffpn_conv_fwd_ws_bn(ctx, d, x, in_scale, in_shift, in_relu, w, y, stat_partial, stat_rows, ws, ws_bytes, (cudaStream_t)stream,
+                                      count, momentum, eps, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd);
+    if (r >= 0) return r;                                  // fused: conv + finalize by the last CTA
+  }
+  if (ffpn_conv_fwd(ctx, d, x, in_scale, in_shift, in_relu, w, y, training ? stat_partial : nullptr, stat_rows, ws, ws_bytes, stream)) return 1;
+  return ffpn_bn_finalize(ctx, stat_partial, training ? *stat_rows : 0, d->Cout, count, gamma, beta, running_mean, running_var, momentum, eps,
+                          training, scale, shift, save_mean, save_invstd, stream);
 }
 
 extern "C" int ffpn_conv_dgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* dy, const float* w, const void* addend,

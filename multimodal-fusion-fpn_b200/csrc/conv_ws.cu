@@ -40,6 +40,9 @@ struct WsParams {
   bf16* y;
   float* stat;
   unsigned tapdesc[27];               // per tap: row offset of the A view in descriptor units ((rows * pitch) >> 4)
+  int fin_on;                         // BatchNorm finalize by the last CTA to finish (ffpn_conv_fwd_bn)
+  ffpn_bn_fin fin;
+  unsigned* fin_counter;
   long long* trace;                   // FFPN_WS_TRACE: per-tile clock64 stamps of CTA 0 (debug)
 };
 
@@ -270,7 +273,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
             const int m = (half + 2 * mbi) * 128 + quad * 32 + lane;
             const int j = p.Lr == 1 ? m : (int)__umulhi((uint32_t)m, magicLr), ii = m - j * p.Lr;
             const int i = tc.i0 + ii;
-            const int oy = p.Xp == 1 ? i : (int)__umulhi((uint32_t)i, magicXp), ox = i - oy * p.Xp;
+            // flat / slice modes have Xp >= every i (one line): the reciprocal is only exact while i * Xp < 2^32 (mode 0)
+            const int oy = i < p.Xp ? 0 : (p.Xp == 1 ? i : (int)__umulhi((uint32_t)i, magicXp)), ox = i - oy * p.Xp;
             const bool valid = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX);
             const long long opos = (long long)tc.nb * p.outNB + (long long)(tc.d0 + j) * p.outD + (long long)oy * p.outY + ox;
             float v[16];
@@ -428,6 +432,53 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+  if (p.fin_on) {
+    // ---- fused BatchNorm finalize: the last CTA to arrive combines all partial rows (fp64, fixed order) ----
+    int* flag = reinterpret_cast<int*>(smem + 248);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *flag = (atomicAdd(p.fin_counter, 1u) == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+    __syncthreads();
+    if (*flag) {
+      __threadfence();
+      double* red = reinterpret_cast<double*>(stat_s);                   // [16 row lanes][32 channels][2]
+      const int rows = (int)gridDim.x, rl = tid >> 5, cl = tid & 31;
+      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+        const int c = c0 + cl;
+        double a = 0.0, b = 0.0;
+        if (c < p.Cout)
+          for (int r = rl; r < rows; r += 16) {
+            a += (double)__ldcg(p.stat + ((size_t)r * 2 + 0) * p.Cout + c);
+            b += (double)__ldcg(p.stat + ((size_t)r * 2 + 1) * p.Cout + c);
+          }
+        __syncthreads();
+        red[(rl * 32 + cl) * 2 + 0] = a;
+        red[(rl * 32 + cl) * 2 + 1] = b;
+        __syncthreads();
+        if (rl == 0 && c < p.Cout) {
+          double s1 = 0.0, s2 = 0.0;
+          for (int l = 0; l < 16; l++) { s1 += red[(l * 32 + cl) * 2 + 0]; s2 += red[(l * 32 + cl) * 2 + 1]; }
+          const double count = p.fin.count;
+          const double mean = s1 / count;
+          double var = s2 / count - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const double invstd = 1.0 / sqrt(var + (double)p.fin.eps);
+          const double gm = (double)p.fin.gamma[c];
+          p.fin.scale[c] = (float)(gm * invstd);
+          p.fin.shift[c] = (float)((double)p.fin.beta[c] - mean * gm * invstd);
+          if (p.fin.save_mean) p.fin.save_mean[c] = (float)mean;
+          if (p.fin.save_invstd) p.fin.save_invstd[c] = (float)invstd;
+          if (p.fin.running_mean != nullptr) {
+            const double mom = (double)p.fin.momentum;
+            const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+            p.fin.running_mean[c] = (float)((1.0 - mom) * (double)p.fin.running_mean[c] + mom * mean);
+            p.fin.running_var[c] = (float)((1.0 - mom) * (double)p.fin.running_var[c] + mom * unb);
+          }
+        }
+      }
+      if (tid == 0) *p.fin_counter = 0u;                                 // self-resetting for the next launch
+    }
   }
 }
 
@@ -606,9 +657,9 @@ bool ws_enabled() {
 }  // namespace
 
 // Returns 0 = launched, 1 = error (message set), -1 = geometry not handled by this kernel (caller falls back).
-int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,
-                     const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
-                     int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,
+                          const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
+                          int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st, const ffpn_bn_fin* fin) {
   if (!ws_enabled()) return -1;
   if (in_scale != nullptr && !in_relu) return -1;                       // NaN-fill halo needs the ReLU
   ffpn_conv_desc dp;
@@ -631,6 +682,15 @@ int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   }
   p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)wimg; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
   { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.fin_on = 0;
+  if (fin != nullptr) {
+    if (stat_partial == nullptr) return -1;
+    if (ctx->d_counter == nullptr) {
+      if (cudaMalloc(&ctx->d_counter, 256) != cudaSuccess || cudaMemset(ctx->d_counter, 0, 256) != cudaSuccess)
+        FFPN_FAIL(ctx, "conv_ws: cannot allocate the arrival counter");
+    }
+    p.fin_on = 1; p.fin = *fin; p.fin_counter = ctx->d_counter;
+  }
   p.aff_mod = (pair && !transposed) ? d->Cin : 0;
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
   static bool attr_set = false;
@@ -678,4 +738,24 @@ int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   }
   if (stat_rows) *stat_rows = (int)pl.grid.x;
   return 0;
+}
+
+int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,
+                     const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
+                     int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return conv_ws_launch(ctx, d, transposed, x, in_scale, in_shift, in_relu, w, addend, y, stat_partial, stat_rows, ws, ws_bytes, st, nullptr);
+}
+
+// Forward conv with the BatchNorm finalize of its output fused in (training mode).  -1: geometry not handled here.
+int ffpn_conv_fwd_ws_bn(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale, const float* in_shift, int in_relu,
+                        const float* w, void* y, float* stat_partial, int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st,
+                        double count, float momentum, float eps, const float* gamma, const float* beta, float* rmean, float* rvar,
+                        float* scale, float* shift, float* smean, float* sinvstd) {
+  static int nofin = -1;
+  if (nofin < 0) { const char* e = getenv("FFPN_NO_FIN"); nofin = e ? atoi(e) : 0; }
+  if (nofin) return -1;
+  ffpn_bn_fin fin;
+  fin.count = count; fin.momentum = momentum; fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.running_mean = rmean;
+  fin.running_var = rvar; fin.scale = scale; fin.shift = shift; fin.save_mean = smean; fin.save_invstd = sinvstd;
+  return conv_ws_launch(ctx, d, false, x, in_scale, in_shift, in_relu, w, nullptr, y, stat_partial, stat_rows, ws, ws_bytes, st, &fin);
 }

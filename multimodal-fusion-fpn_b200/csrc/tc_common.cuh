@@ -153,6 +153,20 @@ static inline bool ffpn_make_pair_desc(const ffpn_conv_desc* d, ffpn_conv_desc* 
   return true;
 }
 
+// BatchNorm finalize fused into the producing conv kernel (done by the last CTA to finish): ffpn_conv_fwd_bn
+struct ffpn_bn_fin {
+  double count;
+  float momentum, eps;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* scale;
+  float* shift;
+  float* save_mean;
+  float* save_invstd;
+};
+
 // canonical geometry + tiling of the staged (no-swizzle) kernels; conv_ws.cu re-tiles on top of the geometry
 Plan ffpn_tc_make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms);
 // fp32 master weights -> bf16 smem image [nchunk][kg][tap][kc][n (Npad)][8] (mode: 0 fwd, 1 dgrad, 2 strided dgrad, 3/4 pair view).

@@ -105,21 +105,17 @@ class ConvXFunction(torch.autograd.Function):
         cur, cur_aff = xp, None
         for i in range(k):
             w, g, b, rm, rv = tensors[5 * i: 5 * i + 5]
-            y, partial, rows = ops.conv_fwd(cur, w, spec.kernels[i], spec.strides[i], spec.pads[i],
-                                            None if cur_aff is None else cur_aff[0],
-                                            None if cur_aff is None else cur_aff[1], cur_aff is not None,
-                                            want_stats=spec.training)
-            count = y.numel() // y.shape[-1]
-            aff = ops.bn_finalize(partial, rows, count, g, b, rm, rv, spec.momentum, spec.eps, spec.training)
+            y, aff = ops.conv_fwd_bn(cur, w, spec.kernels[i], spec.strides[i], spec.pads[i],
+                                     None if cur_aff is None else cur_aff[0], None if cur_aff is None else cur_aff[1],
+                                     cur_aff is not None, g, b, rm, rv, spec.momentum, spec.eps, spec.training)
             ys.append(y)
             affs.append(aff)
             cur, cur_aff = y, aff
         yd, affd = None, None
         if spec.residual and spec.has_ds:
             wd, gd, bd, rmd, rvd = tensors[5 * k: 5 * k + 5]
-            yd, partial, rows = ops.conv_fwd(xp, wd, (1, 1, 1), spec.ds_stride, (0, 0, 0), want_stats=spec.training)
-            affd = ops.bn_finalize(partial, rows, yd.numel() // yd.shape[-1], gd, bd, rmd, rvd, spec.momentum, spec.eps,
-                                   spec.training)
+            yd, affd = ops.conv_fwd_bn(xp, wd, (1, 1, 1), spec.ds_stride, (0, 0, 0), None, None, False, gd, bd, rmd, rvd,
+                                       spec.momentum, spec.eps, spec.training)
         a, b = affs[-1][0], affs[-1][1]
         zp = None
         if spec.tail == 'mean':

@@ -31,6 +31,7 @@ _DP = C.POINTER(ConvDesc)
 # name -> argtypes (after the leading ctx*); restype is int unless listed in _RESTYPE
 SIGNATURES = {
     'ffpn_conv_fwd': [_DP, _P, _P, _P, _I, _P, _P, _P, _IP, _P, _Z, _P],
+    'ffpn_conv_fwd_bn': [_DP, _P, _P, _P, _I, _P, _P, _P, _IP, _D, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _Z, _P],
     'ffpn_conv_dgrad': [_DP, _P, _P, _P, _P, _P, _Z, _P],
     'ffpn_conv_wgrad': [_DP, _P, _P, _P, _I, _P, _P, _P, _Z, _P],
     'ffpn_bn_finalize': [_P, _I, _I, _D, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P],

@@ -1,6 +1,7 @@
 """Thin tensor-level wrappers over the C ABI.  Tensors here are PHYSICAL channels-last activations
 (B, S, W, H, C) contiguous; all launches go to torch's current CUDA stream."""
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -83,6 +84,28 @@ def conv_fwd(x, w, kernel, stride, pad, in_scale=None, in_shift=None, in_relu=Fa
     lib.call('ffpn_conv_fwd', _dev(x), C.byref(d), _ptr(x), _ptr(in_scale), _ptr(in_shift), int(bool(in_relu)), _ptr(w),
              _ptr(y), _ptr(partial), C.byref(rows), _ptr(ws), nws, _stream(x))
     return y, partial, rows.value
+
+
+def conv_fwd_bn(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, gamma, beta, running_mean, running_var, momentum, eps,
+                training):
+    """conv_fwd + bn_finalize of its output in one call -> (y, (scale, shift, save_mean, save_invstd))."""
+    if os.environ.get('FFPN_TWO_CALLS'):                                # debugging aid: the two separate entry points
+        y, partial, rows = conv_fwd(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, want_stats=training)
+        return y, bn_finalize(partial, rows, y.numel() // y.shape[-1], gamma, beta, running_mean, running_var, momentum, eps, training)
+    _chk(x, 'x')
+    cout = w.shape[0]
+    d = make_desc(x.shape, cout, kernel, stride, pad, x.dtype)
+    y = torch.empty((d.B, d.oS, d.oW, d.oH, cout), dtype=x.dtype, device=x.device)
+    partial = new_partial(x.device, 2, cout) if training else None
+    rows = C.c_int(0)
+    ws, nws = _workspace(d, x)
+    out = torch.empty(4, cout, dtype=torch.float32, device=x.device)
+    count = y.numel() // cout
+    lib.call('ffpn_conv_fwd_bn', _dev(x), C.byref(d), _ptr(x), _ptr(in_scale), _ptr(in_shift), int(bool(in_relu)), _ptr(w), _ptr(y),
+             _ptr(partial), C.byref(rows), float(count), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+             float(momentum), float(eps), int(bool(training)), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(ws), nws,
+             _stream(x))
+    return y, (out[0], out[1], out[2], out[3])
 
 
 def conv_dgrad(dy, w, x_shape, kernel, stride, pad, addend=None):

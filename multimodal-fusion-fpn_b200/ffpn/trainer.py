@@ -7,6 +7,7 @@ nn.Parameters are views), ONE sum all-reduce of the flat gradient over NCCL (NVL
 followed by one fused SGD kernel that applies the 1/world scale.  Forward+backward(+SGD on one GPU) can be
 captured into a CUDA graph: the step is ~1.5k small launches otherwise.
 """
+import os
 from typing import Dict, Optional
 
 import torch
@@ -70,7 +71,7 @@ class FusionTrainer:
     def forward_backward(self, batch):
         from . import functional, ops
         from .functional import get_compute_dtype
-        if get_compute_dtype() == torch.bfloat16:
+        if get_compute_dtype() == torch.bfloat16 and not os.environ.get('FFPN_NO_ARENA'):
             if self._arena_state == 0:
                 self._arena = torch.empty(96 << 20, dtype=torch.uint8, device=self.flat_p.device)
                 ops.weight_arena_begin(self._arena)

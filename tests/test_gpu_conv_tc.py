@@ -35,6 +35,8 @@ CASES = [
     ('l5_311', 256, 256, (3, 1, 1), (1, 0, 0), (2, 8, 8, 8)),
     ('sc_111', 16, 32, (1, 1, 1), (0, 0, 0), (2, 3, 20, 24)),
     ('sc_111_big', 128, 256, (1, 1, 1), (0, 0, 0), (1, 4, 8, 8)),
+    # flat mode with > 2^16 positions (regression: reciprocal division in the epilogue must stay exact)
+    ('sc_111_p160k', 16, 32, (1, 1, 1), (0, 0, 0), (8, 320, 64, 1)),
     ('proj_114', 64, 64, (1, 1, 4), (0, 0, 0), (2, 4, 16, 8)),
     ('proj_114_l5', 256, 256, (1, 1, 4), (0, 0, 0), (2, 4, 8, 8)),
     ('dec_331', 96, 32, (3, 3, 1), (1, 1, 0), (2, 16, 24, 1)),
