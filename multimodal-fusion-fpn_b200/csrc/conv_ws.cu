@@ -447,11 +447,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       for (int c0 = 0; c0 < p.Cout; c0 += 32) {
         const int c = c0 + cl;
         double a = 0.0, b = 0.0;
-        if (c < p.Cout)
-          for (int r = rl; r < rows; r += 16) {
+        if (c < p.Cout) {
+          // grid.x <= 160 rows -> at most 10 per row lane: issue all loads first (one L2 round trip), then add in order
+          float va[10], vb[10];
+#pragma unroll
+          for (int u = 0; u < 10; u++) {
+            const int r = rl + 16 * u;
+            va[u] = r < rows ? __ldcg(p.stat + ((size_t)r * 2 + 0) * p.Cout + c) : 0.f;
+            vb[u] = r < rows ? __ldcg(p.stat + ((size_t)r * 2 + 1) * p.Cout + c) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 10; u++) { a += (double)va[u]; b += (double)vb[u]; }
+          for (int r = rl + 160; r < rows; r += 16) {
             a += (double)__ldcg(p.stat + ((size_t)r * 2 + 0) * p.Cout + c);
             b += (double)__ldcg(p.stat + ((size_t)r * 2 + 1) * p.Cout + c);
           }
+        }
         __syncthreads();
         red[(rl * 32 + cl) * 2 + 0] = a;
         red[(rl * 32 + cl) * 2 + 1] = b;
@@ -751,9 +762,11 @@ int ffpn_conv_fwd_ws_bn(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, c
                         const float* w, void* y, float* stat_partial, int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st,
                         double count, float momentum, float eps, const float* gamma, const float* beta, float* rmean, float* rvar,
                         float* scale, float* shift, float* smean, float* sinvstd) {
-  static int nofin = -1;
-  if (nofin < 0) { const char* e = getenv("FFPN_NO_FIN"); nofin = e ? atoi(e) : 0; }
-  if (nofin) return -1;
+  // Measured on B200 (C2 step, same box A/B): 13.3 ms with the last-CTA finalize vs 12.9 ms with the separate 3-block finalize
+  // kernel -- the serial tail in one CTA costs more than the launch it saves.  Off unless FFPN_FUSED_FIN=1.
+  static int fused = -1;
+  if (fused < 0) { const char* e = getenv("FFPN_FUSED_FIN"); fused = e ? atoi(e) : 0; }
+  if (!fused) return -1;
   ffpn_bn_fin fin;
   fin.count = count; fin.momentum = momentum; fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.running_mean = rmean;
   fin.running_var = rvar; fin.scale = scale; fin.shift = shift; fin.save_mean = smean; fin.save_invstd = sinvstd;

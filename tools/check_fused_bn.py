@@ -1,5 +1,6 @@
 """conv_fwd_bn (finalize fused into the conv kernel) against conv_fwd + bn_finalize at the C2 level shapes."""
 import os, sys
+os.environ.setdefault("FFPN_FUSED_FIN", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'multimodal-fusion-fpn_b200'))
 import torch
