@@ -162,6 +162,156 @@ stem_wgrad_kernel(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy,
   }
 }
 
+// Same kernel with compile-time kernel extents: the tap loops unroll completely.
+template <typename T, int KS, int KW, int KH>
+__global__ void __launch_bounds__(ST_THREADS)
+stem_fwd_kernel_t(StemGeom g, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
+                float* __restrict__ stat_partial) {
+  __shared__ float w_s[ST_MAXTAPS * ST_C];
+  __shared__ float red[(ST_THREADS / 32) * 2 * ST_C];
+  constexpr int ntaps = KS * KW * KH;
+  for (int i = threadIdx.x; i < ntaps * ST_C; i += ST_THREADS) w_s[i] = w[(i % ST_C) * ntaps + i / ST_C];   // [tap][co]
+  __syncthreads();
+  float ssum[ST_C], ssq[ST_C];
+#pragma unroll
+  for (int i = 0; i < ST_C; i++) { ssum[i] = 0.f; ssq[i] = 0.f; }
+  const int64_t nlines = (int64_t)g.B * g.oS * g.oW;
+  for (int64_t line = blockIdx.x; line < nlines; line += gridDim.x) {
+    const int ow = (int)(line % g.oW);
+    const int os = (int)((line / g.oW) % g.oS);
+    const int b = (int)(line / ((int64_t)g.oW * g.oS));
+    for (int oh = threadIdx.x; oh < g.oH; oh += ST_THREADS) {
+      float acc[ST_C];
+#pragma unroll
+      for (int i = 0; i < ST_C; i++) acc[i] = 0.f;
+#pragma unroll
+      for (int ts = 0; ts < KS; ts++) {
+        const int s = os - g.pS + ts;
+#pragma unroll
+        for (int tw = 0; tw < KW; tw++) {
+          const int ww = ow - g.pW + tw;
+          const bool ok_sw = s >= 0 && s < g.S && ww >= 0 && ww < g.W;
+          const T* xl = x + (((int64_t)b * g.S + s) * g.W + ww) * g.H;
+#pragma unroll
+          for (int th = 0; th < KH; th++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int tap = (ts * KW + tw) * KH + th;
+            const int h = oh - g.pH + th;
+            if (ok_sw && h >= 0 && h < g.H) {
+              const float xv = Elem<T>::ld1(xl + h);
+              const float4* wr = reinterpret_cast<const float4*>(w_s + tap * ST_C);
+#pragma unroll
+              for (int q = 0; q < ST_C / 4; q++) {
+                const float4 wv = wr[q];
+                acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
+                acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
+              }
+            }
+          }
+        }
+      }
+      T* yp = y + (line * g.oH + oh) * ST_C;
+#pragma unroll
+      for (int i = 0; i < ST_C; i++) acc[i] = Elem<T>::rnd(acc[i]);
+      constexpr int VEC = Elem<T>::VEC;
+#pragma unroll
+      for (int q = 0; q < ST_C / VEC; q++) {
+        float v[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; j++) v[j] = acc[q * VEC + j];
+        Elem<T>::store(yp + q * VEC, v);
+      }
+#pragma unroll
+      for (int i = 0; i < ST_C; i++) { ssum[i] += acc[i]; ssq[i] = fmaf(acc[i], acc[i], ssq[i]); }
+    }
+  }
+  if (stat_partial != nullptr) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < ST_C; i++) {
+      const float a = warp_sum(ssum[i]), b2 = warp_sum(ssq[i]);
+      if (lane == 0) { red[wid * 2 * ST_C + i] = a; red[wid * 2 * ST_C + ST_C + i] = b2; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * ST_C) {
+      float v = 0.f;
+      for (int k = 0; k < ST_THREADS / 32; k++) v += red[k * 2 * ST_C + threadIdx.x];
+      stat_partial[(int64_t)blockIdx.x * 2 * ST_C + threadIdx.x] = v;     // [row][2][16]
+    }
+  }
+}
+
+
+// Compile-time kernel extents: the tap index is a constant in every unrolled iteration (the generic kernel has to
+// compare it against all NT accumulator rows).
+template <typename T, int KS, int KW, int KH>
+__global__ void __launch_bounds__(ST_THREADS)
+stem_wgrad_kernel_t(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
+  constexpr int NT = KS * KW * KH;
+  __shared__ float red[(ST_THREADS / 32) * NT * ST_C];
+  float acc[NT][ST_C];
+#pragma unroll
+  for (int t = 0; t < NT; t++)
+#pragma unroll
+    for (int i = 0; i < ST_C; i++) acc[t][i] = 0.f;
+  const int64_t nlines = (int64_t)g.B * g.oS * g.oW;
+  constexpr int VEC = Elem<T>::VEC;
+  for (int64_t line = blockIdx.x; line < nlines; line += gridDim.x) {
+    const int ow = (int)(line % g.oW);
+    const int os = (int)((line / g.oW) % g.oS);
+    const int b = (int)(line / ((int64_t)g.oW * g.oS));
+    for (int oh = threadIdx.x; oh < g.oH; oh += ST_THREADS) {
+      float d[ST_C];
+      const T* dp = dy + (line * g.oH + oh) * ST_C;
+#pragma unroll
+      for (int q = 0; q < ST_C / VEC; q++) {
+        float v[VEC];
+        Elem<T>::load(dp + q * VEC, v);
+#pragma unroll
+        for (int j = 0; j < VEC; j++) d[q * VEC + j] = v[j];
+      }
+#pragma unroll
+      for (int ts = 0; ts < KS; ts++) {
+        const int s = os - g.pS + ts;
+#pragma unroll
+        for (int tw = 0; tw < KW; tw++) {
+          const int ww = ow - g.pW + tw;
+          const bool ok_sw = s >= 0 && s < g.S && ww >= 0 && ww < g.W;
+          const T* xl = x + (((int64_t)b * g.S + s) * g.W + ww) * g.H;
+#pragma unroll
+          for (int th = 0; th < KH; th++) {
+            constexpr int unused = 0; (void)unused;
+            const int tap = (ts * KW + tw) * KH + th;
+            const int h = oh - g.pH + th;
+            float xv = 0.f;
+            if (ok_sw && h >= 0 && h < g.H) xv = Elem<T>::ld1(xl + h);
+#pragma unroll
+            for (int i = 0; i < ST_C; i++) acc[tap][i] = fmaf(xv, d[i], acc[tap][i]);
+          }
+        }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < NT; t++)
+#pragma unroll
+    for (int i = 0; i < ST_C; i++) {
+      const float a = warp_sum(acc[t][i]);
+      if (lane == 0) red[(wid * NT + t) * ST_C + i] = a;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NT * ST_C; i += ST_THREADS) {
+    float v = 0.f;
+    for (int k = 0; k < ST_THREADS / 32; k++) v += red[k * NT * ST_C + i];
+    const int t = i / ST_C, co = i % ST_C;
+    atomicAdd(dw + co * NT + t, v);            // master layout [Cout][Cin=1][taps]
+  }
+}
+
+
 bool stem_geom(const ffpn_conv_desc* d, StemGeom& g) {
   if (d->Cin != 1 || d->Cout != ST_C) return false;
   if (d->sS != 1 || d->sW != 1 || d->sH != 1) return false;
@@ -191,6 +341,13 @@ int ffpn_stem_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const f
   if (!stem_geom(d, g)) FFPN_FAIL(ctx, "stem_fwd: unsupported geometry");
   const int64_t nlines = (int64_t)g.B * g.oS * g.oW;
   const int grid = (int)(nlines < FFPN_STAT_ROWS ? nlines : FFPN_STAT_ROWS);
+#define STEM_FW(KS, KW, KH)                                                                                                  \
+  if (g.kS == KS && g.kW == KW && g.kH == KH) {                                                                              \
+    if (d->dtype == FFPN_F32) stem_fwd_kernel_t<float, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const float*)x, w, (float*)y, stat_partial); \
+    else stem_fwd_kernel_t<bf16, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const bf16*)x, w, (bf16*)y, stat_partial);        \
+  } else
+  STEM_FW(1, 3, 3) STEM_FW(1, 1, 1) STEM_FW(1, 1, 3) STEM_FW(1, 3, 1)
+#undef STEM_FW
   if (d->dtype == FFPN_F32) stem_fwd_kernel<float><<<grid, ST_THREADS, 0, st>>>(g, (const float*)x, w, (float*)y, stat_partial);
   else stem_fwd_kernel<bf16><<<grid, ST_THREADS, 0, st>>>(g, (const bf16*)x, w, (bf16*)y, stat_partial);
   FFPN_CHECK_LAUNCH(ctx, "stem_fwd");
@@ -205,6 +362,15 @@ int ffpn_stem_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const
   const int64_t nlines = (int64_t)g.B * g.oS * g.oW;
   const int64_t cap = (int64_t)ctx->num_sms * 4;
   const int grid = (int)(nlines < cap ? nlines : cap);
+#define STEM_WT(KS, KW, KH)                                                                                                  \
+  if (g.kS == KS && g.kW == KW && g.kH == KH) {                                                                              \
+    if (d->dtype == FFPN_F32) stem_wgrad_kernel_t<float, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const float*)x, (const float*)dy, dw); \
+    else stem_wgrad_kernel_t<bf16, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const bf16*)x, (const bf16*)dy, dw);           \
+    FFPN_CHECK_LAUNCH(ctx, "stem_wgrad");                                                                                    \
+    return 0;                                                                                                                \
+  }
+  STEM_WT(1, 3, 3) STEM_WT(1, 1, 1) STEM_WT(1, 1, 3) STEM_WT(1, 3, 1)
+#undef STEM_WT
 #define STEM_WG(T, NT) stem_wgrad_kernel<T, NT><<<grid, ST_THREADS, 0, st>>>(g, (const T*)x, (const T*)dy, dw)
   if (d->dtype == FFPN_F32) { if (nt == 1) STEM_WG(float, 1); else if (nt == 3) STEM_WG(float, 3); else if (nt == 9) STEM_WG(float, 9); else FFPN_FAIL(ctx, "stem_wgrad: taps"); }
   else { if (nt == 1) STEM_WG(bf16, 1); else if (nt == 3) STEM_WG(bf16, 3); else if (nt == 9) STEM_WG(bf16, 9); else FFPN_FAIL(ctx, "stem_wgrad: taps"); }

@@ -10,6 +10,8 @@
 // one accumulator per tap.  (tools/umma_probe.cu verifies overlapping slabs and unaligned starts on the hardware.)
 // Accumulators stay in TMEM for the whole persistent CTA; every CTA then stores its partial tile to the workspace and
 // a second small kernel sums the partials in a fixed order into the state_dict layout: no atomics, bitwise reproducible.
+#include <math.h>
+
 #include "ws_common.cuh"
 
 namespace {
@@ -427,6 +429,16 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
       const int ntiles = p.NB * p.nD * p.nI;
       int gx = num_sms / gy; if (gx < 1) gx = 1;
       if (gx > ntiles) gx = ntiles;
+      {
+        // K-split: the MMA chain of a CTA shrinks with 1/gx, the partial tiles the reduce kernel has to read grow with gx.
+        // T(gx) ~ A / gx + B * gx  ->  gx* = sqrt(A / B)  (A: one CTA doing all tiles, B: one more partial-tile set from L2)
+        const double mma_cyc = p.N <= 64 ? (p.M == 64 ? 29.0 : 44.0) : 0.5 * p.N;
+        const double A = (double)ntiles * (Kpad / 16) * p.acc_per_cta * mma_cyc / 1900.0;                       // us
+        const double B = (double)gy * p.acc_per_cta * 128.0 * p.colsN * 4.0 / 2.5e6 + 0.02;                     // us per split
+        int best = (int)(sqrt(A / B) + 0.5);
+        if (best < 1) best = 1;
+        if (best < gx) gx = best;
+      }
       p.gx = gx;
       w.grid = dim3(gx, gy);
       w.smem = WG2_HDR + (size_t)nst * stage;
