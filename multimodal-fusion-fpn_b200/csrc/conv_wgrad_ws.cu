@@ -267,15 +267,18 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
 }
 
 // Sum the per-CTA partial tiles (fixed order) and add them to dW in the state_dict layout [Cout][Cin][taps].
+template <int LANES>
 __global__ void wgrad_reduce_kernel(const WgWsParams p, float* __restrict__ dw) {
-  // four lanes per output, each summing every fourth partial tile (eight loads in flight), combined with two shuffles in
+  // LANES = 4 (small weight tensors, latency-bound): four lanes per output, each summing every fourth partial tile (eight loads in flight), combined with two shuffles in
   // a fixed order: the loop is L2-latency bound, so the shorter dependent chains matter more than the coalescing
   const int Cr = p.pair_cin ? p.pair_cin : p.Cin, ntr = p.pair_cin ? 3 : p.ntaps;     // real (state_dict) input channels / taps
   const int64_t total = (int64_t)p.Cout * Cr * ntr;
-  const int sub = threadIdx.x & 3;
-  const int64_t nthr = ((int64_t)gridDim.x * blockDim.x) >> 2;
+  // LANES = 1 (large weight tensors, bandwidth-bound): one lane per output, consecutive lanes read consecutive columns
+  constexpr int SH = LANES == 4 ? 2 : 0;
+  const int sub = threadIdx.x & (LANES - 1);
+  const int64_t nthr = ((int64_t)gridDim.x * blockDim.x) >> SH;
   const int64_t rounds = (total + nthr - 1) / nthr;
-  int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> SH;
   for (int64_t r = 0; r < rounds; r++, idx += nthr) {                 // uniform trip count: the shuffles stay converged
     const bool live = idx < total;
     float acc = 0.f;
@@ -308,16 +311,18 @@ __global__ void wgrad_reduce_kernel(const WgWsParams p, float* __restrict__ dw) 
       const float* src = p.part + (((size_t)y * p.gx) * p.acc_per_cta + a) * (size_t)(128 * p.colsN) + (size_t)lanei * p.colsN + col;
       const size_t stride = (size_t)p.acc_per_cta * (128 * p.colsN);
       int k = sub;
-      for (; k + 28 < p.gx; k += 32) {
+      for (; k + 7 * LANES < p.gx; k += 8 * LANES) {
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = src[(size_t)(k + 4 * u) * stride];
+        for (int u = 0; u < 8; u++) v[u] = src[(size_t)(k + LANES * u) * stride];
         acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
       }
-      for (; k < p.gx; k += 4) acc += src[(size_t)k * stride];
+      for (; k < p.gx; k += LANES) acc += src[(size_t)k * stride];
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (LANES == 4) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    }
     if (live && sub == 0) dw[((size_t)co * Cr + cir) * ntr + tapr] += acc;   // accumulate contract of ffpn_conv_wgrad
   }
 }
@@ -429,16 +434,6 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
       const int ntiles = p.NB * p.nD * p.nI;
       int gx = num_sms / gy; if (gx < 1) gx = 1;
       if (gx > ntiles) gx = ntiles;
-      {
-        // K-split: the MMA chain of a CTA shrinks with 1/gx, the partial tiles the reduce kernel has to read grow with gx.
-        // T(gx) ~ A / gx + B * gx  ->  gx* = sqrt(A / B)  (A: one CTA doing all tiles, B: one more partial-tile set from L2)
-        const double mma_cyc = p.N <= 64 ? (p.M == 64 ? 29.0 : 44.0) : 0.5 * p.N;
-        const double A = (double)ntiles * (Kpad / 16) * p.acc_per_cta * mma_cyc / 1900.0;                       // us
-        const double B = (double)gy * p.acc_per_cta * 128.0 * p.colsN * 4.0 / 2.5e6 + 0.02;                     // us per split
-        int best = (int)(sqrt(A / B) + 0.5);
-        if (best < 1) best = 1;
-        if (best < gx) gx = best;
-      }
       p.gx = gx;
       w.grid = dim3(gx, gy);
       w.smem = WG2_HDR + (size_t)nst * stage;
@@ -541,8 +536,13 @@ int ffpn_conv_wgrad_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
   conv_wgrad_ws_kernel<<<pl.grid, WG2_THREADS, pl.smem, st>>>(p, tmx, tmy);
   FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_ws");
   const int64_t total = pair ? (int64_t)d->Cout * d->Cin * 3 : (int64_t)p.Cout * p.Cin * p.ntaps;
-  const int blocks = (int)((total * 4 + 255) / 256 < 1184 ? (total * 4 + 255) / 256 : 1184);
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p, dw);
+  if (total <= 65536) {
+    const int blocks = (int)((total * 4 + 255) / 256 < 1184 ? (total * 4 + 255) / 256 : 1184);
+    wgrad_reduce_kernel<4><<<blocks, 256, 0, st>>>(p, dw);
+  } else {
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    wgrad_reduce_kernel<1><<<blocks, 256, 0, st>>>(p, dw);
+  }
   FFPN_CHECK_LAUNCH(ctx, "wgrad_reduce");
   return 0;
 }
