@@ -764,9 +764,7 @@ int ffpn_conv_fwd_ws_bn(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, c
                         float* scale, float* shift, float* smean, float* sinvstd) {
   // Measured on B200 (C2 step, same box A/B): 13.3 ms with the last-CTA finalize vs 12.9 ms with the separate 3-block finalize
   // kernel -- the serial tail in one CTA costs more than the launch it saves.  Off unless FFPN_FUSED_FIN=1.
-  static int fused = -1;
-  if (fused < 0) { const char* e = getenv("FFPN_FUSED_FIN"); fused = e ? atoi(e) : 0; }
-  if (!fused) return -1;
+  { const char* e = getenv("FFPN_FUSED_FIN"); if (!(e && atoi(e))) return -1; }      // read per call: tests toggle it
   ffpn_bn_fin fin;
   fin.count = count; fin.momentum = momentum; fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.running_mean = rmean;
   fin.running_var = rvar; fin.scale = scale; fin.shift = shift; fin.save_mean = smean; fin.save_invstd = sinvstd;

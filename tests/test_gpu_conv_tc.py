@@ -2,6 +2,8 @@
 bf16-rounded inputs, forward (with the fused BN+ReLU prologue and the BatchNorm partial sums) and dgrad
 (with the fused residual addend).  impl=2 forces the tensor-core kernel and errors if it does not apply.
 Tolerance: rel-L2 <= 1e-2 (bf16 operands incl. the re-rounded prologue output, fp32 accumulate)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -90,6 +92,23 @@ def test_conv_tc(case):
             assert torch.equal(y, y1)
             if s1 == (1, 1, 1) and cin in (16, 32, 64, 128, 256, 768) and name != 'sc_111':
                 assert rows1 == rows and torch.equal(partial[:rows * 2 * cout], partial1[:rows * 2 * cout])
+            # one-call conv + BatchNorm finalize: default (separate finalize kernel) and fused into the conv's last CTA
+            # (FFPN_FUSED_FIN=1: measured slower on B200, so it is off by default, but it must stay correct)
+            gm, bt = (0.5 + torch.rand(cout, generator=g)).cuda(), (0.2 * torch.randn(cout, generator=g)).cuda()
+            ref_aff = ops.bn_finalize(partial, rows, y.numel() // cout, gm, bt, torch.zeros(cout).cuda(), torch.ones(cout).cuda(),
+                                      0.1, 1e-5, True)
+            for fused in ('0', '1'):
+                os.environ['FFPN_FUSED_FIN'] = fused
+                try:
+                    rm, rv = torch.zeros(cout).cuda(), torch.ones(cout).cuda()
+                    yb, aff = ops.conv_fwd_bn(phys(x).to(dt), w, k, s1, p, sc if affine else None, sh if affine else None, affine,
+                                              gm, bt, rm, rv, 0.1, 1e-5, True)
+                finally:
+                    os.environ.pop('FFPN_FUSED_FIN', None)
+                torch.cuda.synchronize()
+                assert torch.equal(yb, y)
+                for a_, b_ in zip(aff, ref_aff):
+                    assert torch.allclose(a_, b_, rtol=1e-5, atol=1e-6), (fused, (a_ - b_).abs().max())
             ops.set_conv_impl(1)
             y2, _, _ = ops.conv_fwd(phys(x).to(dt), w, k, s1, p, sc if affine else None, sh if affine else None, affine)
             assert rel(y.float(), y2.float()) <= 1e-2
