@@ -101,15 +101,20 @@ __global__ void resize2d_bwd_kernel(int mode, int B, int Si, int Wi, int So, int
                                     int ostride, int coff, const int32_t* __restrict__ idx, T* __restrict__ dx) {
   const int64_t n = (int64_t)B * Si * Wi * C;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
-    const int c = (int)(i % C);
-    int64_t r = i / C;
-    const int w = (int)(r % Wi); r /= Wi;
-    const int s = (int)(r % Si);
-    const int b = (int)(r / Si);
+    uint32_t r32 = (uint32_t)i;                       // n < 2^31 is checked by the caller
+    const int c = (int)(r32 % (uint32_t)C); r32 /= (uint32_t)C;
+    const int w = (int)(r32 % (uint32_t)Wi); r32 /= (uint32_t)Wi;
+    const int s = (int)(r32 % (uint32_t)Si);
+    const int b = (int)(r32 / (uint32_t)Si);
     const T* db = dout + (int64_t)b * So * Wo * ostride + coff + c;
     float g = 0.f;
     if (mode == 0) {
       g = Elem<T>::ld1(db + ((int64_t)s * Wo + w) * ostride);
+    } else if (mode == 1 && Si % So == 0 && Wi % Wo == 0) {
+      // adaptive windows tile the input exactly: one output window per input position (the shapes of the model)
+      const int os = s / (Si / So), ow = w / (Wi / Wo);
+      const int64_t o = (((int64_t)b * So + os) * Wo + ow);
+      if (idx[o * C + c] == s * Wi + w) g = Elem<T>::ld1(dout + o * ostride + coff + c);
     } else if (mode == 1) {
       // outputs o whose window [floor(o*in/out), ceil((o+1)*in/out)) contains s:  o in [lo, hi]
       int slo = (int)(((int64_t)s * So) / Si); while (slo > 0 && win_end(slo - 1, Si, So) > s) slo--;
@@ -334,6 +339,7 @@ extern "C" int ffpn_resize2d_bwd(ffpn_ctx* ctx, int dtype, int mode, int64_t B, 
                                  void* stream) {
   if (mode < 0 || mode > 2) FFPN_FAIL(ctx, "resize2d: unknown mode %d", mode);
   if (mode == 1 && idx == nullptr) FFPN_FAIL(ctx, "resize2d_bwd: adaptive max needs the forward argmax");
+  if (B * Si * Wi * C >= (1ll << 31)) FFPN_FAIL(ctx, "resize2d_bwd: more than 2^31 elements");
   const int g = grid_of(ctx, B * Si * Wi * C);
   if (dtype == FFPN_F32) resize2d_bwd_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>(mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)dout, ostride, coff, idx, (float*)dx);
   else resize2d_bwd_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>(mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)dout, ostride, coff, idx, (bf16*)dx);
