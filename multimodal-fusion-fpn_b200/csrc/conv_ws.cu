@@ -529,8 +529,10 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   if (cs16 < 0) { const char* e = getenv("FFPN_WS_CS32"); cs16 = (e && atoi(e)) ? 0 : 1; }
   p.colstride = (p.Npad < 32 && !cs16) ? 32 : p.Npad;
   p.nbuf = p.colstride <= 64 ? 4 : 2;                    // TMEM tile buffers: deep enough that the MMAs never wait for the epilogue
+  { const char* e = getenv("FFPN_WS_NBUF"); if (e && (atoi(e) == 2 || atoi(e) == 4) && (512 / atoi(e)) >= p.colstride) p.nbuf = atoi(e); }   // tuning
   int nmb_cap = (512 / p.nbuf) / p.colstride;
   if (nmb_cap > 8) nmb_cap = 8;
+  { const char* e = getenv("FFPN_WS_NMBCAP"); if (e && atoi(e) >= 1 && atoi(e) < nmb_cap) nmb_cap = atoi(e); }                                // tuning
   if (nmb_cap < 1) return w;
   const size_t budget = 227 * 1024 - WS_HDR - 1024;
   const size_t w_total = (size_t)ntaps * p.Cin * p.Npad * 2;
