@@ -312,6 +312,179 @@ stem_wgrad_kernel_t(StemGeom g, const T* __restrict__ x, const T* __restrict__ d
 }
 
 
+// Forward, four consecutive depth positions per thread: every weight vector fetched from shared memory is used for four
+// outputs (the one-position kernel is bound by its 36 LDS.128 per output), 128 contiguous bytes stored per thread.
+template <typename T, int KS, int KW, int KH>
+__global__ void __launch_bounds__(ST_THREADS)
+stem_fwd_kernel_v4(StemGeom g, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
+                   float* __restrict__ stat_partial) {
+  constexpr int NT = KS * KW * KH;
+  __shared__ float w_s[NT * ST_C];
+  __shared__ float red[(ST_THREADS / 32) * 2 * ST_C];
+  for (int i = threadIdx.x; i < NT * ST_C; i += ST_THREADS) w_s[i] = w[(i % ST_C) * NT + i / ST_C];   // [tap][co]
+  __syncthreads();
+  float ssum[ST_C], ssq[ST_C];
+#pragma unroll
+  for (int i = 0; i < ST_C; i++) { ssum[i] = 0.f; ssq[i] = 0.f; }
+  const uint32_t nq = (uint32_t)(g.oH + 3) >> 2;
+  const uint32_t nlines = (uint32_t)g.B * g.oS * g.oW;
+  const uint32_t total = nlines * nq;
+  for (uint32_t it = blockIdx.x * ST_THREADS + threadIdx.x; it < total; it += gridDim.x * ST_THREADS) {
+    const uint32_t line = it / nq;
+    const int oh0 = (int)(it - line * nq) * 4;
+    const int ow = (int)(line % (uint32_t)g.oW);
+    const int os = (int)((line / (uint32_t)g.oW) % (uint32_t)g.oS);
+    const int b = (int)(line / ((uint32_t)g.oW * g.oS));
+    float acc[4][ST_C];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int i = 0; i < ST_C; i++) acc[j][i] = 0.f;
+#pragma unroll
+    for (int ts = 0; ts < KS; ts++) {
+      const int s = os - g.pS + ts;
+#pragma unroll
+      for (int tw = 0; tw < KW; tw++) {
+        const int ww = ow - g.pW + tw;
+        const bool ok_sw = s >= 0 && s < g.S && ww >= 0 && ww < g.W;
+        const T* xl = x + (((int64_t)b * g.S + s) * g.W + ww) * g.H;
+        float xv[KH + 3];
+#pragma unroll
+        for (int u = 0; u < KH + 3; u++) {
+          const int h = oh0 - g.pH + u;
+          xv[u] = (ok_sw && h >= 0 && h < g.H) ? Elem<T>::ld1(xl + h) : 0.f;
+        }
+#pragma unroll
+        for (int th = 0; th < KH; th++) {
+          const float4* wr = reinterpret_cast<const float4*>(w_s + ((ts * KW + tw) * KH + th) * ST_C);
+#pragma unroll
+          for (int q = 0; q < ST_C / 4; q++) {
+            const float4 wv = wr[q];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              acc[j][4 * q + 0] = fmaf(xv[th + j], wv.x, acc[j][4 * q + 0]);
+              acc[j][4 * q + 1] = fmaf(xv[th + j], wv.y, acc[j][4 * q + 1]);
+              acc[j][4 * q + 2] = fmaf(xv[th + j], wv.z, acc[j][4 * q + 2]);
+              acc[j][4 * q + 3] = fmaf(xv[th + j], wv.w, acc[j][4 * q + 3]);
+            }
+          }
+        }
+      }
+    }
+    constexpr int VEC = Elem<T>::VEC;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (oh0 + j < g.oH) {
+        T* yp = y + ((int64_t)line * g.oH + oh0 + j) * ST_C;
+#pragma unroll
+        for (int i = 0; i < ST_C; i++) acc[j][i] = Elem<T>::rnd(acc[j][i]);
+#pragma unroll
+        for (int q = 0; q < ST_C / VEC; q++) {
+          float v[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; e++) v[e] = acc[j][q * VEC + e];
+          Elem<T>::store(yp + q * VEC, v);
+        }
+#pragma unroll
+        for (int i = 0; i < ST_C; i++) { ssum[i] += acc[j][i]; ssq[i] = fmaf(acc[j][i], acc[j][i], ssq[i]); }
+      }
+    }
+  }
+  if (stat_partial != nullptr) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < ST_C; i++) {
+      const float a = warp_sum(ssum[i]), b2 = warp_sum(ssq[i]);
+      if (lane == 0) { red[wid * 2 * ST_C + i] = a; red[wid * 2 * ST_C + ST_C + i] = b2; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * ST_C) {
+      float v = 0.f;
+      for (int k = 0; k < ST_THREADS / 32; k++) v += red[k * 2 * ST_C + threadIdx.x];
+      stat_partial[(int64_t)blockIdx.x * 2 * ST_C + threadIdx.x] = v;     // [row][2][16]
+    }
+  }
+}
+
+// Weight gradient, channels split over two threads per position (72 accumulators each instead of 144): three times
+// the occupancy of the one-thread kernel, whose 188 registers leave two blocks per SM.
+template <typename T, int KS, int KW, int KH>
+__global__ void __launch_bounds__(ST_THREADS)
+stem_wgrad_kernel_v2(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
+  constexpr int NT = KS * KW * KH;
+  constexpr int HC = ST_C / 2;
+  __shared__ float red[(ST_THREADS / 32) * NT * ST_C];
+  float acc[NT][HC];
+#pragma unroll
+  for (int t = 0; t < NT; t++)
+#pragma unroll
+    for (int i = 0; i < HC; i++) acc[t][i] = 0.f;
+  const int half = threadIdx.x & 1;
+  const uint32_t nlines = (uint32_t)g.B * g.oS * g.oW;
+  const uint32_t total = nlines * (uint32_t)g.oH;
+  for (uint32_t it = (blockIdx.x * ST_THREADS + threadIdx.x) >> 1; it < total; it += (gridDim.x * ST_THREADS) >> 1) {
+    const uint32_t line = it / (uint32_t)g.oH;
+    const int oh = (int)(it - line * (uint32_t)g.oH);
+    const int ow = (int)(line % (uint32_t)g.oW);
+    const int os = (int)((line / (uint32_t)g.oW) % (uint32_t)g.oS);
+    const int b = (int)(line / ((uint32_t)g.oW * g.oS));
+    float d[HC];
+    {
+      const T* dp = dy + ((int64_t)line * g.oH + oh) * ST_C + half * HC;
+      if (sizeof(T) == 2) {
+        float v[Elem<T>::VEC];
+        Elem<T>::load(dp, v);
+#pragma unroll
+        for (int i = 0; i < HC; i++) d[i] = v[i % Elem<T>::VEC];
+      } else {
+#pragma unroll
+        for (int q = 0; q < HC / Elem<T>::VEC; q++) {
+          float v[Elem<T>::VEC];
+          Elem<T>::load(dp + q * Elem<T>::VEC, v);
+#pragma unroll
+          for (int e = 0; e < Elem<T>::VEC; e++) d[q * Elem<T>::VEC + e] = v[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int ts = 0; ts < KS; ts++) {
+      const int s = os - g.pS + ts;
+#pragma unroll
+      for (int tw = 0; tw < KW; tw++) {
+        const int ww = ow - g.pW + tw;
+        const bool ok_sw = s >= 0 && s < g.S && ww >= 0 && ww < g.W;
+        const T* xl = x + (((int64_t)b * g.S + s) * g.W + ww) * g.H;
+#pragma unroll
+        for (int th = 0; th < KH; th++) {
+          const int h = oh - g.pH + th;
+          float xv = 0.f;
+          if (ok_sw && h >= 0 && h < g.H) xv = Elem<T>::ld1(xl + h);
+#pragma unroll
+          for (int i = 0; i < HC; i++) acc[(ts * KW + tw) * KH + th][i] = fmaf(xv, d[i], acc[(ts * KW + tw) * KH + th][i]);
+        }
+      }
+    }
+  }
+  // lanes with equal parity hold the same channel half: sum over the 16 lanes of each parity, then over the warps
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < NT; t++)
+#pragma unroll
+    for (int i = 0; i < HC; i++) {
+      float a = acc[t][i];
+#pragma unroll
+      for (int o = 16; o >= 2; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane < 2) red[(wid * NT + t) * ST_C + lane * HC + i] = a;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NT * ST_C; i += ST_THREADS) {
+    float v = 0.f;
+    for (int k = 0; k < ST_THREADS / 32; k++) v += red[k * NT * ST_C + i];
+    const int t = i / ST_C, co = i % ST_C;
+    atomicAdd(dw + co * NT + t, v);            // master layout [Cout][Cin=1][taps]
+  }
+}
+
 bool stem_geom(const ffpn_conv_desc* d, StemGeom& g) {
   if (d->Cin != 1 || d->Cout != ST_C) return false;
   if (d->sS != 1 || d->sW != 1 || d->sH != 1) return false;
@@ -343,8 +516,8 @@ int ffpn_stem_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const f
   const int grid = (int)(nlines < FFPN_STAT_ROWS ? nlines : FFPN_STAT_ROWS);
 #define STEM_FW(KS, KW, KH)                                                                                                  \
   if (g.kS == KS && g.kW == KW && g.kH == KH) {                                                                              \
-    if (d->dtype == FFPN_F32) stem_fwd_kernel_t<float, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const float*)x, w, (float*)y, stat_partial); \
-    else stem_fwd_kernel_t<bf16, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const bf16*)x, w, (bf16*)y, stat_partial);        \
+    if (d->dtype == FFPN_F32) stem_fwd_kernel_v4<float, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const float*)x, w, (float*)y, stat_partial); \
+    else stem_fwd_kernel_v4<bf16, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const bf16*)x, w, (bf16*)y, stat_partial);       \
   } else
   STEM_FW(1, 3, 3) STEM_FW(1, 1, 1) STEM_FW(1, 1, 3) STEM_FW(1, 3, 1)
 #undef STEM_FW
@@ -364,8 +537,8 @@ int ffpn_stem_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const
   const int grid = (int)(nlines < cap ? nlines : cap);
 #define STEM_WT(KS, KW, KH)                                                                                                  \
   if (g.kS == KS && g.kW == KW && g.kH == KH) {                                                                              \
-    if (d->dtype == FFPN_F32) stem_wgrad_kernel_t<float, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const float*)x, (const float*)dy, dw); \
-    else stem_wgrad_kernel_t<bf16, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const bf16*)x, (const bf16*)dy, dw);           \
+    if (d->dtype == FFPN_F32) stem_wgrad_kernel_v2<float, KS, KW, KH><<<grid * 2, ST_THREADS, 0, st>>>(g, (const float*)x, (const float*)dy, dw); \
+    else stem_wgrad_kernel_v2<bf16, KS, KW, KH><<<grid * 2, ST_THREADS, 0, st>>>(g, (const bf16*)x, (const bf16*)dy, dw);      \
     FFPN_CHECK_LAUNCH(ctx, "stem_wgrad");                                                                                    \
     return 0;                                                                                                                \
   }
