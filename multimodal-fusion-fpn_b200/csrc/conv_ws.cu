@@ -93,7 +93,7 @@ struct WsRing {
 };
 
 // NREG: 16-column chunks whose statistics are accumulated in registers (Npad == 16 * NREG); 0 = shuffle per chunk.
-template <int NREG>
+template <int NREG, bool ADD>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ WsParams p,
                                                                 const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -256,12 +256,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       const int nitems = my_nmb * nch;
       for (int it0 = 0; it0 < nitems; it0 += BATCH) {
         uint32_t raw[BATCH][16];
+        long long oposv[BATCH];
+        bool validv[BATCH];
+        uint4 addv[ADD ? BATCH : 1][2];
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
           const int idx = it0 + u;
+          validv[u] = false; oposv[u] = 0;
+          if (ADD) addv[ADD ? u : 0][0] = addv[ADD ? u : 0][1] = make_uint4(0u, 0u, 0u, 0u);
           if (idx < nitems) {
             const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
             tmem_ld16_nowait(t_tile + (uint32_t)((half + 2 * mbi) * p.colstride + ch * 16), raw[u]);
+            const int m = (half + 2 * mbi) * 128 + quad * 32 + lane;
+            const int j = p.Lr == 1 ? m : (int)__umulhi((uint32_t)m, magicLr), ii = m - j * p.Lr;
+            const int i = tc.i0 + ii;
+            // flat / slice modes have Xp >= every i (one line): the reciprocal is only exact while i * Xp < 2^32 (mode 0)
+            const int oy = i < p.Xp ? 0 : (p.Xp == 1 ? i : (int)__umulhi((uint32_t)i, magicXp)), ox = i - oy * p.Xp;
+            validv[u] = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX);
+            oposv[u] = (long long)tc.nb * p.outNB + (long long)(tc.d0 + j) * p.outD + (long long)oy * p.outY + ox;
+            if (ADD && validv[u]) {
+              // residual-branch gradient: all loads of the batch are issued before anything waits on them
+              const int cbase = n0 + ch * 16;
+              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + oposv[u] * p.Cout + cbase);
+              if (cbase < p.Cout) addv[ADD ? u : 0][0] = ap[0];
+              if (cbase + 8 < p.Cout) addv[ADD ? u : 0][1] = ap[1];
+            }
           }
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -270,23 +289,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           const int idx = it0 + u;
           if (idx < nitems) {
             const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
-            const int m = (half + 2 * mbi) * 128 + quad * 32 + lane;
-            const int j = p.Lr == 1 ? m : (int)__umulhi((uint32_t)m, magicLr), ii = m - j * p.Lr;
-            const int i = tc.i0 + ii;
-            // flat / slice modes have Xp >= every i (one line): the reciprocal is only exact while i * Xp < 2^32 (mode 0)
-            const int oy = i < p.Xp ? 0 : (p.Xp == 1 ? i : (int)__umulhi((uint32_t)i, magicXp)), ox = i - oy * p.Xp;
-            const bool valid = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX);
-            const long long opos = (long long)tc.nb * p.outNB + (long long)(tc.d0 + j) * p.outD + (long long)oy * p.outY + ox;
+            const bool valid = validv[u];
+            const long long opos = oposv[u];
             float v[16];
 #pragma unroll
             for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[u][q]);
             const int cbase = n0 + ch * 16;
-            if (p.has_add && valid) {
-              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + opos * p.Cout + cbase);
+            if (ADD && valid) {
 #pragma unroll
               for (int h2 = 0; h2 < 2; h2++) {
                 if (cbase + h2 * 8 < p.Cout) {
-                  const uint4 a4 = ap[h2];
+                  const uint4 a4 = addv[ADD ? u : 0][h2];
                   const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
                   for (int q = 0; q < 4; q++) {
@@ -708,9 +721,10 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_ws: cannot raise dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -730,10 +744,11 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     cudaMalloc(&p.trace, 64 * 16 * sizeof(long long));
     cudaMemset(p.trace, 0, 64 * 16 * sizeof(long long));
   }
-  const int nreg = (p.has_stats && p.Npad == 16) ? 1 : (p.has_stats && p.Npad == 32) ? 2 : 0;
-  if (nreg == 1) conv_ws_kernel<1><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
-  else if (nreg == 2) conv_ws_kernel<2><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
-  else conv_ws_kernel<0><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
+  const int nreg = p.has_add ? 0 : (p.has_stats && p.Npad == 16) ? 1 : (p.has_stats && p.Npad == 32) ? 2 : 0;
+  if (p.has_add) conv_ws_kernel<0, true><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
+  else if (nreg == 1) conv_ws_kernel<1, false><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
+  else if (nreg == 2) conv_ws_kernel<2, false><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
+  else conv_ws_kernel<0, false><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
   FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_ws" : "conv_fwd_ws");
   if (trace_mode) {
     static long long h[64 * 16];

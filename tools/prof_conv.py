@@ -25,6 +25,10 @@ elif kind == 'fwd311':
 elif kind == 'dgrad133':
     w = torch.randn(C, C, 1, 3, 3, device='cuda', generator=g) * 0.1
     fn = lambda: ops.conv_dgrad(x, w, tuple(x.shape), (1, 3, 3), (1, 1, 1), (0, 1, 1))
+elif kind == 'dgrad133add':
+    w = torch.randn(C, C, 1, 3, 3, device='cuda', generator=g) * 0.1
+    add = torch.randn_like(x)
+    fn = lambda: ops.conv_dgrad(x, w, tuple(x.shape), (1, 3, 3), (1, 1, 1), (0, 1, 1), addend=add)
 elif kind in ('dgrad111', 'dgrad113', 'dgrad131'):
     k = {'dgrad111': (1, 1, 1), 'dgrad113': (1, 1, 3), 'dgrad131': (1, 3, 1)}[kind]
     pd = tuple((v - 1) // 2 for v in k)
