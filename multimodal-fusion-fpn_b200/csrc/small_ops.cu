@@ -154,6 +154,38 @@ __global__ void resize2d_bwd_kernel(int mode, int B, int Si, int Wi, int So, int
   }
 }
 
+// Adaptive-max backward when the windows tile the input exactly (Si % So == 0, Wi % Wo == 0): one output window per input
+// position, a vector of channels per thread (16-byte accesses instead of one bf16 at a time).
+template <typename T>
+__global__ void resize2d_bwd_max_tiled_kernel(int B, int Si, int Wi, int So, int Wo, int C, const T* __restrict__ dout, int ostride,
+                                              int coff, const int32_t* __restrict__ idx, T* __restrict__ dx) {
+  constexpr int VEC = Elem<T>::VEC;
+  const int cvecs = C / VEC;
+  const uint32_t n = (uint32_t)B * Si * Wi * cvecs;
+  const int fs = Si / So, fw = Wi / Wo;
+  for (uint32_t i = blockIdx.x * TH + threadIdx.x; i < n; i += gridDim.x * TH) {
+    uint32_t r = i;
+    const int cv = (int)(r % (uint32_t)cvecs); r /= (uint32_t)cvecs;
+    const int w = (int)(r % (uint32_t)Wi); r /= (uint32_t)Wi;
+    const int s = (int)(r % (uint32_t)Si);
+    const int b = (int)(r / (uint32_t)Si);
+    const int64_t o = ((int64_t)b * So + s / fs) * Wo + w / fw;
+    const int self = s * Wi + w;
+    float g[VEC], out[VEC];
+    Elem<T>::load(dout + o * ostride + coff + cv * VEC, g);
+    const int4* ip = reinterpret_cast<const int4*>(idx + o * C + cv * VEC);
+#pragma unroll
+    for (int q = 0; q < VEC / 4; q++) {
+      const int4 iv = ip[q];
+      out[4 * q + 0] = iv.x == self ? g[4 * q + 0] : 0.f;
+      out[4 * q + 1] = iv.y == self ? g[4 * q + 1] : 0.f;
+      out[4 * q + 2] = iv.z == self ? g[4 * q + 2] : 0.f;
+      out[4 * q + 3] = iv.w == self ? g[4 * q + 3] : 0.f;
+    }
+    Elem<T>::store(dx + (int64_t)i * VEC, out);
+  }
+}
+
 template <typename T>
 __global__ void upsample_fwd_kernel(int B, int Si, int Wi, int fS, int fW, int C, const T* __restrict__ x,
                                     T* __restrict__ out, int ostride, int coff) {
@@ -340,6 +372,16 @@ extern "C" int ffpn_resize2d_bwd(ffpn_ctx* ctx, int dtype, int mode, int64_t B, 
   if (mode < 0 || mode > 2) FFPN_FAIL(ctx, "resize2d: unknown mode %d", mode);
   if (mode == 1 && idx == nullptr) FFPN_FAIL(ctx, "resize2d_bwd: adaptive max needs the forward argmax");
   if (B * Si * Wi * C >= (1ll << 31)) FFPN_FAIL(ctx, "resize2d_bwd: more than 2^31 elements");
+  {
+    const int vec = dtype == FFPN_F32 ? 4 : 8;
+    if (mode == 1 && Si % So == 0 && Wi % Wo == 0 && C % vec == 0 && ostride % vec == 0 && coff % vec == 0) {
+      const int gv = grid_of(ctx, B * Si * Wi * (C / vec));
+      if (dtype == FFPN_F32) resize2d_bwd_max_tiled_kernel<float><<<gv, TH, 0, (cudaStream_t)stream>>>((int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)dout, ostride, coff, idx, (float*)dx);
+      else resize2d_bwd_max_tiled_kernel<bf16><<<gv, TH, 0, (cudaStream_t)stream>>>((int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)dout, ostride, coff, idx, (bf16*)dx);
+      FFPN_CHECK_LAUNCH(ctx, "resize2d_bwd");
+      return 0;
+    }
+  }
   const int g = grid_of(ctx, B * Si * Wi * C);
   if (dtype == FFPN_F32) resize2d_bwd_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>(mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)dout, ostride, coff, idx, (float*)dx);
   else resize2d_bwd_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>(mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)dout, ostride, coff, idx, (bf16*)dx);
