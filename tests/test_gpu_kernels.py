@@ -204,6 +204,25 @@ def test_resize2d(ops, dt, mode):
     assert rel(logical(dx.float()).cpu()[..., 0], xr.grad) <= tol(dt)
 
 
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('out', [(5, 48), (10, 24), (20, 12)])
+def test_resize2d_max_tiled(ops, dt, out):
+    """Adaptive-max resize whose windows tile the input exactly (the shapes of the model: 320x128 -> 32x128): the
+    vectorised backward fast path, against torch's adaptive_max_pool3d backward; ties included."""
+    g = torch.Generator().manual_seed(17)
+    B, C, Si, Wi = 2, 16, 20, 48
+    x = (torch.randn(B, C, Si, Wi, generator=g) * 2).round() / 2
+    xr = x.to(dt).float().clone().requires_grad_(True)
+    ref, ref_i = F.adaptive_max_pool3d(xr[:, :, :, :, None], (out[0], out[1], 1), return_indices=True)
+    xp = x.cuda().permute(0, 2, 3, 1).unsqueeze(3).contiguous().to(dt)
+    o, idx = ops.resize2d_fwd(xp, out[0], out[1], '2d_max')
+    assert torch.equal(idx.permute(0, 3, 1, 2).cpu().long(), ref_i[..., 0])
+    dout = torch.randn(ref.shape, generator=g).to(dt).float()
+    ref.backward(dout)
+    dx = ops.resize2d_bwd(phys(dout.cuda()).to(dt), tuple(xp.shape), '2d_max', idx)
+    assert torch.equal(logical(dx.float()).cpu()[..., 0], xr.grad.to(dt).float())
+
+
 def test_resize_golden_fixture(ops, golden_dir):
     ix = np.load(os.path.join(golden_dir, 'index_ops.npz'))
     for name, o in (('a8x32', (8, 32)), ('a8x16', (8, 16)), ('a3x7', (3, 7))):
