@@ -45,6 +45,7 @@ bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double co
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, int training, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  pdl_prologue();
   __shared__ double red[FIN_LANES][32][2];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 bn_bwd_reduce_kernel(int64_t P, int C, const T* __restrict__ dA, const T* __restrict__ y,
                      const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                      float* __restrict__ partial) {
+  pdl_prologue();
   constexpr int VEC = Elem<T>::VEC;
   __shared__ float smem[2 * EW_THREADS * VEC];
   const int cvecs = C / VEC;
@@ -137,6 +139,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int ncols, i
                                        const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ cA,
                                        float* __restrict__ cP, float* __restrict__ cQ) {
+  pdl_prologue();
   __shared__ double red[FIN_LANES][32][2];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
@@ -162,6 +165,7 @@ bn_bwd_apply_kernel(int64_t nvec, int C, const T* __restrict__ dA, const T* __re
                     const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                     const float* __restrict__ cA, const float* __restrict__ cP, const float* __restrict__ cQ,
                     T* __restrict__ dy) {
+  pdl_prologue();
   constexpr int VEC = Elem<T>::VEC;
   const int cvecs = C / VEC;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * EW_THREADS) {
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 block_end_fwd_kernel(int64_t nvec, int C, const T* __restrict__ y, const float* __restrict__ a,
                      const float* __restrict__ b, const T* __restrict__ res, const float* __restrict__ ra,
                      const float* __restrict__ rb, T* __restrict__ z) {
+  pdl_prologue();
   constexpr int VEC = Elem<T>::VEC;
   const int cvecs = C / VEC;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * EW_THREADS) {
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 block_end_bwd_kernel(int B, int S, int W, int H, int C, int kS, int kW, int kH, const T* __restrict__ dz,
                      const T* __restrict__ dzp, const T* __restrict__ z, const T* __restrict__ y,
                      const T* __restrict__ yres, T* __restrict__ G, float* __restrict__ partial) {
+  pdl_prologue();
   constexpr int VEC = Elem<T>::VEC;
   __shared__ float smem[NCOL * EW_THREADS * VEC];
   const int cvecs = C / VEC;
@@ -299,6 +305,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 block_end_bwd_pool_kernel(int B, int S, int W, int H, int C, const T* __restrict__ dz, const T* __restrict__ dzp,
                           const T* __restrict__ z, const T* __restrict__ y, const T* __restrict__ yres, T* __restrict__ G,
                           float* __restrict__ partial) {
+  pdl_prologue();
   constexpr int VEC = Elem<T>::VEC;
   constexpr int NW = KS * KW * KH;
   __shared__ float smem[NCOL * EW_THREADS * VEC];
@@ -366,6 +373,7 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 maxpool_fwd_kernel(int B, int S, int W, int H, int C, int kS, int kW, int kH, const T* __restrict__ z,
                    T* __restrict__ zp, int64_t* __restrict__ idx) {
+  pdl_prologue();
   constexpr int VEC = Elem<T>::VEC;
   const int cvecs = C / VEC;
   const int oS = S / kS, oW = W / kW, oH = H / kH;
@@ -405,6 +413,7 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 maxpool_bwd_kernel(int B, int S, int W, int H, int C, int kS, int kW, int kH, const T* __restrict__ z,
                    const T* __restrict__ dzp, T* __restrict__ dz) {
+  pdl_prologue();
   constexpr int VEC = Elem<T>::VEC;
   const int cvecs = C / VEC;
   const int oS = S / kS, oW = W / kW, oH = H / kH;
@@ -458,7 +467,7 @@ extern "C" int ffpn_bn_finalize(ffpn_ctx* ctx, const float* stat_partial, int st
                                 float momentum, float eps, int training, float* scale, float* shift, float* save_mean,
                                 float* save_invstd, void* stream) {
   if (training && (stat_partial == nullptr || stat_rows <= 0)) FFPN_FAIL(ctx, "bn_finalize: training needs partial sums");
-  bn_finalize_kernel<<<(C + 31) / 32, 32 * FIN_LANES, 0, (cudaStream_t)stream>>>(
+  ffpn_launch(bn_finalize_kernel, (C + 31) / 32, 32 * FIN_LANES, 0, (cudaStream_t)stream, 
       stat_partial, stat_rows, C, count, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift,
       save_mean, save_invstd);
   FFPN_CHECK_LAUNCH(ctx, "bn_finalize");
@@ -473,13 +482,13 @@ extern "C" int ffpn_bn_bwd_reduce(ffpn_ctx* ctx, int dtype, int64_t P, int C, co
     CHECK_C(ctx, C, 4, "bn_bwd_reduce");
     const int lanes = EW_THREADS / (C / 4);
     const int g = ffpn_grid_for(P, lanes * 8, min(ctx->num_sms * 4, FFPN_STAT_ROWS));
-    bn_bwd_reduce_kernel<float><<<g, EW_THREADS, 0, st>>>(P, C, (const float*)dA, (const float*)y, scale, shift, relu, partial);
+    ffpn_launch(bn_bwd_reduce_kernel<float>, g, EW_THREADS, 0, st, P, C, (const float*)dA, (const float*)y, scale, shift, relu, partial);
     *rows = g;
   } else {
     CHECK_C(ctx, C, 8, "bn_bwd_reduce");
     const int lanes = EW_THREADS / (C / 8);
     const int g = ffpn_grid_for(P, lanes * 8, min(ctx->num_sms * 4, FFPN_STAT_ROWS));
-    bn_bwd_reduce_kernel<bf16><<<g, EW_THREADS, 0, st>>>(P, C, (const bf16*)dA, (const bf16*)y, scale, shift, relu, partial);
+    ffpn_launch(bn_bwd_reduce_kernel<bf16>, g, EW_THREADS, 0, st, P, C, (const bf16*)dA, (const bf16*)y, scale, shift, relu, partial);
     *rows = g;
   }
   FFPN_CHECK_LAUNCH(ctx, "bn_bwd_reduce");
@@ -489,7 +498,7 @@ extern "C" int ffpn_bn_bwd_reduce(ffpn_ctx* ctx, int dtype, int64_t P, int C, co
 extern "C" int ffpn_bn_bwd_finalize(ffpn_ctx* ctx, const float* partial, int rows, int ncols, int ycol, int C,
                                     double count, const float* gamma, const float* save_mean, const float* save_invstd,
                                     float* dgamma, float* dbeta, float* cA, float* cP, float* cQ, void* stream) {
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * FIN_LANES, 0, (cudaStream_t)stream>>>(
+  ffpn_launch(bn_bwd_finalize_kernel, (C + 31) / 32, 32 * FIN_LANES, 0, (cudaStream_t)stream, 
       partial, rows, ncols, ycol, C, count, gamma, save_mean, save_invstd, dgamma, dbeta, cA, cP, cQ);
   FFPN_CHECK_LAUNCH(ctx, "bn_bwd_finalize");
   return 0;
@@ -502,11 +511,11 @@ extern "C" int ffpn_bn_bwd_apply(ffpn_ctx* ctx, int dtype, int64_t P, int C, con
   if (dtype == FFPN_F32) {
     CHECK_C(ctx, C, 4, "bn_bwd_apply");
     const int64_t nvec = P * C / 4;
-    bn_bwd_apply_kernel<float><<<ew_grid(ctx, nvec), EW_THREADS, 0, st>>>(nvec, C, (const float*)dA, (const float*)y, scale, shift, relu, cA, cP, cQ, (float*)dy);
+    ffpn_launch(bn_bwd_apply_kernel<float>, ew_grid(ctx, nvec), EW_THREADS, 0, st, nvec, C, (const float*)dA, (const float*)y, scale, shift, relu, cA, cP, cQ, (float*)dy);
   } else {
     CHECK_C(ctx, C, 8, "bn_bwd_apply");
     const int64_t nvec = P * C / 8;
-    bn_bwd_apply_kernel<bf16><<<ew_grid(ctx, nvec), EW_THREADS, 0, st>>>(nvec, C, (const bf16*)dA, (const bf16*)y, scale, shift, relu, cA, cP, cQ, (bf16*)dy);
+    ffpn_launch(bn_bwd_apply_kernel<bf16>, ew_grid(ctx, nvec), EW_THREADS, 0, st, nvec, C, (const bf16*)dA, (const bf16*)y, scale, shift, relu, cA, cP, cQ, (bf16*)dy);
   }
   FFPN_CHECK_LAUNCH(ctx, "bn_bwd_apply");
   return 0;
@@ -519,11 +528,11 @@ extern "C" int ffpn_block_end_fwd(ffpn_ctx* ctx, int dtype, int64_t P, int C, co
   if (dtype == FFPN_F32) {
     CHECK_C(ctx, C, 4, "block_end_fwd");
     const int64_t nvec = P * C / 4;
-    block_end_fwd_kernel<float><<<ew_grid(ctx, nvec), EW_THREADS, 0, st>>>(nvec, C, (const float*)y, a, b, (const float*)res, ra, rb, (float*)z);
+    ffpn_launch(block_end_fwd_kernel<float>, ew_grid(ctx, nvec), EW_THREADS, 0, st, nvec, C, (const float*)y, a, b, (const float*)res, ra, rb, (float*)z);
   } else {
     CHECK_C(ctx, C, 8, "block_end_fwd");
     const int64_t nvec = P * C / 8;
-    block_end_fwd_kernel<bf16><<<ew_grid(ctx, nvec), EW_THREADS, 0, st>>>(nvec, C, (const bf16*)y, a, b, (const bf16*)res, ra, rb, (bf16*)z);
+    ffpn_launch(block_end_fwd_kernel<bf16>, ew_grid(ctx, nvec), EW_THREADS, 0, st, nvec, C, (const bf16*)y, a, b, (const bf16*)res, ra, rb, (bf16*)z);
   }
   FFPN_CHECK_LAUNCH(ctx, "block_end_fwd");
   return 0;
@@ -545,7 +554,7 @@ extern "C" int ffpn_block_end_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S
     const int64_t nwin = B * (S / kS) * (W / kW) * (H / kH);
     const int gw = ffpn_grid_for(nwin, lanes * 2, min(ctx->num_sms * 4, FFPN_STAT_ROWS));
 #define LAUNCH_BP(T, N, KS_, KW_, KH_)                                                                                              \
-    block_end_bwd_pool_kernel<T, N, KS_, KW_, KH_><<<gw, EW_THREADS, 0, st>>>((int)B, (int)S, (int)W, (int)H, C, (const T*)dz, (const T*)dzp, \
+    ffpn_launch(block_end_bwd_pool_kernel<T, N, KS_, KW_, KH_>, gw, EW_THREADS, 0, st, (int)B, (int)S, (int)W, (int)H, C, (const T*)dz, (const T*)dzp, \
                                                                               (const T*)z, (const T*)y, (const T*)yres, (T*)G, partial)
 #define DISPATCH_BP(KS_, KW_, KH_)                                                                  \
     if (kS == KS_ && kW == KW_ && kH == KH_) {                                                      \
@@ -559,7 +568,7 @@ extern "C" int ffpn_block_end_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S
 #undef DISPATCH_BP
 #undef LAUNCH_BP
   }
-#define LAUNCH_BE(T, N) block_end_bwd_kernel<T, N><<<g, EW_THREADS, 0, st>>>((int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const T*)dz, (const T*)dzp, (const T*)z, (const T*)y, (const T*)yres, (T*)G, partial)
+#define LAUNCH_BE(T, N) ffpn_launch(block_end_bwd_kernel<T, N>, g, EW_THREADS, 0, st, (int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const T*)dz, (const T*)dzp, (const T*)z, (const T*)y, (const T*)yres, (T*)G, partial)
   if (dtype == FFPN_F32) { if (yres) LAUNCH_BE(float, 3); else LAUNCH_BE(float, 2); }
   else { if (yres) LAUNCH_BE(bf16, 3); else LAUNCH_BE(bf16, 2); }
 #undef LAUNCH_BE
@@ -577,9 +586,9 @@ extern "C" int ffpn_maxpool_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S, 
   const int64_t nvec = B * (S / kS) * (W / kW) * (H / kH) * (C / vec);
   if (nvec <= 0) FFPN_FAIL(ctx, "maxpool: empty output");
   if (dtype == FFPN_F32)
-    maxpool_fwd_kernel<float><<<ew_grid(ctx, nvec), EW_THREADS, 0, st>>>((int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const float*)z, (float*)zp, idx);
+    ffpn_launch(maxpool_fwd_kernel<float>, ew_grid(ctx, nvec), EW_THREADS, 0, st, (int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const float*)z, (float*)zp, idx);
   else
-    maxpool_fwd_kernel<bf16><<<ew_grid(ctx, nvec), EW_THREADS, 0, st>>>((int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const bf16*)z, (bf16*)zp, idx);
+    ffpn_launch(maxpool_fwd_kernel<bf16>, ew_grid(ctx, nvec), EW_THREADS, 0, st, (int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const bf16*)z, (bf16*)zp, idx);
   FFPN_CHECK_LAUNCH(ctx, "maxpool_fwd");
   return 0;
 }
@@ -592,9 +601,9 @@ extern "C" int ffpn_maxpool_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S, 
   CHECK_C(ctx, C, vec, "maxpool_bwd");
   const int64_t nvec = B * S * W * H * (C / vec);
   if (dtype == FFPN_F32)
-    maxpool_bwd_kernel<float><<<ew_grid(ctx, nvec), EW_THREADS, 0, st>>>((int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const float*)z, (const float*)dzp, (float*)dz);
+    ffpn_launch(maxpool_bwd_kernel<float>, ew_grid(ctx, nvec), EW_THREADS, 0, st, (int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const float*)z, (const float*)dzp, (float*)dz);
   else
-    maxpool_bwd_kernel<bf16><<<ew_grid(ctx, nvec), EW_THREADS, 0, st>>>((int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const bf16*)z, (const bf16*)dzp, (bf16*)dz);
+    ffpn_launch(maxpool_bwd_kernel<bf16>, ew_grid(ctx, nvec), EW_THREADS, 0, st, (int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const bf16*)z, (const bf16*)dzp, (bf16*)dz);
   FFPN_CHECK_LAUNCH(ctx, "maxpool_bwd");
   return 0;
 }

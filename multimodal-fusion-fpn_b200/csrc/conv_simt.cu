@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(CONV_THREADS)
 conv_simt_kernel(Geom g, const T* __restrict__ x, const float* __restrict__ in_scale,
                  const float* __restrict__ in_shift, int in_relu, const float* __restrict__ w,
                  const T* __restrict__ addend, T* __restrict__ y, float* __restrict__ stat_partial) {
+  pdl_prologue();
   extern __shared__ float smem[];
   const int ntaps = g.kS * g.kW * g.kH;
   const int KIN = TRANSPOSED ? g.Cout : g.Cin;
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__((KI_B / 2) * (KO_B / 2))
 conv_wgrad_simt_kernel(Geom g, const T* __restrict__ x, const float* __restrict__ in_scale,
                        const float* __restrict__ in_shift, int in_relu, const T* __restrict__ dy,
                        float* __restrict__ dw, int n_ki_tiles) {
+  pdl_prologue();
   constexpr int NT = (KI_B / 2) * (KO_B / 2);
   extern __shared__ float smem[];
   const int ntaps = g.kS * g.kW * g.kH;
@@ -299,9 +301,9 @@ int launch_conv(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const v
   size_t smem = (size_t)(ntaps * CI_CHUNK * CO_T + 2 * CI_CHUNK) * sizeof(float);
   smem = max(smem, (size_t)(CONV_THREADS / 32) * 2 * CO_T * sizeof(float));
   if (transposed)
-    conv_simt_kernel<T, true><<<grid, CONV_THREADS, smem, st>>>(g, (const T*)x, nullptr, nullptr, 0, w, (const T*)addend, (T*)y, nullptr);
+    ffpn_launch(conv_simt_kernel<T, true>, grid, CONV_THREADS, smem, st, g, (const T*)x, nullptr, nullptr, 0, w, (const T*)addend, (T*)y, nullptr);
   else
-    conv_simt_kernel<T, false><<<grid, CONV_THREADS, smem, st>>>(g, (const T*)x, in_scale, in_shift, in_relu, w, (const T*)addend,
+    ffpn_launch(conv_simt_kernel<T, false>, grid, CONV_THREADS, smem, st, g, (const T*)x, in_scale, in_shift, in_relu, w, (const T*)addend,
                                                                (T*)y, stat_partial);
   FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_simt" : "conv_fwd_simt");
   if (stat_rows) *stat_rows = gx;
@@ -325,9 +327,9 @@ int launch_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const fl
   dim3 grid(gx, nki * nko);
   const size_t smem = (size_t)(WG_PT * kob + ntaps * WG_PT * kib) * sizeof(float) + (size_t)ntaps * WG_PT * sizeof(int);
   if (small)
-    conv_wgrad_simt_kernel<T, 16, 16><<<grid, 64, smem, st>>>(g, (const T*)x, in_scale, in_shift, in_relu, (const T*)dy, dw, nki);
+    ffpn_launch(conv_wgrad_simt_kernel<T, 16, 16>, grid, 64, smem, st, g, (const T*)x, in_scale, in_shift, in_relu, (const T*)dy, dw, nki);
   else
-    conv_wgrad_simt_kernel<T, 32, 32><<<grid, 256, smem, st>>>(g, (const T*)x, in_scale, in_shift, in_relu, (const T*)dy, dw, nki);
+    ffpn_launch(conv_wgrad_simt_kernel<T, 32, 32>, grid, 256, smem, st, g, (const T*)x, in_scale, in_shift, in_relu, (const T*)dy, dw, nki);
   FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_simt");
   return 0;
 }

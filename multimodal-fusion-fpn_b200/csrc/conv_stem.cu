@@ -18,6 +18,7 @@ template <typename T>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_fwd_kernel(StemGeom g, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                 float* __restrict__ stat_partial) {
+  pdl_prologue();
   __shared__ float w_s[ST_MAXTAPS * ST_C];
   __shared__ float red[(ST_THREADS / 32) * 2 * ST_C];
   const int ntaps = g.kS * g.kW * g.kH;
@@ -93,6 +94,7 @@ stem_fwd_kernel(StemGeom g, const T* __restrict__ x, const float* __restrict__ w
 template <typename T, int NT>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_wgrad_kernel(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
+  pdl_prologue();
   __shared__ float red[(ST_THREADS / 32) * NT * ST_C];
   float acc[NT][ST_C];
 #pragma unroll
@@ -167,6 +169,7 @@ template <typename T, int KS, int KW, int KH>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_fwd_kernel_t(StemGeom g, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                 float* __restrict__ stat_partial) {
+  pdl_prologue();
   __shared__ float w_s[ST_MAXTAPS * ST_C];
   __shared__ float red[(ST_THREADS / 32) * 2 * ST_C];
   constexpr int ntaps = KS * KW * KH;
@@ -249,6 +252,7 @@ stem_fwd_kernel_t(StemGeom g, const T* __restrict__ x, const float* __restrict__
 template <typename T, int KS, int KW, int KH>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_wgrad_kernel_t(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
+  pdl_prologue();
   constexpr int NT = KS * KW * KH;
   __shared__ float red[(ST_THREADS / 32) * NT * ST_C];
   float acc[NT][ST_C];
@@ -318,6 +322,7 @@ template <typename T, int KS, int KW, int KH>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_fwd_kernel_v4(StemGeom g, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                    float* __restrict__ stat_partial) {
+  pdl_prologue();
   constexpr int NT = KS * KW * KH;
   __shared__ float w_s[NT * ST_C];
   __shared__ float red[(ST_THREADS / 32) * 2 * ST_C];
@@ -411,6 +416,7 @@ stem_fwd_kernel_v4(StemGeom g, const T* __restrict__ x, const float* __restrict_
 template <typename T, int KS, int KW, int KH>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_wgrad_kernel_v2(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
+  pdl_prologue();
   constexpr int NT = KS * KW * KH;
   constexpr int HC = ST_C / 2;
   __shared__ float red[(ST_THREADS / 32) * NT * ST_C];
@@ -516,13 +522,13 @@ int ffpn_stem_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const f
   const int grid = (int)(nlines < FFPN_STAT_ROWS ? nlines : FFPN_STAT_ROWS);
 #define STEM_FW(KS, KW, KH)                                                                                                  \
   if (g.kS == KS && g.kW == KW && g.kH == KH) {                                                                              \
-    if (d->dtype == FFPN_F32) stem_fwd_kernel_v4<float, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const float*)x, w, (float*)y, stat_partial); \
-    else stem_fwd_kernel_v4<bf16, KS, KW, KH><<<grid, ST_THREADS, 0, st>>>(g, (const bf16*)x, w, (bf16*)y, stat_partial);       \
+    if (d->dtype == FFPN_F32) ffpn_launch(stem_fwd_kernel_v4<float, KS, KW, KH>, grid, ST_THREADS, 0, st, g, (const float*)x, w, (float*)y, stat_partial); \
+    else ffpn_launch(stem_fwd_kernel_v4<bf16, KS, KW, KH>, grid, ST_THREADS, 0, st, g, (const bf16*)x, w, (bf16*)y, stat_partial);       \
   } else
   STEM_FW(1, 3, 3) STEM_FW(1, 1, 1) STEM_FW(1, 1, 3) STEM_FW(1, 3, 1)
 #undef STEM_FW
-  if (d->dtype == FFPN_F32) stem_fwd_kernel<float><<<grid, ST_THREADS, 0, st>>>(g, (const float*)x, w, (float*)y, stat_partial);
-  else stem_fwd_kernel<bf16><<<grid, ST_THREADS, 0, st>>>(g, (const bf16*)x, w, (bf16*)y, stat_partial);
+  if (d->dtype == FFPN_F32) ffpn_launch(stem_fwd_kernel<float>, grid, ST_THREADS, 0, st, g, (const float*)x, w, (float*)y, stat_partial);
+  else ffpn_launch(stem_fwd_kernel<bf16>, grid, ST_THREADS, 0, st, g, (const bf16*)x, w, (bf16*)y, stat_partial);
   FFPN_CHECK_LAUNCH(ctx, "stem_fwd");
   if (stat_rows) *stat_rows = grid;
   return 0;
@@ -537,14 +543,14 @@ int ffpn_stem_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const
   const int grid = (int)(nlines < cap ? nlines : cap);
 #define STEM_WT(KS, KW, KH)                                                                                                  \
   if (g.kS == KS && g.kW == KW && g.kH == KH) {                                                                              \
-    if (d->dtype == FFPN_F32) stem_wgrad_kernel_v2<float, KS, KW, KH><<<grid * 2, ST_THREADS, 0, st>>>(g, (const float*)x, (const float*)dy, dw); \
-    else stem_wgrad_kernel_v2<bf16, KS, KW, KH><<<grid * 2, ST_THREADS, 0, st>>>(g, (const bf16*)x, (const bf16*)dy, dw);      \
+    if (d->dtype == FFPN_F32) ffpn_launch(stem_wgrad_kernel_v2<float, KS, KW, KH>, grid * 2, ST_THREADS, 0, st, g, (const float*)x, (const float*)dy, dw); \
+    else ffpn_launch(stem_wgrad_kernel_v2<bf16, KS, KW, KH>, grid * 2, ST_THREADS, 0, st, g, (const bf16*)x, (const bf16*)dy, dw);      \
     FFPN_CHECK_LAUNCH(ctx, "stem_wgrad");                                                                                    \
     return 0;                                                                                                                \
   }
   STEM_WT(1, 3, 3) STEM_WT(1, 1, 1) STEM_WT(1, 1, 3) STEM_WT(1, 3, 1)
 #undef STEM_WT
-#define STEM_WG(T, NT) stem_wgrad_kernel<T, NT><<<grid, ST_THREADS, 0, st>>>(g, (const T*)x, (const T*)dy, dw)
+#define STEM_WG(T, NT) ffpn_launch(stem_wgrad_kernel<T, NT>, grid, ST_THREADS, 0, st, g, (const T*)x, (const T*)dy, dw)
   if (d->dtype == FFPN_F32) { if (nt == 1) STEM_WG(float, 1); else if (nt == 3) STEM_WG(float, 3); else if (nt == 9) STEM_WG(float, 9); else FFPN_FAIL(ctx, "stem_wgrad: taps"); }
   else { if (nt == 1) STEM_WG(bf16, 1); else if (nt == 3) STEM_WG(bf16, 3); else if (nt == 9) STEM_WG(bf16, 9); else FFPN_FAIL(ctx, "stem_wgrad: taps"); }
 #undef STEM_WG

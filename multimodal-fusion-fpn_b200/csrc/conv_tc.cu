@@ -198,8 +198,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TileCoord
         sm += __shfl_xor_sync(0xffffffffu, sm, 16);
         s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
         if (lane < 16) {
-          atomicAdd(&stat_s[ch * 16 + c], sm);
-          atomicAdd(&stat_s[p.Npad + ch * 16 + c], s2);
+          float* slot = stat_s + (warp & 7) * 2 * p.Npad;     // one slot per warp: no atomics, fixed summation order
+          slot[ch * 16 + c] += sm;
+          slot[p.Npad + ch * 16 + c] += s2;
         }
       }
     }
@@ -211,13 +212,14 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const TileCoord
 //   epilogue of the previous tile (other TMEM buffer).
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p,
                                                              const __grid_constant__ CUtensorMap tmap) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   // header: [0],[8] weight barriers, [16] mma barrier, [24] tmem base, [32] tap offsets, [144],[152] TMA barriers, [160..] stats
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 24);
   int* tapoff_s = reinterpret_cast<int*>(smem + HDR_TAPS);
   float* stat_s = reinterpret_cast<float*>(smem + HDR_STATS);
-  const uint32_t hdr = (HDR_STATS + 2 * p.Npad * 4 + 127) & ~127u;
+  const uint32_t hdr = (HDR_STATS + 16 * p.Npad * 4 + 127) & ~127u;
   float* scr = reinterpret_cast<float*>(smem + hdr);                            // [8 warps][32][SCR_STRIDE]
   const uint32_t a_off = hdr + 8 * 32 * SCR_STRIDE * 4;
   uint8_t* a_s[2] = {smem + a_off, smem + a_off + p.a_bytes};
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int set = p.nsets == 1 ? 0 : res;
     tapoff_s[tid] = set * nkc * p.rows_alloc + dd * p.Lr + dy * p.Xp + q + p.hl;
   }
-  for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) stat_s[i] = 0.f;
+  for (int i = tid; i < 16 * p.Npad; i += TC_THREADS) stat_s[i] = 0.f;   // [8 warps][2][Npad]
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)p.tmem_cols));
@@ -364,7 +366,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   if (p.has_stats) {
     for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) {
       const int which = i / p.Npad, c = i - which * p.Npad;
-      if (n0 + c < p.Cout) p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = stat_s[which * p.Npad + c];
+      if (n0 + c < p.Cout) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += stat_s[(w * 2 + which) * p.Npad + c];
+        p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = t;
+      }
     }
   }
   if (warp == 0) {
@@ -378,12 +385,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 // each other's phases.  Measured on B200 this beats the two-stage pipeline above when N <= 32.
 __global__ void __launch_bounds__(TC_THREADS, 4) conv_tc_simple_kernel(const __grid_constant__ TcParams p,
                                                                        const __grid_constant__ CUtensorMap tmap) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 24);
   int* tapoff_s = reinterpret_cast<int*>(smem + HDR_TAPS);
   float* stat_s = reinterpret_cast<float*>(smem + HDR_STATS);
-  const uint32_t hdr = (HDR_STATS + 2 * p.Npad * 4 + 127) & ~127u;
+  const uint32_t hdr = (HDR_STATS + 16 * p.Npad * 4 + 127) & ~127u;
   float* scr = reinterpret_cast<float*>(smem + hdr);
   const uint32_t a_off = hdr + 8 * 32 * SCR_STRIDE * 4;
   uint8_t* a_s = smem + a_off;
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) conv_tc_simple_kernel(const __g
     const int set = p.nsets == 1 ? 0 : res;
     tapoff_s[tid] = set * nkc * p.rows_alloc + dd * p.Lr + dy * p.Xp + q + p.hl;
   }
-  for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) stat_s[i] = 0.f;
+  for (int i = tid; i < 16 * p.Npad; i += TC_THREADS) stat_s[i] = 0.f;   // [8 warps][2][Npad]
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)p.tmem_cols));
@@ -480,7 +488,12 @@ __global__ void __launch_bounds__(TC_THREADS, 4) conv_tc_simple_kernel(const __g
   if (p.has_stats) {
     for (int i = tid; i < 2 * p.Npad; i += TC_THREADS) {
       const int which = i / p.Npad, c = i - which * p.Npad;
-      if (n0 + c < p.Cout) p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = stat_s[which * p.Npad + c];
+      if (n0 + c < p.Cout) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += stat_s[(w * 2 + which) * p.Npad + c];
+        p.stat[((size_t)blockIdx.x * 2 + which) * p.Cout + n0 + c] = t;
+      }
     }
   }
   if (warp == 0) {
@@ -526,6 +539,7 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ w, int64_t
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ntaps,
                                     int Kc, int Nc, int Npad, int KG, int nchunks, int mode, int sH, int pH, int kH,
                                     int tmin) {
+  pdl_prologue();
   const int64_t total = (int64_t)nchunks * ntaps * Kc * Npad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(pack_value(w, i, Cout, Cin, ntaps, Kc, Nc, Npad, KG, mode, sH, pH, kH, tmin));
@@ -533,6 +547,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
 
 // All images of the packed-weight arena in one launch: element -> job by binary search on the prefix sums.
 __global__ void pack_all_kernel(const ffpn_pack_job* __restrict__ jobs, int njobs, long long total, bf16* __restrict__ arena) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
@@ -648,7 +663,7 @@ Plan ffpn_tc_make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   if ((size_t)ntaps * KG * p.Npad * 2 > 200 * 1024) return pl;
   p.KG = KG; p.nkg = Cin / KG;
   p.b_bytes = (unsigned)((size_t)ntaps * KG * p.Npad * 2);
-  const uint32_t hdr = (HDR_STATS + 2 * p.Npad * 4 + 127) & ~127u;
+  const uint32_t hdr = (HDR_STATS + 16 * p.Npad * 4 + 127) & ~127u;
   const size_t fixed = hdr + 8 * 32 * SCR_STRIDE * 4 + (size_t)(p.nkg > 1 ? 2 : 1) * p.b_bytes;
   // Tile size: bounded by the TMEM columns and shared memory of the target occupancy.  Several CTAs per SM is
   // what overlaps one CTA's staging / epilogue with another's MMAs, so small-N layers aim for 4 CTAs per SM.
@@ -777,11 +792,13 @@ struct WgParams {
   const float* sc;
   const float* sh;
   float* dw;
+  long long dw_slice;    // > 0: CTA column blockIdx.x adds into its own zeroed slice dw + blockIdx.x * dw_slice (summed in a fixed order afterwards)
 };
 
 constexpr int WG_THREADS = 512;
 
 __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);          // [0], [8]: one per smem buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
@@ -937,7 +954,7 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
 #pragma unroll
           for (int k = 0; k < 16; k++) {
             const int co = co0 + ch * 16 + k;
-            if (co < p.Cout) atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.ntaps + tap, __uint_as_float(raw[k]));
+            if (co < p.Cout) atomicAdd(p.dw + (size_t)blockIdx.x * p.dw_slice + ((size_t)co * p.Cin + ci) * p.ntaps + tap, __uint_as_float(raw[k]));
           }
         }
       }
@@ -1067,6 +1084,7 @@ struct WgTmaParams {
   const float* sc;
   const float* sh;
   float* dw;
+  long long dw_slice;    // > 0: CTA column blockIdx.x adds into its own zeroed slice dw + blockIdx.x * dw_slice (summed in a fixed order afterwards)
 };
 
 constexpr int WG_STAGES = 3;          // maximum ring depth (p.nstages = 2 or 3)
@@ -1105,6 +1123,7 @@ __device__ __forceinline__ void wgrad_tma_issue(const WgTmaParams& p, const CUte
 __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tma_kernel(const __grid_constant__ WgTmaParams p,
                                                                      const __grid_constant__ CUtensorMap tmx,
                                                                      const __grid_constant__ CUtensorMap tmy) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);          // [0..2] MMA done per stage; [3..5] TMA landed per stage
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
@@ -1226,7 +1245,7 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tma_kernel(const __grid
           const int nn = ch * 16 + k;
           const int sft = nn / p.ci_t, ci = ci0 + nn - sft * p.ci_t;
           const int tap = g * p.nshift + sft;
-          if (tap < p.ntaps && ci < p.Cin) atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.ntaps + tap, __uint_as_float(raw[k]));
+          if (tap < p.ntaps && ci < p.Cin) atomicAdd(p.dw + (size_t)blockIdx.x * p.dw_slice + ((size_t)co * p.Cin + ci) * p.ntaps + tap, __uint_as_float(raw[k]));
         }
       }
     }
@@ -1384,6 +1403,38 @@ bool encode_map4(CUtensorMap* m, const void* base, const long long* dims, const 
 
 }  // namespace
 
+namespace {
+// dw[i] += sum over the K-split slices, in slice order (bitwise reproducible, unlike atomics on dw itself)
+__global__ void wgrad_slice_reduce_kernel(const float* __restrict__ part, int nslices, long long n, float* __restrict__ dw) {
+  pdl_prologue();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 3 < nslices; k += 4) {
+      a0 += part[(size_t)k * n + i];
+      a1 += part[(size_t)(k + 1) * n + i];
+      a2 += part[(size_t)(k + 2) * n + i];
+      a3 += part[(size_t)(k + 3) * n + i];
+    }
+    for (; k < nslices; k++) a0 += part[(size_t)k * n + i];
+    dw[i] += (a0 + a1) + (a2 + a3);
+  }
+}
+constexpr size_t FFPN_WG_SLICE_MAX_BYTES = (size_t)64 << 20;
+// K-split slices for the first-generation wgrad kernels: returns the slice length (elements) when the workspace can hold them
+long long wgrad_slices(const ffpn_conv_desc* d, unsigned gx, size_t ws_bytes) {
+  const long long n = (long long)d->Cout * d->Cin * d->kS * d->kW * d->kH;
+  const size_t need = (size_t)gx * (size_t)n * 4;
+  return (need <= FFPN_WG_SLICE_MAX_BYTES && need <= ws_bytes) ? n : 0;
+}
+int wgrad_slices_finish(ffpn_ctx* ctx, const float* part, unsigned gx, long long n, float* dw, cudaStream_t st) {
+  const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+  ffpn_launch(wgrad_slice_reduce_kernel, blocks, 256, 0, st, part, (int)gx, n, dw);
+  FFPN_CHECK_LAUNCH(ctx, "wgrad_slice_reduce");
+  return 0;
+}
+}  // namespace
+
 bool ffpn_wgrad_ws_supported(const ffpn_conv_desc* d);
 bool ffpn_tc_wgrad_supported(const ffpn_conv_desc* d) { return ffpn_wgrad_ws_supported(d) || make_wgrad_plan(d, 148).ok; }
 
@@ -1411,9 +1462,14 @@ int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
         if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tma: cannot raise dynamic smem: %s", cudaGetErrorString(e));
         attr_tma = true;
       }
-      conv_wgrad_tma_kernel<<<t.grid, WG_THREADS, t.smem, st>>>(q, tmx, tmy);
+      q.dw_slice = ws ? wgrad_slices(d, t.grid.x, ws_bytes) : 0;
+      if (q.dw_slice) {
+        q.dw = (float*)ws;
+        if (cudaMemsetAsync(ws, 0, (size_t)t.grid.x * q.dw_slice * 4, st) != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tma: memset failed");
+      }
+      ffpn_launch(conv_wgrad_tma_kernel, t.grid, WG_THREADS, t.smem, st, q, tmx, tmy);
       FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_tma");
-      return 0;
+      return q.dw_slice ? wgrad_slices_finish(ctx, (const float*)ws, t.grid.x, q.dw_slice, dw, st) : 0;
     }
   }
   WgPlan w = make_wgrad_plan(d, ctx->num_sms);
@@ -1427,9 +1483,14 @@ int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_wgrad_tc_kernel<<<w.grid, WG_THREADS, w.smem, st>>>(p);
+  p.dw_slice = ws ? wgrad_slices(d, w.grid.x, ws_bytes) : 0;
+  if (p.dw_slice) {
+    p.dw = (float*)ws;
+    if (cudaMemsetAsync(ws, 0, (size_t)w.grid.x * p.dw_slice * 4, st) != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tc: memset failed");
+  }
+  ffpn_launch(conv_wgrad_tc_kernel, w.grid, WG_THREADS, w.smem, st, p);
   FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_tc");
-  return 0;
+  return p.dw_slice ? wgrad_slices_finish(ctx, (const float*)ws, w.grid.x, p.dw_slice, dw, st) : 0;
 }
 
 namespace {
@@ -1442,7 +1503,12 @@ size_t ffpn_wgrad_ws_workspace_bytes(const ffpn_conv_desc* d);
 size_t ffpn_tc_workspace_bytes(const ffpn_conv_desc* d) {
   const size_t taps = (size_t)d->kS * d->kW * d->kH;
   const size_t cin = (d->Cin + 63) & ~63, cout = (d->Cout + 63) & ~63;
-  const size_t pack = taps * cin * cout * 2 + 65536, wg = ffpn_wgrad_ws_workspace_bytes(d);   // packed weights | wgrad partial tiles
+  const size_t pack = taps * cin * cout * 2 + 65536;                  // packed weights | wgrad partial tiles
+  size_t wg = ffpn_wgrad_ws_workspace_bytes(d);
+  if (wg == 0 && d->dtype == FFPN_BF16) {                              // first-generation wgrad: one dW slice per CTA column
+    const size_t slices = (size_t)296 * d->Cout * d->Cin * taps * 4;
+    if (slices <= FFPN_WG_SLICE_MAX_BYTES) wg = slices;
+  }
   return pack > wg ? pack : wg;
 }
 
@@ -1502,7 +1568,7 @@ const void* ffpn_tc_pack_weights(ffpn_ctx* ctx, const float* w, void* ws, const 
     ctx->arena_elems += total;
   }
   const int g = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
-  pack_weights_kernel<<<g, 256, 0, st>>>(w, (bf16*)out, j.Cout, j.Cin, ntaps, j.Kc, j.Nc, j.Npad, KG, nchunks, j.mode, j.sH, j.pH, j.kH,
+  ffpn_launch(pack_weights_kernel, g, 256, 0, st, w, (bf16*)out, j.Cout, j.Cin, ntaps, j.Kc, j.Nc, j.Npad, KG, nchunks, j.mode, j.sH, j.pH, j.kH,
                                          j.tmin);
   *launched = true;
   return out;
@@ -1531,7 +1597,7 @@ extern "C" int ffpn_weight_arena_pack(ffpn_ctx* ctx, void* stream) {
   if (ctx->arena_state != 2) return 0;
   const long long total = ctx->arena_elems;
   const int g = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  pack_all_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(ctx->d_jobs, ctx->njobs, total, (bf16*)ctx->arena);
+  ffpn_launch(pack_all_kernel, g, 256, 0, (cudaStream_t)stream, ctx->d_jobs, ctx->njobs, total, (bf16*)ctx->arena);
   FFPN_CHECK_LAUNCH(ctx, "weight_arena_pack");
   return 0;
 }
@@ -1578,8 +1644,8 @@ int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
     // BN+ReLU prologue: halo filled with NaN so that relu(scale*NaN+shift) = 0; without a prologue: zero fill
     if ((p.has_aff && !p.relu) || !encode_act_map(&tmap, p, x, p.has_aff != 0)) p.use_tma = 0;
   }
-  if (pl.simple) conv_tc_simple_kernel<<<grid, TC_THREADS, pl.smem, st>>>(p, tmap);
-  else conv_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(p, tmap);
+  if (pl.simple) ffpn_launch(conv_tc_simple_kernel, grid, TC_THREADS, pl.smem, st, p, tmap);
+  else ffpn_launch(conv_tc_kernel, grid, TC_THREADS, pl.smem, st, p, tmap);
   FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_tc" : "conv_fwd_tc");
   if (stat_rows) *stat_rows = pl.grid;
   return 0;

@@ -58,6 +58,7 @@ struct WgTile {
 __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __grid_constant__ WgWsParams p,
                                                                        const __grid_constant__ CUtensorMap tmx,
                                                                        const __grid_constant__ CUtensorMap tmy) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
 // Sum the per-CTA partial tiles (fixed order) and add them to dW in the state_dict layout [Cout][Cin][taps].
 template <int LANES>
 __global__ void wgrad_reduce_kernel(const WgWsParams p, float* __restrict__ dw) {
+  pdl_prologue();
   // LANES = 4 (small weight tensors, latency-bound): four lanes per output, each summing every fourth partial tile (eight loads in flight), combined with two shuffles in
   // a fixed order: the loop is L2-latency bound, so the shorter dependent chains matter more than the coalescing
   const int Cr = p.pair_cin ? p.pair_cin : p.Cin, ntr = p.pair_cin ? 3 : p.ntaps;     // real (state_dict) input channels / taps
@@ -533,15 +535,15 @@ int ffpn_conv_wgrad_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
               p.tma_mode, p.co_t, p.ci_t, p.M, p.N, p.sA, p.sB, p.passesA, p.passesB, p.acc_per_cta, p.npg, p.tY, p.tD, p.L, p.Kpad,
               p.nstages, p.stage_bytes, pl.smem, p.tmem_cols, pl.grid.x, pl.grid.y, pl.ws_bytes);
   }
-  conv_wgrad_ws_kernel<<<pl.grid, WG2_THREADS, pl.smem, st>>>(p, tmx, tmy);
+  ffpn_launch(conv_wgrad_ws_kernel, pl.grid, WG2_THREADS, pl.smem, st, p, tmx, tmy);
   FFPN_CHECK_LAUNCH(ctx, "conv_wgrad_ws");
   const int64_t total = pair ? (int64_t)d->Cout * d->Cin * 3 : (int64_t)p.Cout * p.Cin * p.ntaps;
   if (total <= 65536) {
     const int blocks = (int)((total * 4 + 255) / 256 < 1184 ? (total * 4 + 255) / 256 : 1184);
-    wgrad_reduce_kernel<4><<<blocks, 256, 0, st>>>(p, dw);
+    ffpn_launch(wgrad_reduce_kernel<4>, blocks, 256, 0, st, p, dw);
   } else {
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    wgrad_reduce_kernel<1><<<blocks, 256, 0, st>>>(p, dw);
+    ffpn_launch(wgrad_reduce_kernel<1>, blocks, 256, 0, st, p, dw);
   }
   FFPN_CHECK_LAUNCH(ctx, "wgrad_reduce");
   return 0;

@@ -96,6 +96,7 @@ struct WsRing {
 template <int NREG, bool ADD>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ WsParams p,
                                                                 const __grid_constant__ CUtensorMap tmap) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -745,10 +746,10 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     cudaMemset(p.trace, 0, 64 * 16 * sizeof(long long));
   }
   const int nreg = p.has_add ? 0 : (p.has_stats && p.Npad == 16) ? 1 : (p.has_stats && p.Npad == 32) ? 2 : 0;
-  if (p.has_add) conv_ws_kernel<0, true><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
-  else if (nreg == 1) conv_ws_kernel<1, false><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
-  else if (nreg == 2) conv_ws_kernel<2, false><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
-  else conv_ws_kernel<0, false><<<pl.grid, WS_THREADS, pl.smem, st>>>(p, tmap);
+  if (p.has_add) ffpn_launch(conv_ws_kernel<0, true>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (nreg == 1) ffpn_launch(conv_ws_kernel<1, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (nreg == 2) ffpn_launch(conv_ws_kernel<2, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else ffpn_launch(conv_ws_kernel<0, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
   FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_ws" : "conv_fwd_ws");
   if (trace_mode) {
     static long long h[64 * 16];

@@ -10,6 +10,7 @@ constexpr int TH = 256;
 template <typename T>
 __global__ void proj_tail_fwd_kernel(int64_t EW, int H, int C, const T* __restrict__ y, const float* __restrict__ a,
                                      const float* __restrict__ b, T* __restrict__ out, int ostride, int coff) {
+  pdl_prologue();
   const int64_t n = EW * C;
   const float inv = 1.f / (float)H;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
@@ -28,6 +29,7 @@ __global__ void proj_tail_fwd_kernel(int64_t EW, int H, int C, const T* __restri
 template <typename T>
 __global__ void proj_tail_bwd_kernel(int64_t EW, int H, int C, const T* __restrict__ dout, int ostride, int coff,
                                      T* __restrict__ dA) {
+  pdl_prologue();
   const int64_t n = EW * H * C;
   const float inv = 1.f / (float)H;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
@@ -56,6 +58,7 @@ __device__ __forceinline__ void lin_src(int o, int n_in, int n_out, int& i0, int
 template <typename T>
 __global__ void resize2d_fwd_kernel(int mode, int B, int Si, int Wi, int So, int Wo, int C, const T* __restrict__ x,
                                     T* __restrict__ out, int ostride, int coff, int32_t* __restrict__ idx) {
+  pdl_prologue();
   const int64_t n = (int64_t)B * So * Wo * C;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
     const int c = (int)(i % C);
@@ -99,6 +102,7 @@ __global__ void resize2d_fwd_kernel(int mode, int B, int Si, int Wi, int So, int
 template <typename T>
 __global__ void resize2d_bwd_kernel(int mode, int B, int Si, int Wi, int So, int Wo, int C, const T* __restrict__ dout,
                                     int ostride, int coff, const int32_t* __restrict__ idx, T* __restrict__ dx) {
+  pdl_prologue();
   const int64_t n = (int64_t)B * Si * Wi * C;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
     uint32_t r32 = (uint32_t)i;                       // n < 2^31 is checked by the caller
@@ -159,6 +163,7 @@ __global__ void resize2d_bwd_kernel(int mode, int B, int Si, int Wi, int So, int
 template <typename T>
 __global__ void resize2d_bwd_max_tiled_kernel(int B, int Si, int Wi, int So, int Wo, int C, const T* __restrict__ dout, int ostride,
                                               int coff, const int32_t* __restrict__ idx, T* __restrict__ dx) {
+  pdl_prologue();
   constexpr int VEC = Elem<T>::VEC;
   const int cvecs = C / VEC;
   const uint32_t n = (uint32_t)B * Si * Wi * cvecs;
@@ -189,6 +194,7 @@ __global__ void resize2d_bwd_max_tiled_kernel(int B, int Si, int Wi, int So, int
 template <typename T>
 __global__ void upsample_fwd_kernel(int B, int Si, int Wi, int fS, int fW, int C, const T* __restrict__ x,
                                     T* __restrict__ out, int ostride, int coff) {
+  pdl_prologue();
   const int So = Si * fS, Wo = Wi * fW;
   const int64_t n = (int64_t)B * So * Wo * C;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
@@ -205,6 +211,7 @@ __global__ void upsample_fwd_kernel(int B, int Si, int Wi, int fS, int fW, int C
 template <typename T>
 __global__ void upsample_bwd_kernel(int B, int Si, int Wi, int fS, int fW, int C, const T* __restrict__ dout,
                                     int ostride, int coff, T* __restrict__ dx) {
+  pdl_prologue();
   const int So = Si * fS, Wo = Wi * fW;
   const int64_t n = (int64_t)B * Si * Wi * C;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
@@ -224,6 +231,7 @@ __global__ void upsample_bwd_kernel(int B, int Si, int Wi, int fS, int fW, int C
 template <typename T>
 __global__ void slice_copy_kernel(int64_t P, int C, const T* __restrict__ src, int sstride, int soff, T* __restrict__ dst,
                                   int dstride, int doff) {
+  pdl_prologue();
   const int64_t n = P * C;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
     const int c = (int)(i % C);
@@ -236,6 +244,7 @@ __global__ void slice_copy_kernel(int64_t P, int C, const T* __restrict__ src, i
 template <typename T>
 __global__ void head_fwd_kernel(int B, int64_t EW, int C, int n, const T* __restrict__ x, const float* __restrict__ w,
                                 const float* __restrict__ bias, float* __restrict__ logits) {
+  pdl_prologue();
   const int64_t tot = (int64_t)B * EW;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < tot; i += (int64_t)gridDim.x * TH) {
     const int64_t b = i / EW, ew = i % EW;
@@ -252,6 +261,7 @@ __global__ void head_fwd_kernel(int B, int64_t EW, int C, int n, const T* __rest
 template <typename T>
 __global__ void head_bwd_dx_kernel(int B, int64_t EW, int C, int n, const float* __restrict__ w,
                                    const float* __restrict__ dl, T* __restrict__ dx) {
+  pdl_prologue();
   const int64_t tot = (int64_t)B * EW * C;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < tot; i += (int64_t)gridDim.x * TH) {
     const int c = (int)(i % C);
@@ -266,6 +276,7 @@ __global__ void head_bwd_dx_kernel(int B, int64_t EW, int C, int n, const float*
 template <typename T>
 __global__ void head_bwd_dw_kernel(int B, int64_t EW, int C, int n, const T* __restrict__ x, const float* __restrict__ dl,
                                    float* __restrict__ dw, float* __restrict__ dbias) {
+  pdl_prologue();
   // grid = n * (C + 1) blocks: block (k, c) reduces over all positions; c == C is the bias column
   __shared__ double red[TH];
   const int k = blockIdx.x / (C + 1), c = blockIdx.x % (C + 1);
@@ -291,6 +302,7 @@ __global__ void head_bwd_dw_kernel(int B, int64_t EW, int C, int n, const T* __r
 // (R, H, W) fp32 -> (R, W, H) T, 32x32 smem tile transpose
 template <typename T>
 __global__ void pack_volume_kernel(int64_t R, int H, int W, const float* __restrict__ src, T* __restrict__ dst) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int tw = (W + 31) / 32, thh = (H + 31) / 32;
   const int64_t ntile = R * tw * thh;
@@ -313,11 +325,13 @@ __global__ void pack_volume_kernel(int64_t R, int H, int W, const float* __restr
 
 template <typename T>
 __global__ void cast_kernel(int64_t n, const float* __restrict__ src, T* __restrict__ dst) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) Elem<T>::st1(dst + i, src[i]);
 }
 
 __global__ void sgd_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, float lr,
                            float momentum, float wd, float gscale, int first) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
     const float pv = p[i];
     const float d = fmaf(wd, pv, g[i] * gscale);
@@ -333,23 +347,23 @@ inline int grid_of(ffpn_ctx* ctx, int64_t n) { return ffpn_grid_for(n, TH, ctx->
 
 #define DISPATCH(dtype, KERNEL, grid, ...)                                                     \
   do {                                                                                         \
-    if ((dtype) == FFPN_F32) KERNEL<float><<<grid, TH, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
-    else KERNEL<bf16><<<grid, TH, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                    \
+    if ((dtype) == FFPN_F32) ffpn_launch(KERNEL<float>, grid, TH, 0, (cudaStream_t)stream, __VA_ARGS__); \
+    else ffpn_launch(KERNEL<bf16>, grid, TH, 0, (cudaStream_t)stream, __VA_ARGS__);                    \
   } while (0)
 
 extern "C" int ffpn_proj_tail_fwd(ffpn_ctx* ctx, int dtype, int64_t EW, int64_t H, int C, const void* y, const float* a,
                                   const float* b, void* out, int ostride, int coff, void* stream) {
   if (H <= 0) FFPN_FAIL(ctx, "proj_tail_fwd: empty depth");
-  if (dtype == FFPN_F32) proj_tail_fwd_kernel<float><<<grid_of(ctx, EW * C), TH, 0, (cudaStream_t)stream>>>(EW, (int)H, C, (const float*)y, a, b, (float*)out, ostride, coff);
-  else proj_tail_fwd_kernel<bf16><<<grid_of(ctx, EW * C), TH, 0, (cudaStream_t)stream>>>(EW, (int)H, C, (const bf16*)y, a, b, (bf16*)out, ostride, coff);
+  if (dtype == FFPN_F32) ffpn_launch(proj_tail_fwd_kernel<float>, grid_of(ctx, EW * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const float*)y, a, b, (float*)out, ostride, coff);
+  else ffpn_launch(proj_tail_fwd_kernel<bf16>, grid_of(ctx, EW * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const bf16*)y, a, b, (bf16*)out, ostride, coff);
   FFPN_CHECK_LAUNCH(ctx, "proj_tail_fwd");
   return 0;
 }
 
 extern "C" int ffpn_proj_tail_bwd(ffpn_ctx* ctx, int dtype, int64_t EW, int64_t H, int C, const void* dout, int ostride,
                                   int coff, void* dA, void* stream) {
-  if (dtype == FFPN_F32) proj_tail_bwd_kernel<float><<<grid_of(ctx, EW * H * C), TH, 0, (cudaStream_t)stream>>>(EW, (int)H, C, (const float*)dout, ostride, coff, (float*)dA);
-  else proj_tail_bwd_kernel<bf16><<<grid_of(ctx, EW * H * C), TH, 0, (cudaStream_t)stream>>>(EW, (int)H, C, (const bf16*)dout, ostride, coff, (bf16*)dA);
+  if (dtype == FFPN_F32) ffpn_launch(proj_tail_bwd_kernel<float>, grid_of(ctx, EW * H * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const float*)dout, ostride, coff, (float*)dA);
+  else ffpn_launch(proj_tail_bwd_kernel<bf16>, grid_of(ctx, EW * H * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const bf16*)dout, ostride, coff, (bf16*)dA);
   FFPN_CHECK_LAUNCH(ctx, "proj_tail_bwd");
   return 0;
 }
@@ -360,8 +374,8 @@ extern "C" int ffpn_resize2d_fwd(ffpn_ctx* ctx, int dtype, int mode, int64_t B, 
   if (mode < 0 || mode > 2) FFPN_FAIL(ctx, "resize2d: unknown mode %d", mode);
   if (mode == 0 && (Si != So || Wi != Wo)) FFPN_FAIL(ctx, "resize2d: copy mode needs equal sizes (%lld,%lld)!=(%lld,%lld)", (long long)Si, (long long)Wi, (long long)So, (long long)Wo);
   const int g = grid_of(ctx, B * So * Wo * C);
-  if (dtype == FFPN_F32) resize2d_fwd_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>(mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)x, (float*)out, ostride, coff, idx);
-  else resize2d_fwd_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>(mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)x, (bf16*)out, ostride, coff, idx);
+  if (dtype == FFPN_F32) ffpn_launch(resize2d_fwd_kernel<float>, g, TH, 0, (cudaStream_t)stream, mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)x, (float*)out, ostride, coff, idx);
+  else ffpn_launch(resize2d_fwd_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)x, (bf16*)out, ostride, coff, idx);
   FFPN_CHECK_LAUNCH(ctx, "resize2d_fwd");
   return 0;
 }
@@ -376,15 +390,15 @@ extern "C" int ffpn_resize2d_bwd(ffpn_ctx* ctx, int dtype, int mode, int64_t B, 
     const int vec = dtype == FFPN_F32 ? 4 : 8;
     if (mode == 1 && Si % So == 0 && Wi % Wo == 0 && C % vec == 0 && ostride % vec == 0 && coff % vec == 0) {
       const int gv = grid_of(ctx, B * Si * Wi * (C / vec));
-      if (dtype == FFPN_F32) resize2d_bwd_max_tiled_kernel<float><<<gv, TH, 0, (cudaStream_t)stream>>>((int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)dout, ostride, coff, idx, (float*)dx);
-      else resize2d_bwd_max_tiled_kernel<bf16><<<gv, TH, 0, (cudaStream_t)stream>>>((int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)dout, ostride, coff, idx, (bf16*)dx);
+      if (dtype == FFPN_F32) ffpn_launch(resize2d_bwd_max_tiled_kernel<float>, gv, TH, 0, (cudaStream_t)stream, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)dout, ostride, coff, idx, (float*)dx);
+      else ffpn_launch(resize2d_bwd_max_tiled_kernel<bf16>, gv, TH, 0, (cudaStream_t)stream, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)dout, ostride, coff, idx, (bf16*)dx);
       FFPN_CHECK_LAUNCH(ctx, "resize2d_bwd");
       return 0;
     }
   }
   const int g = grid_of(ctx, B * Si * Wi * C);
-  if (dtype == FFPN_F32) resize2d_bwd_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>(mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)dout, ostride, coff, idx, (float*)dx);
-  else resize2d_bwd_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>(mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)dout, ostride, coff, idx, (bf16*)dx);
+  if (dtype == FFPN_F32) ffpn_launch(resize2d_bwd_kernel<float>, g, TH, 0, (cudaStream_t)stream, mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const float*)dout, ostride, coff, idx, (float*)dx);
+  else ffpn_launch(resize2d_bwd_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, mode, (int)B, (int)Si, (int)Wi, (int)So, (int)Wo, C, (const bf16*)dout, ostride, coff, idx, (bf16*)dx);
   FFPN_CHECK_LAUNCH(ctx, "resize2d_bwd");
   return 0;
 }
@@ -393,8 +407,8 @@ extern "C" int ffpn_upsample_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t Si
                                  const void* x, void* out, int ostride, int coff, void* stream) {
   if (fS < 1 || fW < 1) FFPN_FAIL(ctx, "upsample: integer factors >= 1 required");
   const int g = grid_of(ctx, B * Si * fS * Wi * fW * C);
-  if (dtype == FFPN_F32) upsample_fwd_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>((int)B, (int)Si, (int)Wi, fS, fW, C, (const float*)x, (float*)out, ostride, coff);
-  else upsample_fwd_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>((int)B, (int)Si, (int)Wi, fS, fW, C, (const bf16*)x, (bf16*)out, ostride, coff);
+  if (dtype == FFPN_F32) ffpn_launch(upsample_fwd_kernel<float>, g, TH, 0, (cudaStream_t)stream, (int)B, (int)Si, (int)Wi, fS, fW, C, (const float*)x, (float*)out, ostride, coff);
+  else ffpn_launch(upsample_fwd_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, (int)B, (int)Si, (int)Wi, fS, fW, C, (const bf16*)x, (bf16*)out, ostride, coff);
   FFPN_CHECK_LAUNCH(ctx, "upsample_fwd");
   return 0;
 }
@@ -403,8 +417,8 @@ extern "C" int ffpn_upsample_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t Si
                                  const void* dout, int ostride, int coff, void* dx, void* stream) {
   if (fS < 1 || fW < 1) FFPN_FAIL(ctx, "upsample: integer factors >= 1 required");
   const int g = grid_of(ctx, B * Si * Wi * C);
-  if (dtype == FFPN_F32) upsample_bwd_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>((int)B, (int)Si, (int)Wi, fS, fW, C, (const float*)dout, ostride, coff, (float*)dx);
-  else upsample_bwd_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>((int)B, (int)Si, (int)Wi, fS, fW, C, (const bf16*)dout, ostride, coff, (bf16*)dx);
+  if (dtype == FFPN_F32) ffpn_launch(upsample_bwd_kernel<float>, g, TH, 0, (cudaStream_t)stream, (int)B, (int)Si, (int)Wi, fS, fW, C, (const float*)dout, ostride, coff, (float*)dx);
+  else ffpn_launch(upsample_bwd_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, (int)B, (int)Si, (int)Wi, fS, fW, C, (const bf16*)dout, ostride, coff, (bf16*)dx);
   FFPN_CHECK_LAUNCH(ctx, "upsample_bwd");
   return 0;
 }
@@ -412,8 +426,8 @@ extern "C" int ffpn_upsample_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t Si
 extern "C" int ffpn_slice_copy(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* src, int sstride, int soff,
                                void* dst, int dstride, int doff, void* stream) {
   const int g = grid_of(ctx, P * C);
-  if (dtype == FFPN_F32) slice_copy_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>(P, C, (const float*)src, sstride, soff, (float*)dst, dstride, doff);
-  else slice_copy_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>(P, C, (const bf16*)src, sstride, soff, (bf16*)dst, dstride, doff);
+  if (dtype == FFPN_F32) ffpn_launch(slice_copy_kernel<float>, g, TH, 0, (cudaStream_t)stream, P, C, (const float*)src, sstride, soff, (float*)dst, dstride, doff);
+  else ffpn_launch(slice_copy_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, P, C, (const bf16*)src, sstride, soff, (bf16*)dst, dstride, doff);
   FFPN_CHECK_LAUNCH(ctx, "slice_copy");
   return 0;
 }
@@ -421,8 +435,8 @@ extern "C" int ffpn_slice_copy(ffpn_ctx* ctx, int dtype, int64_t P, int C, const
 extern "C" int ffpn_head_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, const void* x, const float* w,
                              const float* bias, float* logits, void* stream) {
   const int g = grid_of(ctx, B * EW);
-  if (dtype == FFPN_F32) head_fwd_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>((int)B, EW, C, n, (const float*)x, w, bias, logits);
-  else head_fwd_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>((int)B, EW, C, n, (const bf16*)x, w, bias, logits);
+  if (dtype == FFPN_F32) ffpn_launch(head_fwd_kernel<float>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const float*)x, w, bias, logits);
+  else ffpn_launch(head_fwd_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const bf16*)x, w, bias, logits);
   FFPN_CHECK_LAUNCH(ctx, "head_fwd");
   return 0;
 }
@@ -431,12 +445,12 @@ extern "C" int ffpn_head_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, in
                              const float* dlogits, void* dx, float* dw, float* dbias, void* stream) {
   const int g = grid_of(ctx, B * EW * C);
   if (dx != nullptr) {
-    if (dtype == FFPN_F32) head_bwd_dx_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>((int)B, EW, C, n, w, dlogits, (float*)dx);
-    else head_bwd_dx_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>((int)B, EW, C, n, w, dlogits, (bf16*)dx);
+    if (dtype == FFPN_F32) ffpn_launch(head_bwd_dx_kernel<float>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, w, dlogits, (float*)dx);
+    else ffpn_launch(head_bwd_dx_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, w, dlogits, (bf16*)dx);
     FFPN_CHECK_LAUNCH(ctx, "head_bwd_dx");
   }
-  if (dtype == FFPN_F32) head_bwd_dw_kernel<float><<<n * (C + 1), TH, 0, (cudaStream_t)stream>>>((int)B, EW, C, n, (const float*)x, dlogits, dw, dbias);
-  else head_bwd_dw_kernel<bf16><<<n * (C + 1), TH, 0, (cudaStream_t)stream>>>((int)B, EW, C, n, (const bf16*)x, dlogits, dw, dbias);
+  if (dtype == FFPN_F32) ffpn_launch(head_bwd_dw_kernel<float>, n * (C + 1), TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const float*)x, dlogits, dw, dbias);
+  else ffpn_launch(head_bwd_dw_kernel<bf16>, n * (C + 1), TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const bf16*)x, dlogits, dw, dbias);
   FFPN_CHECK_LAUNCH(ctx, "head_bwd_dw");
   return 0;
 }
@@ -445,22 +459,22 @@ extern "C" int ffpn_pack_volume(ffpn_ctx* ctx, int dtype, int64_t R, int64_t H, 
                                 void* stream) {
   const int64_t ntile = R * ((W + 31) / 32) * ((H + 31) / 32);
   const int g = (int)(ntile < (int64_t)ctx->num_sms * 16 ? ntile : (int64_t)ctx->num_sms * 16);
-  if (dtype == FFPN_F32) pack_volume_kernel<float><<<g, TH, 0, (cudaStream_t)stream>>>(R, (int)H, (int)W, src, (float*)dst);
-  else pack_volume_kernel<bf16><<<g, TH, 0, (cudaStream_t)stream>>>(R, (int)H, (int)W, src, (bf16*)dst);
+  if (dtype == FFPN_F32) ffpn_launch(pack_volume_kernel<float>, g, TH, 0, (cudaStream_t)stream, R, (int)H, (int)W, src, (float*)dst);
+  else ffpn_launch(pack_volume_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, R, (int)H, (int)W, src, (bf16*)dst);
   FFPN_CHECK_LAUNCH(ctx, "pack_volume");
   return 0;
 }
 
 extern "C" int ffpn_cast(ffpn_ctx* ctx, int dtype, int64_t n, const float* src, void* dst, void* stream) {
-  if (dtype == FFPN_F32) cast_kernel<float><<<grid_of(ctx, n), TH, 0, (cudaStream_t)stream>>>(n, src, (float*)dst);
-  else cast_kernel<bf16><<<grid_of(ctx, n), TH, 0, (cudaStream_t)stream>>>(n, src, (bf16*)dst);
+  if (dtype == FFPN_F32) ffpn_launch(cast_kernel<float>, grid_of(ctx, n), TH, 0, (cudaStream_t)stream, n, src, (float*)dst);
+  else ffpn_launch(cast_kernel<bf16>, grid_of(ctx, n), TH, 0, (cudaStream_t)stream, n, src, (bf16*)dst);
   FFPN_CHECK_LAUNCH(ctx, "cast");
   return 0;
 }
 
 extern "C" int ffpn_sgd_step(ffpn_ctx* ctx, int64_t n, float* p, const float* g, float* mom, float lr, float momentum,
                              float weight_decay, float grad_scale, int first_step, void* stream) {
-  sgd_kernel<<<grid_of(ctx, n), TH, 0, (cudaStream_t)stream>>>(n, p, g, mom, lr, momentum, weight_decay, grad_scale, first_step);
+  ffpn_launch(sgd_kernel, grid_of(ctx, n), TH, 0, (cudaStream_t)stream, n, p, g, mom, lr, momentum, weight_decay, grad_scale, first_step);
   FFPN_CHECK_LAUNCH(ctx, "sgd_step");
   return 0;
 }

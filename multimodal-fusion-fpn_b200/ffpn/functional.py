@@ -4,6 +4,7 @@ Tensors crossing these Functions are LOGICAL reference-shaped tensors -- (B, C, 
 and (B, C, S', W') for 2-D ones -- stored channels-last (torch.channels_last_3d / channels_last), so a
 caller sees the same shapes the reference produces while the kernels see (B, S, W, H, C).
 """
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -40,6 +41,58 @@ def set_grad_sink(mapping) -> None:
 
 def _sink(t):
     return _GRAD_SINK.get(t.data_ptr()) if _GRAD_SINK else None
+
+
+# ---- branch streams --------------------------------------------------------------------------------------
+# The model is a DAG, not a chain: the 2-D encoder is independent of the 3-D one, the projective block of level l is
+# independent of encoder levels > l, and most of the step's ~800 launches are small (deep levels, en-face maps: a few
+# CTAs each).  Branches are therefore forked onto side streams (event fork / join); autograd replays each node's
+# backward on the stream its forward ran on, so the backward gets the mirrored DAG, and a captured CUDA graph keeps the
+# parallel edges.  FFPN_STREAMS=0 runs everything on the caller's stream.
+_SIDE_STREAMS = {}
+_USED_SIDE = set()
+
+
+def streams_enabled(kind: str = 'branches') -> bool:
+    """FFPN_STREAMS: '1' (default) everything, '0' nothing, 'branches' / 'wgrad' one of the two mechanisms."""
+    v = os.environ.get('FFPN_STREAMS', '1')
+    return v == '1' or v == kind
+
+
+def side_stream(device, i: int) -> 'torch.cuda.Stream':
+    key = (torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device(), i)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key[0])
+    return st
+
+
+def fork(side: 'torch.cuda.Stream', *tensors) -> 'torch.cuda.Stream':
+    """``side`` continues after everything enqueued so far on the current stream; ``tensors`` (allocated on the current
+    stream) will be read there."""
+    side.wait_stream(torch.cuda.current_stream())
+    _USED_SIDE.add(side)
+    for t in tensors:
+        t.record_stream(side)
+    return side
+
+
+def join(side: 'torch.cuda.Stream', *tensors) -> None:
+    """The current stream continues after ``side``; ``tensors`` (allocated on ``side``) will be read here."""
+    cur = torch.cuda.current_stream()
+    cur.wait_stream(side)
+    for t in tensors:
+        t.record_stream(cur)
+
+
+def join_side_streams() -> None:
+    """Join every side stream used since the last call into the current stream (end of backward: the gradient sink is
+    written from all of them; a CUDA-graph capture must not end with unjoined work)."""
+    cur = torch.cuda.current_stream()
+    for st in list(_USED_SIDE):
+        if st.device == cur.device:
+            cur.wait_stream(st)
+            _USED_SIDE.discard(st)
 
 
 # ---- layout helpers ------------------------------------------------------------------------------------
@@ -89,6 +142,20 @@ class ConvXSpec:
     eps: float
     need_dx: bool
     ndim: int
+
+
+def _wgrad(inp, dy, w_shape, kernel, stride, pad, a_in, b_in, relu, out):
+    """Weight gradient of one conv.  With the gradient sink installed nothing downstream in this backward reads the
+    result, so the launch (+ its partial-tile reduce) goes to a side stream paired with the current one and leaves the
+    dgrad -> BatchNorm-backward chain, which is the critical path; the trainer joins the side streams before the
+    optimiser reads the flat gradient."""
+    if out is None or not streams_enabled('wgrad'):
+        return ops.conv_wgrad(inp, dy, w_shape, kernel, stride, pad, a_in, b_in, relu, out=out)
+    cur = torch.cuda.current_stream()
+    wg = fork(side_stream(inp.device, ('wgrad', cur.cuda_stream)), inp, dy, *([a_in, b_in] if a_in is not None else []))
+    with torch.cuda.stream(wg):
+        ops.conv_wgrad(inp, dy, w_shape, kernel, stride, pad, a_in, b_in, relu, out=out)
+    return None
 
 
 class ConvXFunction(torch.autograd.Function):
@@ -182,7 +249,7 @@ class ConvXFunction(torch.autograd.Function):
                 dgd, dbd, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 2, yd.numel() // yd.shape[-1], gd,
                                                            affd[2], affd[3], _sink(gd), _sink(tensors[5 * k + 2]))
                 dyd = ops.bn_bwd_apply(G, yd, affd[0], affd[1], False, cA, cP, cQ)
-                grads[5 * k] = ops.conv_wgrad(xp, dyd, wd.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0), out=_sink(wd))
+                grads[5 * k] = _wgrad(xp, dyd, wd.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0), None, None, False, _sink(wd))
                 grads[5 * k + 1], grads[5 * k + 2] = dgd, dbd
                 if spec.need_dx:
                     dx_short = ops.conv_dgrad(dyd, wd, xp.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0))
@@ -196,8 +263,8 @@ class ConvXFunction(torch.autograd.Function):
                 inp, a_in, b_in = ys[i - 1], affs[i - 1][0], affs[i - 1][1]
             else:
                 inp, a_in, b_in = xp, None, None
-            grads[5 * i] = ops.conv_wgrad(inp, dy, w.shape, spec.kernels[i], spec.strides[i], spec.pads[i], a_in, b_in,
-                                          i > 0, out=_sink(w))
+            grads[5 * i] = _wgrad(inp, dy, w.shape, spec.kernels[i], spec.strides[i], spec.pads[i], a_in, b_in, i > 0,
+                                  _sink(w))
             if i > 0:
                 dA = ops.conv_dgrad(dy, w, inp.shape, spec.kernels[i], spec.strides[i], spec.pads[i])
                 cnt = inp.numel() // inp.shape[-1]

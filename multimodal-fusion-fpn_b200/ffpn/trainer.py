@@ -84,6 +84,7 @@ class FusionTrainer:
             out = self.model(batch)
             loss, _ = self.criterion(batch, out)
             (loss / self.accumulate if self.accumulate > 1 else loss).backward()
+            functional.join_side_streams()     # the sink is written from every branch stream
         finally:
             functional.set_grad_sink(None)
             if self._arena_state == 1:

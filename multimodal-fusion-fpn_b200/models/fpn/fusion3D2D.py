@@ -214,8 +214,44 @@ class ModifiedUnet3D2D(SegmentationNetwork):
             deeper = getattr(self, f'up_concat{l}')(proj[l - 1], r2d[l - 1], deeper)
         return self.final1(deeper)
 
+    def _forward_branches(self, oct, slo, levels2d):
+        """The forward DAG on side streams: the 2-D encoder (+ resizes) on one, the projective block of each level 1-4
+        on its own, the 3-D encoder -> level-5 projection -> decoder chain on the caller's stream.  Each up block waits
+        only for the two skips it reads, so the large level-1 projection overlaps the deep (latency-bound) levels."""
+        dev = oct.device
+        s2d = FF.fork(FF.side_stream(dev, 0), slo)
+        with torch.cuda.stream(s2d):
+            f2d = self._encode_2d(slo, levels2d)
+        proj, x = [None] * 5, FF.pack_oct(oct)
+        shapes = []
+        for l in range(1, 6):
+            f, x = self._level(getattr(self, f'conv{l}'), x, getattr(self, f'pool{l}') if l < 5 else None,
+                               need_dx=l > 1)
+            if l < 5:
+                sp = FF.fork(FF.side_stream(dev, l), f)
+                with torch.cuda.stream(sp):
+                    proj[l - 1] = self._project(f, l)
+            else:
+                proj[4] = self._project(f, 5)
+            shapes.append(tuple(proj[l - 1].shape[2:4]))
+        with torch.cuda.stream(s2d):
+            r2d = [FF.Resize2DFunction.apply(f2d[l], shapes[l], self.interpolate) for l in range(levels2d)]
+        deeper = proj[4]
+        if levels2d == 5:
+            FF.join(s2d, r2d[4])
+            deeper = FF.CatFunction.apply(proj[4], r2d[4])
+        for l in (4, 3, 2, 1):
+            FF.join(FF.side_stream(dev, l), proj[l - 1])
+            if l == 4 and levels2d < 5:
+                FF.join(s2d)
+            r2d[l - 1].record_stream(torch.cuda.current_stream())
+            deeper = getattr(self, f'up_concat{l}')(proj[l - 1], r2d[l - 1], deeper)
+        return self.final1(deeper)
+
     def forward(self, oct, slo):
         self._bump_bn_counters()
+        if oct.is_cuda and FF.streams_enabled():
+            return self._forward_branches(oct, slo, 4)
         f2d = self._encode_2d(slo, 4)
         f3d = self._encode_3d(oct)
         proj = [self._project(f3d[l - 1], l) for l in range(1, 6)]
@@ -238,6 +274,8 @@ class ModifiedUnet3D2DLevel5(ModifiedUnet3D2D):
 
     def forward(self, oct, slo):
         self._bump_bn_counters()
+        if oct.is_cuda and FF.streams_enabled():
+            return self._forward_branches(oct, slo, 5)
         f2d = self._encode_2d(slo, 5)
         f3d = self._encode_3d(oct)
         proj = [self._project(f3d[l - 1], l) for l in range(1, 6)]
