@@ -11,7 +11,8 @@ int ffpn_conv_wgrad_simt(ffpn_ctx*, const ffpn_conv_desc*, const void*, const fl
 // conv_stem.cu
 bool ffpn_stem_supported(const ffpn_conv_desc* d);
 int ffpn_stem_fwd(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, void*, float*, int*, cudaStream_t);
-int ffpn_stem_wgrad(ffpn_ctx*, const ffpn_conv_desc*, const void*, const void*, float*, cudaStream_t);
+int ffpn_stem_wgrad(ffpn_ctx*, const ffpn_conv_desc*, const void*, const void*, float*, void*, size_t, cudaStream_t);
+size_t ffpn_stem_wgrad_workspace_bytes(const ffpn_conv_desc*);
 // conv_tc.cu
 bool ffpn_tc_fwd_supported(const ffpn_conv_desc* d);
 bool ffpn_tc_dgrad_supported(const ffpn_conv_desc* d);
@@ -74,7 +75,12 @@ extern "C" void ffpn_destroy(ffpn_ctx* ctx) {
 extern "C" const char* ffpn_last_error(ffpn_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 extern "C" int64_t ffpn_launch_count(ffpn_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
-extern "C" size_t ffpn_conv_workspace_bytes(const ffpn_conv_desc* d) { return d ? ffpn_tc_workspace_bytes(d) : 0; }
+extern "C" size_t ffpn_conv_workspace_bytes(const ffpn_conv_desc* d) {
+  if (!d) return 0;
+  size_t n = ffpn_tc_workspace_bytes(d);
+  if (ffpn_stem_supported(d)) { const size_t s = ffpn_stem_wgrad_workspace_bytes(d); if (s > n) n = s; }
+  return n;
+}
 
 extern "C" int ffpn_conv_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale,
                              const float* in_shift, int in_relu, const float* w, void* y, float* stat_partial,
@@ -126,7 +132,7 @@ extern "C" int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const voi
   if (check_desc(ctx, d, "conv_wgrad")) return 1;
   if ((in_scale == nullptr) != (in_shift == nullptr)) FFPN_FAIL(ctx, "conv_wgrad: in_scale/in_shift must both be set or both null");
   if (d->impl == 0 && in_scale == nullptr && ffpn_stem_supported(d))
-    return ffpn_stem_wgrad(ctx, d, x, dy, dw, (cudaStream_t)stream);
+    return ffpn_stem_wgrad(ctx, d, x, dy, dw, ws, ws_bytes, (cudaStream_t)stream);
   const bool tc_ok = ffpn_tc_wgrad_supported(d);
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_wgrad: tcgen05 kernel does not support this geometry");
   if (tc_ok && d->impl != 1)

@@ -93,7 +93,7 @@ stem_fwd_kernel(StemGeom g, const T* __restrict__ x, const float* __restrict__ w
 
 template <typename T, int NT>
 __global__ void __launch_bounds__(ST_THREADS)
-stem_wgrad_kernel(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
+stem_wgrad_kernel(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ part) {
   pdl_prologue();
   __shared__ float red[(ST_THREADS / 32) * NT * ST_C];
   float acc[NT][ST_C];
@@ -160,7 +160,8 @@ stem_wgrad_kernel(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy,
     float v = 0.f;
     for (int k = 0; k < ST_THREADS / 32; k++) v += red[k * NT * ST_C + i];
     const int t = i / ST_C, co = i % ST_C;
-    atomicAdd(dw + co * NT + t, v);            // master layout [Cout][Cin=1][taps]
+    if (part) part[(size_t)blockIdx.x * (NT * ST_C) + co * NT + t] = v;   // per-block slice, summed in block order afterwards
+    else atomicAdd(dw + co * NT + t, v);     // master layout [Cout][Cin=1][taps]
   }
 }
 
@@ -251,7 +252,7 @@ stem_fwd_kernel_t(StemGeom g, const T* __restrict__ x, const float* __restrict__
 // compare it against all NT accumulator rows).
 template <typename T, int KS, int KW, int KH>
 __global__ void __launch_bounds__(ST_THREADS)
-stem_wgrad_kernel_t(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
+stem_wgrad_kernel_t(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ part) {
   pdl_prologue();
   constexpr int NT = KS * KW * KH;
   __shared__ float red[(ST_THREADS / 32) * NT * ST_C];
@@ -311,7 +312,8 @@ stem_wgrad_kernel_t(StemGeom g, const T* __restrict__ x, const T* __restrict__ d
     float v = 0.f;
     for (int k = 0; k < ST_THREADS / 32; k++) v += red[k * NT * ST_C + i];
     const int t = i / ST_C, co = i % ST_C;
-    atomicAdd(dw + co * NT + t, v);            // master layout [Cout][Cin=1][taps]
+    if (part) part[(size_t)blockIdx.x * (NT * ST_C) + co * NT + t] = v;   // per-block slice, summed in block order afterwards
+    else atomicAdd(dw + co * NT + t, v);     // master layout [Cout][Cin=1][taps]
   }
 }
 
@@ -415,7 +417,7 @@ stem_fwd_kernel_v4(StemGeom g, const T* __restrict__ x, const float* __restrict_
 // the occupancy of the one-thread kernel, whose 188 registers leave two blocks per SM.
 template <typename T, int KS, int KW, int KH>
 __global__ void __launch_bounds__(ST_THREADS)
-stem_wgrad_kernel_v2(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
+stem_wgrad_kernel_v2(StemGeom g, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ part) {
   pdl_prologue();
   constexpr int NT = KS * KW * KH;
   constexpr int HC = ST_C / 2;
@@ -487,7 +489,8 @@ stem_wgrad_kernel_v2(StemGeom g, const T* __restrict__ x, const T* __restrict__ 
     float v = 0.f;
     for (int k = 0; k < ST_THREADS / 32; k++) v += red[k * NT * ST_C + i];
     const int t = i / ST_C, co = i % ST_C;
-    atomicAdd(dw + co * NT + t, v);            // master layout [Cout][Cin=1][taps]
+    if (part) part[(size_t)blockIdx.x * (NT * ST_C) + co * NT + t] = v;   // per-block slice, summed in block order afterwards
+    else atomicAdd(dw + co * NT + t, v);     // master layout [Cout][Cin=1][taps]
   }
 }
 
@@ -534,26 +537,62 @@ int ffpn_stem_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const f
   return 0;
 }
 
-int ffpn_stem_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+namespace {
+// dw[i] += sum over the per-block slices in block order (bitwise reproducible)
+__global__ void stem_slice_reduce_kernel(const float* __restrict__ part, int nslices, int n, float* __restrict__ dw) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 3 < nslices; k += 4) {
+    a0 += part[(size_t)k * n + i];
+    a1 += part[(size_t)(k + 1) * n + i];
+    a2 += part[(size_t)(k + 2) * n + i];
+    a3 += part[(size_t)(k + 3) * n + i];
+  }
+  for (; k < nslices; k++) a0 += part[(size_t)k * n + i];
+  dw[i] += (a0 + a1) + (a2 + a3);
+}
+}  // namespace
+
+size_t ffpn_stem_wgrad_workspace_bytes(const ffpn_conv_desc* d) {
+  return (size_t)148 * 8 * d->kS * d->kW * d->kH * ST_C * 4;     // one dW slice per block (grid <= 8 per SM)
+}
+
+int ffpn_stem_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   StemGeom g;
   if (!stem_geom(d, g)) FFPN_FAIL(ctx, "stem_wgrad: unsupported geometry");
   const int nt = g.kS * g.kW * g.kH;
   const int64_t nlines = (int64_t)g.B * g.oS * g.oW;
   const int64_t cap = (int64_t)ctx->num_sms * 4;
   const int grid = (int)(nlines < cap ? nlines : cap);
+  // per-block slices in the workspace + ordered reduce when it fits, atomics on dw otherwise
+  float* part = (ws && (size_t)grid * 2 * nt * ST_C * 4 <= ws_bytes) ? (float*)ws : nullptr;
+  int nblocks = grid;
+#define STEM_FINISH()                                                                                                        \
+  if (part) {                                                                                                                \
+    ffpn_launch(stem_slice_reduce_kernel, (nt * ST_C + 127) / 128, 128, 0, st, (const float*)part, nblocks, nt * ST_C, dw);  \
+    FFPN_CHECK_LAUNCH(ctx, "stem_slice_reduce");                                                                             \
+  }
 #define STEM_WT(KS, KW, KH)                                                                                                  \
   if (g.kS == KS && g.kW == KW && g.kH == KH) {                                                                              \
-    if (d->dtype == FFPN_F32) ffpn_launch(stem_wgrad_kernel_v2<float, KS, KW, KH>, grid * 2, ST_THREADS, 0, st, g, (const float*)x, (const float*)dy, dw); \
-    else ffpn_launch(stem_wgrad_kernel_v2<bf16, KS, KW, KH>, grid * 2, ST_THREADS, 0, st, g, (const bf16*)x, (const bf16*)dy, dw);      \
+    if (d->dtype == FFPN_F32) ffpn_launch(stem_wgrad_kernel_v2<float, KS, KW, KH>, grid * 2, ST_THREADS, 0, st, g, (const float*)x, (const float*)dy, dw, part); \
+    else ffpn_launch(stem_wgrad_kernel_v2<bf16, KS, KW, KH>, grid * 2, ST_THREADS, 0, st, g, (const bf16*)x, (const bf16*)dy, dw, part);      \
     FFPN_CHECK_LAUNCH(ctx, "stem_wgrad");                                                                                    \
+    nblocks = grid * 2;                                                                                                      \
+    STEM_FINISH()                                                                                                            \
     return 0;                                                                                                                \
   }
   STEM_WT(1, 3, 3) STEM_WT(1, 1, 1) STEM_WT(1, 1, 3) STEM_WT(1, 3, 1)
 #undef STEM_WT
-#define STEM_WG(T, NT) ffpn_launch(stem_wgrad_kernel<T, NT>, grid, ST_THREADS, 0, st, g, (const T*)x, (const T*)dy, dw)
+#define STEM_WG(T, NT) ffpn_launch(stem_wgrad_kernel<T, NT>, grid, ST_THREADS, 0, st, g, (const T*)x, (const T*)dy, dw, part)
   if (d->dtype == FFPN_F32) { if (nt == 1) STEM_WG(float, 1); else if (nt == 3) STEM_WG(float, 3); else if (nt == 9) STEM_WG(float, 9); else FFPN_FAIL(ctx, "stem_wgrad: taps"); }
   else { if (nt == 1) STEM_WG(bf16, 1); else if (nt == 3) STEM_WG(bf16, 3); else if (nt == 9) STEM_WG(bf16, 9); else FFPN_FAIL(ctx, "stem_wgrad: taps"); }
 #undef STEM_WG
   FFPN_CHECK_LAUNCH(ctx, "stem_wgrad");
+  STEM_FINISH()
+#undef STEM_FINISH
   return 0;
 }
