@@ -295,7 +295,9 @@ def main():
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': w['name'], 'per_gpu_batch': w['B'], 'global_batch': w['B'] * world,
-                       'parallelism': f'dp{world}', 'cuda_graph': use_graph, 'optimizer': 'SGD(0.1, 0.9, wd 1e-4) fused',
+                       'parallelism': f'dp{world}', 'cuda_graph': use_graph,
+                       'branch_streams': os.environ.get('FFPN_STREAMS', '1'), 'pdl': os.environ.get('FFPN_PDL', '0'),
+                       'optimizer': 'SGD(0.1, 0.9, wd 1e-4) fused',
                        'l2': 'per-step working set >> 126 MB L2 (no flush needed)', 'final_loss': last},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,

@@ -539,20 +539,21 @@ int ffpn_stem_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const f
 
 namespace {
 // dw[i] += sum over the per-block slices in block order (bitwise reproducible)
-__global__ void stem_slice_reduce_kernel(const float* __restrict__ part, int nslices, int n, float* __restrict__ dw) {
+__global__ void __launch_bounds__(128) stem_slice_reduce_kernel(const float* __restrict__ part, int nslices, int n, float* __restrict__ dw) {
   pdl_prologue();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int k = 0;
-  for (; k + 3 < nslices; k += 4) {
-    a0 += part[(size_t)k * n + i];
-    a1 += part[(size_t)(k + 1) * n + i];
-    a2 += part[(size_t)(k + 2) * n + i];
-    a3 += part[(size_t)(k + 3) * n + i];
+  // one block per output: thread t adds slices t, t + 128, ... then a fixed-shape tree -> same bits every run
+  __shared__ float red[128];
+  const int i = blockIdx.x;
+  float a = 0.f;
+  for (int k = threadIdx.x; k < nslices; k += 128) a += part[(size_t)k * n + i];
+  red[threadIdx.x] = a;
+  __syncthreads();
+#pragma unroll
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
   }
-  for (; k < nslices; k++) a0 += part[(size_t)k * n + i];
-  dw[i] += (a0 + a1) + (a2 + a3);
+  if (threadIdx.x == 0) dw[i] += red[0];
 }
 }  // namespace
 
@@ -573,7 +574,7 @@ int ffpn_stem_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const
   int nblocks = grid;
 #define STEM_FINISH()                                                                                                        \
   if (part) {                                                                                                                \
-    ffpn_launch(stem_slice_reduce_kernel, (nt * ST_C + 127) / 128, 128, 0, st, (const float*)part, nblocks, nt * ST_C, dw);  \
+    ffpn_launch(stem_slice_reduce_kernel, nt * ST_C, 128, 0, st, (const float*)part, nblocks, nt * ST_C, dw);  \
     FFPN_CHECK_LAUNCH(ctx, "stem_slice_reduce");                                                                             \
   }
 #define STEM_WT(KS, KW, KH)                                                                                                  \

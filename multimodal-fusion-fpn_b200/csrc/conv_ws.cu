@@ -32,7 +32,7 @@ struct WsParams {
   int colstride, tmem_cols;
   int fshift;                         // flat (1x1x1) mode: log2 of the TMA box row unit (256 or 128 positions)
   int aff_mod;                        // BatchNorm vectors are indexed modulo this (pair view: two positions share them); 0 = off
-  int relu, has_aff, has_stats, has_add, dbg;   // dbg (FFPN_TC_DEBUG, timing experiments): 1 no MMA, 2 no epilogue body, 4 no TMA, 8 no transform body
+  int relu, has_aff, has_stats, has_add, dbg;   // dbg (FFPN_TC_DEBUG, timing experiments): 1 no MMA, 2 no epilogue body, 4 no TMA, 8 no transform body, 16 no output stores, 32 no statistics
   const float* sc;
   const float* sh;
   const bf16* wp;
@@ -249,17 +249,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     for (tc.init(p); tc.valid(p); tc.next(p), tl++) {
       const int buf = tl % p.nbuf;
       if (warp == 4 && lane == 0) WS_TRACE(7, tl);
-      mbar_wait(TFULL(buf), (uint32_t)(tl / p.nbuf) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp == 4 && lane == 0) WS_TRACE(8, tl);
-      const uint32_t t_tile = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
       const int my_nmb = (p.dbg & 2) ? 0 : (tc.nmb - half + 1) >> 1;               // accumulator blocks half, half + 2, ...
       const int nitems = my_nmb * nch;
-      for (int it0 = 0; it0 < nitems; it0 += BATCH) {
-        uint32_t raw[BATCH][16];
-        long long oposv[BATCH];
-        bool validv[BATCH];
-        uint4 addv[ADD ? BATCH : 1][2];
+      uint32_t raw[BATCH][16];
+      long long oposv[BATCH];
+      bool validv[BATCH];
+      uint4 addv[ADD ? BATCH : 1][2];
+      // output position of every item of a batch (+ the residual-branch gradient loads, all issued before anything waits)
+      auto prep = [&](int it0) {
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
           const int idx = it0 + u;
@@ -267,7 +264,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           if (ADD) addv[ADD ? u : 0][0] = addv[ADD ? u : 0][1] = make_uint4(0u, 0u, 0u, 0u);
           if (idx < nitems) {
             const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
-            tmem_ld16_nowait(t_tile + (uint32_t)((half + 2 * mbi) * p.colstride + ch * 16), raw[u]);
             const int m = (half + 2 * mbi) * 128 + quad * 32 + lane;
             const int j = p.Lr == 1 ? m : (int)__umulhi((uint32_t)m, magicLr), ii = m - j * p.Lr;
             const int i = tc.i0 + ii;
@@ -276,12 +272,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
             validv[u] = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX);
             oposv[u] = (long long)tc.nb * p.outNB + (long long)(tc.d0 + j) * p.outD + (long long)oy * p.outY + ox;
             if (ADD && validv[u]) {
-              // residual-branch gradient: all loads of the batch are issued before anything waits on them
               const int cbase = n0 + ch * 16;
               const uint4* ap = reinterpret_cast<const uint4*>(p.addend + oposv[u] * p.Cout + cbase);
-              if (cbase < p.Cout) addv[ADD ? u : 0][0] = ap[0];
-              if (cbase + 8 < p.Cout) addv[ADD ? u : 0][1] = ap[1];
+              if (cbase + 16 <= p.Cout) {
+                uint32_t t8[8];
+                ld_global_v8(ap, t8);
+                addv[ADD ? u : 0][0] = make_uint4(t8[0], t8[1], t8[2], t8[3]);
+                addv[ADD ? u : 0][1] = make_uint4(t8[4], t8[5], t8[6], t8[7]);
+              } else if (cbase < p.Cout) {
+                addv[ADD ? u : 0][0] = ap[0];
+              }
             }
+          }
+        }
+      };
+      // the addend loads of the first batch go out BEFORE the wait for the accumulators: their DRAM latency hides behind the MMAs
+      if (ADD) prep(0);
+      mbar_wait(TFULL(buf), (uint32_t)(tl / p.nbuf) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 4 && lane == 0) WS_TRACE(8, tl);
+      const uint32_t t_tile = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
+      for (int it0 = 0; it0 < nitems; it0 += BATCH) {
+        if (!ADD || it0 > 0) prep(it0);
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+          const int idx = it0 + u;
+          if (idx < nitems) {
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
+            tmem_ld16_nowait(t_tile + (uint32_t)((half + 2 * mbi) * p.colstride + ch * 16), raw[u]);
           }
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -316,12 +334,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
               __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
               packed[q] = *reinterpret_cast<uint32_t*>(&hh);
             }
-            if (valid) {
+            if (valid && !(p.dbg & 16)) {
               uint4* yp = reinterpret_cast<uint4*>(p.y + opos * p.Cout + cbase);
-              if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-              if (cbase + 8 < p.Cout) yp[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+              if (cbase + 16 <= p.Cout) st_global_v8(yp, packed);                  // one full sector per lane
+              else if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
-            if (p.has_stats) {
+            if (p.has_stats && !(p.dbg & 32)) {
               // statistics of the stored (rounded) values
 #pragma unroll
               for (int q = 0; q < 8; q++) {

@@ -224,3 +224,74 @@ def test_trainer_gradient_sink_and_fused_sgd(mirror, dtype):
         for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
             assert rel(p.data, q.data) <= 1e-5, k
     assert float(tr.flat_g.abs().max()) == 0.0
+
+
+def _trainer_grads(mirror, sd, batch, env):
+    """One FusionTrainer forward+backward under the given environment toggles -> (loss, flat gradient copy)."""
+    from ffpn.trainer import FusionTrainer
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                                'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+        model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        tr = FusionTrainer(model, crit, lr=0.1, momentum=0.9, weight_decay=1e-4)
+        loss = tr.forward_backward(batch)
+        torch.cuda.synchronize()
+        out = (loss.item(), tr.flat_g.clone(), {k: b.clone() for k, b in model.named_buffers()})
+        tr.close()
+        return out
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_branch_streams_are_bitwise_equal_to_serial(mirror):
+    """The forward/backward DAG on side streams (2-D encoder, per-level projections, weight gradients) must give the
+    SAME BITS as the single-stream order -- every kernel is deterministic, so any difference is a race between streams.
+    bf16 path (the tcgen05 kernels), a shape with all five levels and several tiles per CTA."""
+    import ffpn
+    ffpn.set_compute_dtype(torch.bfloat16)
+    sd = O.make_state_dict(seed=11)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 8, 64, 64, 40, 64, seed=4).items()}
+    l0, g0, b0 = _trainer_grads(mirror, sd, batch, {'FFPN_STREAMS': '0'})
+    for mode in ('1', 'branches', 'wgrad', '0', '1'):
+        l1, g1, b1 = _trainer_grads(mirror, sd, batch, {'FFPN_STREAMS': mode})
+        assert l1 == l0, (mode, l1, l0)
+        assert torch.equal(g1, g0), (mode, float((g1 - g0).abs().max()))
+        for k in b0:
+            assert torch.equal(b1[k], b0[k]), (mode, k)             # BatchNorm running statistics too
+
+
+def test_captured_graph_step_matches_eager_bitwise(mirror):
+    """FusionTrainer.capture()/replay() (multi-stream CUDA graph with the fused SGD) against eager step() on a twin model:
+    identical parameters after three optimisation steps."""
+    import ffpn
+    from ffpn.trainer import FusionTrainer
+    ffpn.set_compute_dtype(torch.bfloat16)
+    sd = O.make_state_dict(seed=12)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 32, 16, 32, seed=6).items()}
+    crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                            'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+    params = []
+    for graph in (False, True):
+        model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        tr = FusionTrainer(model, crit, lr=0.1, momentum=0.9, weight_decay=1e-4)
+        if graph:
+            tr.capture(batch, warmup=2)
+            for _ in range(3):
+                tr.replay()
+        else:
+            for _ in range(3):
+                tr.step(batch)
+        torch.cuda.synchronize()
+        params.append(tr.flat_p.clone())
+        tr.close()
+    assert torch.equal(params[0], params[1]), float((params[0] - params[1]).abs().max())
