@@ -1448,6 +1448,7 @@ int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
     const int r = ffpn_conv_wgrad_ws(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, ws, ws_bytes, st);
     if (r >= 0) return r;                                 // handled (or failed) by the warp-specialised kernel
   }
+  ffpn_log_route("conv_wgrad -> first-generation tcgen05 kernel", d);
   static bool attr_tma = false;
   if (!(in_scale != nullptr && !in_relu)) {
     WgTmaPlan t = make_wgrad_tma_plan(d, ctx->num_sms);
@@ -1617,6 +1618,7 @@ int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
     const int r = ffpn_conv_fwd_ws(ctx, d, transposed, x, in_scale, in_shift, in_relu, w, addend, y, stat_partial, stat_rows, ws, ws_bytes, st);
     if (r >= 0) return r;                                 // handled (or failed) by the warp-specialised kernel
   }
+  ffpn_log_route(transposed ? "conv_dgrad -> first-generation tcgen05 kernel" : "conv_fwd -> first-generation tcgen05 kernel", d);
   Plan pl = ffpn_tc_make_plan(d, transposed, ctx->num_sms);
   if (!pl.ok) FFPN_FAIL(ctx, "conv_tc: geometry not supported");
   TcParams& p = pl.p;

@@ -31,6 +31,7 @@ struct WgWsParams {
   int region_x, Kpad, xsub_bytes, ysub_bytes, stage_bytes, nstages, tmem_cols;
   unsigned tx_bytes, lboA, lboB;
   unsigned accA[WG2_MAX_ACC], accB[WG2_MAX_ACC];     // per global accumulator: start offsets (descriptor units) of A and B
+  int xseg;                           // lines wider than one TMA box: X cut into NB segments of xseg outputs (0 = off); dy then comes through a 5-D map
   int has_aff, gx, dbg, pair_cin;     // pair_cin: real Cin when the plan runs on the pair view of a depth-strided conv (0 = off)     // dbg (FFPN_TC_DEBUG, timing experiments): 1 no MMA, 4 no TMA, 8 no transform body
   const float* sc;
   const float* sh;
@@ -114,12 +115,16 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
         const uint32_t dst = smem_u32(stage0) + (uint32_t)s * (uint32_t)p.stage_bytes;
         mbar_expect_tx(FULL(s), (p.dbg & 4) ? 0u : p.tx_bytes);
         int x1, x2, x3, y1, y2, y3;
-        if (p.tma_mode == 0) { x1 = -p.hl; x2 = tc.it * p.tY - p.pY; x3 = tc.dt; y1 = 0; y2 = tc.it * p.tY; y3 = tc.dt; }
+        if (p.tma_mode == 0) { x1 = -p.hl + tc.nb * p.xseg; x2 = tc.it * p.tY - p.pY; x3 = tc.dt; y1 = 0; y2 = tc.it * p.tY; y3 = tc.dt; }
         else if (p.tma_mode == 1) { x1 = tc.it * p.L; x2 = tc.dt * p.tD - p.pD; x3 = tc.nb; y1 = x1; y2 = tc.dt * p.tD; y3 = tc.nb; }
         else { x1 = 0; x2 = (tc.it * p.L) >> 8; x3 = 0; y1 = 0; y2 = x2; y3 = 0; }
         if (!(p.dbg & 4))
         for (int j = 0; j < p.nys; j++)        // dy sub-tiles land 8 rows in: the rows before stay zero (shifted views)
-          tma_load_4d(dst + (uint32_t)(j * p.ysub_bytes) + 8u * (uint32_t)p.pitch_y, &tmy, co0 + j * p.Cy, y1, y2, y3, FULL(s));
+        {
+          const uint32_t ydst = dst + (uint32_t)(j * p.ysub_bytes) + 8u * (uint32_t)p.pitch_y;
+          if (p.xseg) tma_load_5d(ydst, &tmy, co0 + j * p.Cy, 0, tc.nb, y2, y3, FULL(s));
+          else tma_load_4d(ydst, &tmy, co0 + j * p.Cy, y1, y2, y3, FULL(s));
+        }
         if (!(p.dbg & 4))
         for (int j = 0; j < p.nxs; j++)
           tma_load_4d(dst + ybytes + (uint32_t)(j * p.xsub_bytes), &tmx, ci0 + j * p.Cx, x1, x2, x3, FULL(s));
@@ -357,7 +362,18 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
   const bool flat = (p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1 && p.kD == 1);
   if (p.kD > 1) { if (p.kY != 1 || p.kX != 1) return w; p.tma_mode = 1; p.kA = 1; p.kB = p.kD; }
   else if (flat) { if (p.X % 256 != 0) return w; p.tma_mode = 2; p.kA = 1; p.kB = 1; }
-  else { if (p.Xp > 256) return w; p.tma_mode = 0; p.kA = p.kX; p.kB = p.kY; }
+  else {
+    p.tma_mode = 0; p.kA = p.kX; p.kB = p.kY;
+    if (p.Xp > 256) {
+      // a padded line does not fit one TMA box: cut X into equal segments walked like batch entries.  The x tile of a segment
+      // carries real neighbour columns as halo; the dy tile must be ZERO there, which a 5-D map (C, tX, nX, Y, D) gives for
+      // free: box columns >= tX are out of bounds of the segment axis and zero-filled.
+      const int halo = p.Xp - p.oX;
+      const int nX = (p.oX + (256 - halo) - 1) / (256 - halo);
+      if (p.NB != 1 || p.oX % nX != 0) return w;
+      p.xseg = p.oX / nX; p.NB = nX; p.Xp = p.xseg + halo;
+    }
+  }
   // channel tiles and slabs
   p.co_t = p.Cout < 128 ? p.Cout : 128; p.n_co = p.Cout / p.co_t;
   p.Cy = p.co_t < 64 ? p.co_t : 64; p.nys = p.co_t / p.Cy; p.pitch_y = p.Cy * 2;
@@ -462,9 +478,19 @@ bool encode_wg_map(CUtensorMap* m, const WgWsPlan& w, const void* base, bool is_
   const cuuint64_t cb = (cuuint64_t)C * 2;
   const long long sY = is_x ? c.inY : c.outY, sD = is_x ? c.inD : c.outD, sNB = is_x ? c.inNB : c.outNB;
   const int eX = is_x ? p.X : p.oX, eY = is_x ? p.Y : p.oY, eD = is_x ? p.D : p.oD;
-  cuuint64_t dims[4], strides[3];
-  cuuint32_t box[4], es[4] = {1, 1, 1, 1};
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
   dims[0] = (cuuint64_t)C;
+  if (p.tma_mode == 0 && p.xseg && !is_x) {
+    // dy of a segmented line: (C, tX, nX, Y, D); the box is one segment wide plus the (out-of-bounds, zero) halo columns
+    dims[1] = p.xseg; dims[2] = eX / p.xseg; dims[3] = eY; dims[4] = eD;
+    strides[0] = cb; strides[1] = (cuuint64_t)p.xseg * cb; strides[2] = (cuuint64_t)(eY == 1 ? eX : sY) * cb; strides[3] = (cuuint64_t)sD * cb;
+    box[0] = (cuuint32_t)w.ybox[0]; box[1] = (cuuint32_t)w.ybox[1]; box[2] = 1; box[3] = (cuuint32_t)w.ybox[2]; box[4] = 1;
+    const int pitch = p.pitch_y;
+    const CUtensorMapSwizzle sw = pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   if (p.tma_mode == 0) {
     dims[1] = eX; dims[2] = eY; dims[3] = eD;
     strides[0] = cb; strides[1] = (cuuint64_t)(eY == 1 ? eX : sY) * cb; strides[2] = (cuuint64_t)sD * cb;

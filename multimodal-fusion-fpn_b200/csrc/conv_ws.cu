@@ -16,7 +16,7 @@ namespace {
 
 constexpr int WS_THREADS = 512;
 constexpr int WS_MAX_STAGES = 6;
-constexpr int WS_NT = 160;            // transform threads: warps 3, 12..15
+constexpr int WS_NT = 128;            // transform threads: warps 12..15, one per SM sub-partition (FFPN_WS_NT=160 adds warp 3: a fifth warp doubles one scheduler's share)
 constexpr int WS_NEPI = 8;            // epilogue warps 4..11
 constexpr int WS_HDR = 1024 + 8 * 2 * 256 * 4;   // barriers, then one statistics slot per epilogue warp (fixed-order sum: deterministic)
 
@@ -40,6 +40,8 @@ struct WsParams {
   bf16* y;
   float* stat;
   unsigned tapdesc[27];               // per tap: row offset of the A view in descriptor units ((rows * pitch) >> 4)
+  int nt;                             // transform threads (128, or 160 with warp 3)
+  int xseg, oXtot;                    // lines wider than one TMA box: X is cut into segments of xseg outputs that take the place of the batch axis (0 = off)
   int fin_on;                         // BatchNorm finalize by the last CTA to finish (ffpn_conv_fwd_bn)
   ffpn_bn_fin fin;
   unsigned* fin_counter;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < WS_MAX_STAGES; s++) {
       mbar_init(FULL(s), 1);
-      mbar_init(READY(s), WS_NT);
+      mbar_init(READY(s), (uint32_t)p.nt);
       mbar_init(EMPTY(s), 1);
     }
     for (int b = 0; b < 4; b++) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), WS_NEPI); }
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       for (tc.init(p); tc.valid(p); tc.next(p), ptl++) {
         const int r = p.niss == 2 ? (ptl & 1) : 0;
         int c1, c2, c3;
-        if (p.tma_mode == 0) { c1 = -p.hl; c2 = tc.it * p.tY - p.pY; c3 = tc.d0; }
+        if (p.tma_mode == 0) { c1 = -p.hl + tc.nb * p.xseg; c2 = tc.it * p.tY - p.pY; c3 = tc.d0; }
         else if (p.tma_mode == 1) { c1 = tc.i0; c2 = tc.d0 - p.pD; c3 = tc.nb; }
         else { c1 = 0; c2 = tc.i0 >> p.fshift; c3 = 0; }
         for (int uk = 0; uk < p.upt; uk++) {
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
             const int i = tc.i0 + ii;
             // flat / slice modes have Xp >= every i (one line): the reciprocal is only exact while i * Xp < 2^32 (mode 0)
             const int oy = i < p.Xp ? 0 : (p.Xp == 1 ? i : (int)__umulhi((uint32_t)i, magicXp)), ox = i - oy * p.Xp;
-            validv[u] = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX);
+            validv[u] = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX) && (tc.nb * p.xseg + ox < p.oXtot);
             oposv[u] = (long long)tc.nb * p.outNB + (long long)(tc.d0 + j) * p.outD + (long long)oy * p.outY + ox;
             if (ADD && validv[u]) {
               const int cbase = n0 + ch * 16;
@@ -389,12 +391,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         }
       }
     }
-  } else {
+  } else if (warp >= 12 || p.nt > WS_NT) {
     // ================= in-place BatchNorm scale/shift + ReLU of landed tiles =================
     if (p.has_aff) {
-      const int tix = warp < 4 ? tid - 96 : tid - 384 + 32;        // 0..159
+      const int tix = p.nt > WS_NT ? (warp < 4 ? tid - 96 : tid - 384 + 32) : tid - 384;   // 0..nt-1
       const int cpu = p.kgu * (p.Kc >> 3);                         // 16-byte channel chunks per row of a unit
-      const int rstep = WS_NT / cpu;
+      const int rstep = p.nt / cpu;
       const bool active = tix < rstep * cpu;
       const int c = tix % cpu, r0 = tix / cpu;
       const int kgi = c / (p.Kc >> 3), cc = c % (p.Kc >> 3);
@@ -555,6 +557,16 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   }
   const int ntaps = p.kD * p.kY * p.kX;
   if (ntaps > 27 || p.Cin % 16 != 0) return w;
+  p.xseg = 0; p.oXtot = p.oX;
+  if (p.kD == 1 && p.Xp > 256 && p.NB == 1 && !(p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1)) {
+    // a padded line does not fit one TMA box (256 positions): cut X into nX segments.  A segment is a tile column with
+    // its own halo (real neighbour data inside the image, TMA fill outside) and is walked like a batch entry: the TMA x
+    // coordinate and the output position both advance by nb * xseg.
+    const int halo = p.Xp - p.oX;
+    const int nX = (p.oX + (256 - halo) - 1) / (256 - halo);
+    const int tX = (p.oX + nX - 1) / nX;
+    p.xseg = tX; p.NB = nX; p.outNB = tX; p.oX = tX; p.Xp = tX + halo; p.Qout = (p.oY - 1) * p.Xp + p.oX;
+  }
   const int hr = p.Xp - p.oX;
   const int maxinner = (p.kY - 1) * p.Xp + hr;
   static int cs16 = -1;
@@ -737,6 +749,7 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     p.fin_on = 1; p.fin = *fin; p.fin_counter = ctx->d_counter;
   }
   p.aff_mod = (pair && !transposed) ? d->Cin : 0;
+  { const char* e = getenv("FFPN_WS_NT"); p.nt = (e && atoi(e) == 160) ? 160 : WS_NT; }
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
   static bool attr_set = false;
   if (!attr_set) {

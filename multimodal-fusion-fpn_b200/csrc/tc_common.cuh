@@ -131,6 +131,13 @@ static __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorM
       : "memory");
 }
 
+static __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 struct Plan {
   TcParams p;
   size_t smem;

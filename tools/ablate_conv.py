@@ -28,6 +28,12 @@ for level in levels:
         elif kind == 'fwd133stats':
             gam, bet, rm, rv = torch.ones(C, device='cuda'), torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
             fn = lambda: ops.conv_fwd_bn(x, w, (1, 3, 3), (1, 1, 1), (0, 1, 1), sc, sh, True, gam, bet, rm, rv, 0.1, 1e-5, True)
+        elif kind == 'proj':
+            wp = torch.randn(C, C, 1, 1, 3, device='cuda', generator=g) * 0.1
+            fn = lambda: ops.conv_fwd(x, wp, (1, 1, 3), (1, 1, 2), (0, 0, 1), sc, sh, True)
+        elif kind == 'fwd311':
+            w3 = torch.randn(C, C, 3, 1, 1, device='cuda', generator=g) * 0.1
+            fn = lambda: ops.conv_fwd(x, w3, (3, 1, 1), (1, 1, 1), (1, 0, 0), sc, sh, True)
         elif kind == 'dgrad133':
             fn = lambda: ops.conv_dgrad(x, w, tuple(x.shape), (1, 3, 3), (1, 1, 1), (0, 1, 1))
         elif kind == 'dgrad133add':
@@ -36,6 +42,9 @@ for level in levels:
             raise SystemExit(kind)
         out = []
         for d in dbgs:
+            if d >= 1000:                                   # 1128 / 1160: full kernel with FFPN_WS_NT = 128 / 160 transform threads
+                os.environ['FFPN_WS_NT'] = str(d - 1000)
+                d = 0
             os.environ['FFPN_TC_DEBUG'] = str(d)
             fn(); torch.cuda.synchronize()
             side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
@@ -51,6 +60,6 @@ for level in levels:
             e0.record(); graph.replay(); e1.record(); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / iters * 1e3
             off = '+'.join(n for b, n in names.items() if d & b) or 'none'
-            out.append(f'off[{off}] {us:.1f}')
+            out.append(f'off[{off}] nt{os.environ.get("FFPN_WS_NT", "128")} {us:.1f}')
         os.environ['FFPN_TC_DEBUG'] = '0'
         print(f'level {level} {kind}: ' + ' | '.join(out), flush=True)
