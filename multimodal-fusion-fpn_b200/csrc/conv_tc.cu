@@ -1405,19 +1405,22 @@ bool encode_map4(CUtensorMap* m, const void* base, const long long* dims, const 
 
 namespace {
 // dw[i] += sum over the K-split slices, in slice order (bitwise reproducible, unlike atomics on dw itself)
-__global__ void wgrad_slice_reduce_kernel(const float* __restrict__ part, int nslices, long long n, float* __restrict__ dw) {
+__global__ void __launch_bounds__(128) wgrad_slice_reduce_kernel(const float* __restrict__ part, int nslices, long long n, float* __restrict__ dw) {
   pdl_prologue();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int k = 0;
-    for (; k + 3 < nslices; k += 4) {
-      a0 += part[(size_t)k * n + i];
-      a1 += part[(size_t)(k + 1) * n + i];
-      a2 += part[(size_t)(k + 2) * n + i];
-      a3 += part[(size_t)(k + 3) * n + i];
+  // one block per output: thread t adds slices t, t + 128, ... then a fixed-shape tree (same bits every run)
+  __shared__ float red[128];
+  for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+    float a = 0.f;
+    for (int k = threadIdx.x; k < nslices; k += 128) a += part[(size_t)k * n + i];
+    red[threadIdx.x] = a;
+    __syncthreads();
+#pragma unroll
+    for (int o = 64; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
     }
-    for (; k < nslices; k++) a0 += part[(size_t)k * n + i];
-    dw[i] += (a0 + a1) + (a2 + a3);
+    if (threadIdx.x == 0) dw[i] += red[0];
+    __syncthreads();
   }
 }
 constexpr size_t FFPN_WG_SLICE_MAX_BYTES = (size_t)64 << 20;
@@ -1428,8 +1431,8 @@ long long wgrad_slices(const ffpn_conv_desc* d, unsigned gx, size_t ws_bytes) {
   return (need <= FFPN_WG_SLICE_MAX_BYTES && need <= ws_bytes) ? n : 0;
 }
 int wgrad_slices_finish(ffpn_ctx* ctx, const float* part, unsigned gx, long long n, float* dw, cudaStream_t st) {
-  const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
-  ffpn_launch(wgrad_slice_reduce_kernel, blocks, 256, 0, st, part, (int)gx, n, dw);
+  const int blocks = (int)(n < 16384 ? n : 16384);
+  ffpn_launch(wgrad_slice_reduce_kernel, blocks, 128, 0, st, part, (int)gx, n, dw);
   FFPN_CHECK_LAUNCH(ctx, "wgrad_slice_reduce");
   return 0;
 }

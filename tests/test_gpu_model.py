@@ -295,3 +295,39 @@ def test_captured_graph_step_matches_eager_bitwise(mirror):
         params.append(tr.flat_p.clone())
         tr.close()
     assert torch.equal(params[0], params[1]), float((params[0] - params[1]).abs().max())
+
+
+def test_prefetched_replay_equals_direct_replay(mirror):
+    """FusionTrainer.prefetch() (copy stream + staging buffers) followed by replay(prefetched=True) must feed the captured step
+    exactly the batch that replay(batch) would: two different batches, identical parameters afterwards."""
+    import ffpn
+    from ffpn.trainer import FusionTrainer
+    ffpn.set_compute_dtype(torch.bfloat16)
+    sd = O.make_state_dict(seed=13)
+    hosts = [{k: v.pin_memory() for k, v in O.synthetic_batch(2, 4, 64, 32, 16, 32, seed=s).items()} for s in (7, 8)]
+    crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                            'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+    params, losses = [], []
+    for pre in (False, True):
+        model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        tr = FusionTrainer(model, crit, lr=0.1, momentum=0.9, weight_decay=1e-4)
+        tr.capture({k: v.cuda() for k, v in hosts[0].items()}, warmup=2)
+        ls = []
+        if pre:
+            tr.prefetch(hosts[0])
+            for i in range(2):
+                loss = tr.replay(prefetched=True)
+                if i == 0:
+                    tr.prefetch(hosts[1])
+                ls.append(loss.item())
+        else:
+            for i in range(2):
+                ls.append(tr.replay(hosts[i]).item())
+        torch.cuda.synchronize()
+        params.append(tr.flat_p.clone())
+        losses.append(ls)
+        tr.close()
+    assert losses[0] == losses[1] and losses[0][0] != losses[0][1]
+    assert torch.equal(params[0], params[1])
