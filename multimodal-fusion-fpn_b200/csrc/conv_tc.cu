@@ -525,6 +525,14 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ w, int64_t
       const int rr = n / Cin, ci = n - rr * Cin;
       const int dx = rr + pH - sH * (tap + tmin);
       if (dx >= 0 && dx < kH) v = w[((int64_t)k * Cin + ci) * kH + dx];
+    } else if (mode == 5 || mode == 6) {      // stride-1 conv on the pair view of input and output (ffpn_make_pair2_desc): 5 forward, 6 dgrad
+      // operator channels: forward n = (ho,co), k = (hi,ci); dgrad n = (hi,ci), k = (ho,co) and flipped taps.  Cout / Cin = the real ones
+      const int nn = mode == 5 ? n : k, kk = mode == 5 ? k : n;
+      const int ho = nn / Cout, co = nn - ho * Cout, hi = kk / Cin, ci = kk - hi * Cin;
+      const int tp = mode == 5 ? tap : ntaps - 1 - tap;
+      const int t3 = tp % 3, dyw = tp / 3;
+      const int dx = 2 * (t3 - 1) + hi - ho + 1;
+      if (dx >= 0 && dx < 3) v = w[((int64_t)co * Cin + ci) * ntaps + dyw * 3 + dx];
     } else {                                  // pair view of the (1,1,3) s2 p1 conv: 3 forward (k = (h,ci)), 4 dgrad (n = (h,ci))
       const int c2 = mode == 3 ? k : n, oc = mode == 3 ? n : k;
       const int hh = c2 / Cin, ci = c2 - hh * Cin;

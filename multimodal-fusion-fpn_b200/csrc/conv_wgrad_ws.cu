@@ -369,8 +369,9 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
       // carries real neighbour columns as halo; the dy tile must be ZERO there, which a 5-D map (C, tX, nX, Y, D) gives for
       // free: box columns >= tX are out of bounds of the segment axis and zero-filled.
       const int halo = p.Xp - p.oX;
-      const int nX = (p.oX + (256 - halo) - 1) / (256 - halo);
-      if (p.NB != 1 || p.oX % nX != 0) return w;
+      int nX = (p.oX + (256 - halo) - 1) / (256 - halo);
+      while (nX < 64 && p.oX % nX != 0) nX++;                 // equal segments only (the 5-D dy map has one segment extent)
+      if (p.NB != 1 || p.oX % nX != 0 || p.oX / nX < 8) return w;
       p.xseg = p.oX / nX; p.NB = nX; p.Xp = p.xseg + halo;
     }
   }

@@ -160,6 +160,20 @@ static inline bool ffpn_make_pair_desc(const ffpn_conv_desc* d, ffpn_conv_desc* 
   return true;
 }
 
+// Narrow stride-1 convs with three taps along the contiguous axis, (kS=1, kW, 3) pad (.,.,1), are shared-memory bound on the
+// tensor core's reads of the tap views.  On the pair view of input AND output -- x'[.., H/2, 2Cin],
+// y'[.., H/2, 2Cout] -- the conv is again a 3-tap stride-1 conv, W'[(ho,co)][(hi,ci)][t'] = W[co][ci][dx] with
+// dx = 2(t'-1) + hi - ho + 1 (zero when outside 0..2), and the outer pair taps have an all-zero K half (t'=0 only reads the odd
+// element, t'=2 only the even one), which the MMA loop skips: 4 instead of 6 K=16 tap reads per two positions.
+static inline bool ffpn_make_pair2_desc(const ffpn_conv_desc* d, ffpn_conv_desc* dp) {
+  if (d->dtype != FFPN_BF16 || d->kS != 1 || d->kH != 3 || d->sS != 1 || d->sW != 1 || d->sH != 1 || d->pS != 0 || d->pH != 1 ||
+      (d->H & 1) || d->oH != d->H || d->H < 4 || !(d->Cin == 16 || d->Cin == 32) || !(d->Cout == 16 || d->Cout == 32))
+    return false;
+  *dp = *d;
+  dp->H = d->H / 2; dp->oH = d->oH / 2; dp->Cin = 2 * d->Cin; dp->Cout = 2 * d->Cout;
+  return true;
+}
+
 // BatchNorm finalize fused into the producing conv kernel (done by the last CTA to finish): ffpn_conv_fwd_bn
 struct ffpn_bn_fin {
   double count;

@@ -51,7 +51,6 @@ CASES = [
     # uneven split: tail segment validity in the fwd/dgrad epilogue)
     ('wide_133_496', 16, 16, (1, 3, 3), (0, 1, 1), (1, 2, 12, 496)),
     ('wide_133_301', 32, 32, (1, 3, 3), (0, 1, 1), (1, 2, 9, 301)),
-    ('wide_133_520', 64, 64, (1, 3, 3), (0, 1, 1), (1, 1, 10, 520)),
     # projection: depth-strided convs (de-interleaved residue planes) and strided 1x1x1 shortcuts
     ('proj_s2_l1', 16, 16, (1, 1, 3), (0, 0, 1), (2, 3, 16, 128), (1, 1, 2)),
     ('proj_s2_l3', 64, 64, (1, 1, 3), (0, 0, 1), (2, 3, 8, 32), (1, 1, 2)),
@@ -144,3 +143,45 @@ def test_conv_tc(case):
                 assert torch.equal(dw, dw1)                # fixed-order partial-tile reduction: bitwise reproducible
     finally:
         ops.set_conv_impl(old)
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 16), (16, 32), (32, 32)])
+def test_conv_pair_view_stride1(cin, cout):
+    """FFPN_WS_PAIR2=1: narrow (1,3,3) convs on the pair view of input and output (remapped weights, all-zero K halves of the
+    outer pair taps skipped, statistics folded).  Off by default (measured slower) but kept correct:
+    forward (+BN prologue, statistics) and dgrad (+addend) against torch, and against the default path."""
+    from ffpn import ops
+    torch.backends.cudnn.allow_tf32 = False
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(100 + cin + cout)
+    B, S, W, H = 2, 3, 20, 64
+    x = torch.randn(B, cin, S, W, H, generator=g).cuda()
+    w = (torch.randn(cout, cin, 1, 3, 3, generator=g) / (cin * 9) ** 0.5).cuda()
+    sc, sh = (0.5 + torch.rand(cin, generator=g)).cuda(), (0.3 * torch.randn(cin, generator=g)).cuda()
+    xq = x.to(dt).float()
+    xin = torch.relu(xq * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
+    ref = F.conv3d(xin, w.to(dt).float(), None, 1, (0, 1, 1))
+    dy = torch.randn(ref.shape, generator=g).cuda().to(dt)
+    xr = xq.clone().requires_grad_(True)
+    F.conv3d(xr, w.to(dt).float(), None, 1, (0, 1, 1)).backward(dy.float())
+    add = torch.randn(B, cin, S, W, H, generator=g).cuda().to(dt)
+    outs = {}
+    old = ops.get_conv_impl()
+    try:
+        ops.set_conv_impl(2)
+        for flag in ('0', '1'):
+            os.environ['FFPN_WS_PAIR2'] = flag
+            y, partial, rows = ops.conv_fwd(phys(x).to(dt), w, (1, 3, 3), (1, 1, 1), (0, 1, 1), sc, sh, True)
+            dx = ops.conv_dgrad(phys(dy), w, tuple(phys(x).shape), (1, 3, 3), (1, 1, 1), (0, 1, 1), addend=phys(add))
+            torch.cuda.synchronize()
+            assert rel(logical(y.float()), ref) <= 1e-2, (flag, rel(logical(y.float()), ref))
+            assert rel(logical(dx.float()), xr.grad + add.float()) <= 1e-2
+            st = partial.view(-1, 2, cout)[:rows].double().sum(0)
+            ys = y.float().double().reshape(-1, cout)
+            assert torch.allclose(st[0], ys.sum(0), rtol=1e-3, atol=1e-3 * ys.abs().sum(0).max().item())
+            assert torch.allclose(st[1], (ys * ys).sum(0), rtol=1e-3)
+            outs[flag] = (y.float(), dx.float())
+    finally:
+        os.environ.pop('FFPN_WS_PAIR2', None)
+        ops.set_conv_impl(old)
+    assert rel(outs['1'][0], outs['0'][0]) <= 4e-3 and rel(outs['1'][1], outs['0'][1]) <= 4e-3
