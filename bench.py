@@ -304,7 +304,7 @@ def main():
             'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': w['name'], 'per_gpu_batch': w['B'], 'global_batch': w['B'] * world,
                        'parallelism': f'dp{world}', 'cuda_graph': use_graph,
-                       'branch_streams': os.environ.get('FFPN_STREAMS', '1'), 'pdl': os.environ.get('FFPN_PDL', '0'),
+                       'branch_streams': os.environ.get('FFPN_STREAMS', '1'), 'pdl': os.environ.get('FFPN_PDL', '1'),
                        'optimizer': 'SGD(0.1, 0.9, wd 1e-4) fused',
                        'l2': 'per-step working set >> 126 MB L2 (no flush needed)', 'final_loss': last},
             'clocks': clocks,
