@@ -31,6 +31,7 @@ struct WgWsParams {
   int region_x, Kpad, xsub_bytes, ysub_bytes, stage_bytes, nstages, tmem_cols;
   unsigned tx_bytes, lboA, lboB;
   unsigned accA[WG2_MAX_ACC], accB[WG2_MAX_ACC];     // per global accumulator: start offsets (descriptor units) of A and B
+  int pdl_early;                      // wait for the predecessor grid only after the prologue (FFPN_PDL_EARLY)
   int xseg;                           // lines wider than one TMA box: X cut into NB segments of xseg outputs (0 = off); dy then comes through a 5-D map
   int has_aff, gx, dbg, pair_cin;     // pair_cin: real Cin when the plan runs on the pair view of a depth-strided conv (0 = off)     // dbg (FFPN_TC_DEBUG, timing experiments): 1 no MMA, 4 no TMA, 8 no transform body
   const float* sc;
@@ -59,7 +60,8 @@ struct WgTile {
 __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __grid_constant__ WgWsParams p,
                                                                        const __grid_constant__ CUtensorMap tmx,
                                                                        const __grid_constant__ CUtensorMap tmy) {
-  pdl_prologue();
+  pdl_trigger();
+  if (!p.pdl_early) pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (p.pdl_early) pdl_wait();                    // barrier init, smem zeroing and TMEM allocation overlapped the predecessor
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t ybytes = (uint32_t)(p.nys * p.ysub_bytes);
 
@@ -546,6 +549,7 @@ int ffpn_conv_wgrad_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
   WgWsParams& p = pl.p;
   p.sc = in_scale; p.sh = in_shift; p.has_aff = in_scale != nullptr; p.part = (float*)ws;
   p.pair_cin = pair ? d->Cin : 0;
+  { const char* e = getenv("FFPN_PDL_EARLY"); p.pdl_early = (e && atoi(e) == 0) ? 0 : 1; }
   { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   static bool attr_set = false;
   if (!attr_set) {

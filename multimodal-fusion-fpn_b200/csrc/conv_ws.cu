@@ -40,6 +40,7 @@ struct WsParams {
   bf16* y;
   float* stat;
   unsigned tapdesc[27];               // per tap: row offset of the A view in descriptor units ((rows * pitch) >> 4)
+  int pdl_early;                      // wait for the predecessor grid only after the prologue (FFPN_PDL_EARLY)
   int nt;                             // transform threads (128, or 160 with warp 3)
   int pair2;                          // stride-1 conv on the pair view of input and output: real Cout (statistics are folded to it), 0 = off
   int xseg, oXtot;                    // lines wider than one TMA box: X is cut into segments of xseg outputs that take the place of the batch axis (0 = off)
@@ -99,7 +100,8 @@ struct WsRing {
 template <int NREG, bool ADD>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ WsParams p,
                                                                 const __grid_constant__ CUtensorMap tmap) {
-  pdl_prologue();
+  pdl_trigger();
+  if (!p.pdl_early) pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (p.pdl_early) pdl_wait();                    // nothing above touched global memory: the prologue overlapped the predecessor
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t buf_cols = (uint32_t)(p.tmem_cols / p.nbuf);
 
@@ -775,6 +778,7 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     p.fin_on = 1; p.fin = *fin; p.fin_counter = ctx->d_counter;
   }
   p.aff_mod = ((pair || pair2) && !transposed) ? d->Cin : 0;
+  { const char* e = getenv("FFPN_PDL_EARLY"); p.pdl_early = (e && atoi(e) == 0) ? 0 : 1; }
   p.pair2 = pair2 ? (transposed ? d->Cin : d->Cout) : 0;
   { const char* e = getenv("FFPN_WS_NT"); p.nt = (e && atoi(e) == 160) ? 160 : WS_NT; }
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
