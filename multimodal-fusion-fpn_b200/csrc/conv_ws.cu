@@ -5,11 +5,13 @@
 //     the matching SWIZZLE_32B/64B/128B K-major layout, so ONE TMA box (inner extent = the whole channel run) stages a
 //     tile.  The hardware swizzle is a function of the absolute smem address, so a descriptor whose start address is
 //     shifted by any number of rows still reads the right data (tools/umma_probe.cu, base_offset 0);
-//   * roles are split over warps and decoupled by mbarriers: warp 0 issues TMA into a ring of stages, six warps apply
-//     the producer's BatchNorm scale/shift + ReLU in place (halo = NaN fill -> 0), warp 1 issues the MMAs (tap-outer,
-//     accumulator-block-inner so consecutive MMAs hit different TMEM tiles), eight warps drain the double-buffered
-//     TMEM accumulators, store channels-last bf16 rows (+ residual addend) and accumulate the BatchNorm partial sums
-//     in registers (N <= 32) or by warp-shuffle transposes.
+//   * roles are split over warps and decoupled by mbarriers: warp 0 issues TMA into a ring of stages, four warps (one
+//     per SM sub-partition) apply the producer's BatchNorm scale/shift + ReLU in place (halo = NaN fill -> 0), warps 1-2
+//     issue the MMAs (alternating tiles; tap-outer, accumulator-block-inner so consecutive MMAs hit different TMEM
+//     tiles), eight warps drain the TMEM tile buffers, store channels-last bf16 rows with one 256-bit store per lane
+//     (+ residual addend) and accumulate the BatchNorm partial sums in registers (N <= 32) or by warp-shuffle transposes;
+//   * lines wider than one TMA box are cut into X segments walked like batch entries (xseg); narrow 3-tap layers can run
+//     on the pair view of input and output (pair2, off by default).
 #include "ws_common.cuh"
 
 namespace {
