@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
   if (tid == 0) {
     for (int s = 0; s < WG2_MAX_STAGES; s++) {
       mbar_init(FULL(s), 1);
-      mbar_init(READY(s), WG2_NT);
+      mbar_init(READY(s), WG2_NT / 32);
       mbar_init(EMPTY(s), 1);
     }
     mbar_init(DONE, 1);
@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(READY(st));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(READY(st));           // one arrival per warp
         if (++st == p.nstages) { st = 0; ph ^= 1u; }
       }
     }

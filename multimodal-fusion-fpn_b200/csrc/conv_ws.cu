@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < WS_MAX_STAGES; s++) {
       mbar_init(FULL(s), 1);
-      mbar_init(READY(s), (uint32_t)p.nt);
+      mbar_init(READY(s), (uint32_t)(p.nt >> 5));
       mbar_init(EMPTY(s), 1);
     }
     for (int b = 0; b < 4; b++) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), WS_NEPI); }
@@ -456,7 +456,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(READY(st));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(READY(st));         // one arrival per warp: 128 arrivals on one barrier serialise in shared memory
           if (tix == 0 && uk == p.upt - 1) WS_TRACE(11, ttl);
           ring.advance(r, p);
         }
