@@ -42,6 +42,7 @@ struct WsParams {
   bf16* y;
   float* stat;
   unsigned tapdesc[27];               // per tap: row offset of the A view in descriptor units ((rows * pitch) >> 4)
+  unsigned tap_dx, tap_dy, tap_dd;    // its increments per dx / dy / dd step (the issue loop only loads tapdesc[0])
   int pdl_early;                      // wait for the predecessor grid only after the prologue (FFPN_PDL_EARLY)
   int nt;                             // transform threads (128, or 160 with warp 3)
   int pair2;                          // stride-1 conv on the pair view of input and output: real Cout (statistics are folded to it), 0 = off
@@ -219,12 +220,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           for (int kgi = 0; kgi < p.kgu; kgi++) {
             const uint32_t a_lo0 = (((a_stage + (uint32_t)(kgi * p.sub_bytes)) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t first_k = (uint32_t)(uk | kgi);
-            for (int tap = 0; tap < ntaps; tap++) {
-              const uint32_t a_lo1 = a_lo0 + p.tapdesc[tap];
-              const uint32_t b_lo1 = b_lo0 + (uint32_t)(kgi * ntaps + tap) * btap;
+            // taps walked as (dd, dy, dx) with running descriptor offsets: an indexed constant load per tap (p.tapdesc[tap]) sits
+            // ~190 cycles on the issue path, which starves the tensor pipe on small tiles (FFPN_WS_TRACE, everything-off mode)
+            int tx = 0, ty = 0;
+            uint32_t t_off = p.tapdesc[0], t_row = p.tapdesc[0], t_slice = p.tapdesc[0];
+            uint32_t b_lo1 = b_lo0 + (uint32_t)(kgi * ntaps) * btap;
+            for (int tap = 0; tap < ntaps; tap++, b_lo1 += btap) {
+              const uint32_t a_lo1 = a_lo0 + t_off;
               // pair view: the outer pair taps only read one element of the pair -> half of their K steps are all-zero weights
-              const int t3 = p.pair2 ? tap % 3 : 1;
+              const int t3 = p.pair2 ? tx : 1;
               const int ks_lo = t3 == 0 ? (nks >> 1) : 0, ks_hi = t3 == 2 ? (nks >> 1) : nks;
+              // next tap's offset: dx fastest, then dy (one padded line), then dd (one slice region)
+              if (++tx == p.kX) {
+                tx = 0;
+                if (++ty == p.kY) { ty = 0; t_slice += p.tap_dd; t_row = t_slice; } else { t_row += p.tap_dy; }
+                t_off = t_row;
+              } else {
+                t_off += p.tap_dx;
+              }
               for (int ks = ks_lo; ks < ks_hi; ks++) {
                 const uint64_t bd = desc64(b_lo1 + (uint32_t)ks * bstep, b_hi);
                 const uint32_t acc = (first_k | started) != 0 ? 1u : 0u;
@@ -679,6 +692,7 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
           const int dx = t % p.kX, dy = (t / p.kX) % p.kY, dd = t / (p.kX * p.kY);
           p.tapdesc[t] = (unsigned)((dd * Lr + dy * p.Xp + dx - p.pX + p.hl) * pitch) >> 4;
         }
+        p.tap_dx = (unsigned)pitch >> 4; p.tap_dy = (unsigned)(p.Xp * pitch) >> 4; p.tap_dd = (unsigned)(Lr * pitch) >> 4;
         p.nD = (p.oD + tD - 1) / tD;
         p.nI = (p.Qout + L - 1) / L;
         const int ntiles = p.NB * p.nD * p.nI;
