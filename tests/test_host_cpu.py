@@ -166,3 +166,50 @@ def test_dp_gradient_average_world2_gloo():
         assert r[3]
         for k in want:
             assert torch.allclose(r[2][k], want[k], atol=1e-7)
+
+
+def test_every_kernel_waits_for_its_predecessor_grid():
+    """Programmatic dependent launch is only safe if EVERY kernel launched with the attribute begins with
+    griddepcontrol.wait before it touches global memory, and if no launch bypasses ffpn_launch().  Source-level guard:
+    each __global__ body starts with pdl_prologue() (or pdl_trigger() + a later pdl_wait()), no raw <<< >>> launches."""
+    import glob
+    csrc = os.path.join(REPO, 'multimodal-fusion-fpn_b200', 'csrc')
+    nkernels = 0
+    for path in sorted(glob.glob(os.path.join(csrc, '*.cu'))):
+        src = open(path).read()
+        assert '<<<' not in src, f'{os.path.basename(path)}: raw kernel launch bypasses ffpn_launch()'
+        pos = 0
+        while True:
+            j = src.find('__global__', pos)
+            if j < 0:
+                break
+            k = j + len('__global__')
+            m = re.compile(r'\s*(?:void\s+)?__launch_bounds__\s*\(').match(src, k)
+            if m:                                   # skip the balanced __launch_bounds__(...)
+                depth, k = 1, m.end()
+                while depth:
+                    depth += (src[k] == '(') - (src[k] == ')')
+                    k += 1
+            k = src.find('(', k)                    # parameter list
+            depth, k = 1, k + 1
+            while depth:
+                depth += (src[k] == '(') - (src[k] == ')')
+                k += 1
+            b = src.find('{', k)
+            first = src[b + 1:b + 200].strip()
+            assert first.startswith('pdl_prologue();') or first.startswith('pdl_trigger();'), (os.path.basename(path), first[:60])
+            if first.startswith('pdl_trigger();'):
+                end = src.find('\n}\n', b)
+                assert 'pdl_wait();' in src[b:end], os.path.basename(path)
+            nkernels += 1
+            pos = b + 1
+    assert nkernels >= 40
+
+
+def test_branch_stream_toggle(monkeypatch):
+    from ffpn import functional as FF
+    for value, branches, wgrad in (('1', True, True), ('0', False, False), ('branches', True, False), ('wgrad', False, True)):
+        monkeypatch.setenv('FFPN_STREAMS', value)
+        assert FF.streams_enabled() is branches and FF.streams_enabled('wgrad') is wgrad
+    monkeypatch.delenv('FFPN_STREAMS')
+    assert FF.streams_enabled() and FF.streams_enabled('wgrad')
