@@ -143,9 +143,10 @@ def _dp_worker(rank, world, port, q):
     g = torch.Generator().manual_seed(100 + rank)
     for p in net.parameters():
         p.grad.copy_(torch.randn(p.shape, generator=g))          # rank-local gradients (own BN stats / loss)
-    local = {k: p.grad.clone() for k, p in net.named_parameters()}
+    local = {k: p.grad.clone().numpy() for k, p in net.named_parameters()}
     scale = allreduce_mean_(flat_g)
-    q.put((rank, local, {k: p.grad.clone() * scale for k, p in net.named_parameters()},
+    # numpy arrays are pickled by value: torch tensors would travel as file descriptors that die with this process
+    q.put((rank, local, {k: (p.grad.clone() * scale).numpy() for k, p in net.named_parameters()},
            all(p.data_ptr() >= flat_p.data_ptr() for p in net.parameters())))
     dist.destroy_process_group()
 
@@ -161,11 +162,11 @@ def test_dp_gradient_average_world2_gloo():
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
-    want = O.dp_average_gradients([res[0][1], res[1][1]])
+    want = O.dp_average_gradients([{k: torch.from_numpy(v) for k, v in res[i][1].items()} for i in range(2)])
     for r in res:
         assert r[3]
         for k in want:
-            assert torch.allclose(r[2][k], want[k], atol=1e-7)
+            assert torch.allclose(torch.from_numpy(r[2][k]), want[k], atol=1e-7)
 
 
 def test_every_kernel_waits_for_its_predecessor_grid():
