@@ -214,3 +214,56 @@ def test_branch_stream_toggle(monkeypatch):
         assert FF.streams_enabled() is branches and FF.streams_enabled('wgrad') is wgrad
     monkeypatch.delenv('FFPN_STREAMS')
     assert FF.streams_enabled() and FF.streams_enabled('wgrad')
+
+
+def test_checkpoint_roundtrip_reference_layout(mirror, tmp_path):
+    """ffpn.checkpoint: pytorch-lightning 1.5.10 `save_weights_only` layout (wrapper keys, `model.` prefix), the loading
+    rules of train.py:146-153 (with / without 'state_dict') and the legacy key fix of validate_ensemble.py:251-256."""
+    from ffpn import checkpoint as ck
+    torch.manual_seed(3)
+    net = mirror.build('FPNHybridFusion')
+    net.apply(mirror.weight_init.weight_init)
+    wrap = mirror.wrapper.Model(net, None, None, None, None, None)
+    path = str(tmp_path / 'epoch=3-Dice=0.9000.ckpt')
+    ck.save_checkpoint(net, path, epoch=3, global_step=120)            # from the bare network ...
+    blob = torch.load(path)
+    assert set(blob) == {'epoch', 'global_step', 'pytorch-lightning_version', 'state_dict'} and blob['epoch'] == 3
+    assert list(blob['state_dict']) == list(wrap.state_dict())          # ... same keys and order as the wrapper's
+    # wrapper <- file, bare network <- file, bare network <- bare state dict, legacy 'resensenet' spelling
+    for target, source in ((mirror.wrapper.Model(mirror.build('FPNHybridFusion'), None, None, None, None, None), path),
+                           (mirror.build('FPNHybridFusion'), path),
+                           (mirror.build('FPNHybridFusion'), net.state_dict()),
+                           (mirror.build('FPNHybridFusion'),
+                            {'state_dict': {k.replace('resensnet', 'resensenet'): v for k, v in wrap.state_dict().items()}})):
+        ck.load_checkpoint(target, source, strict=True)
+        got = target.model.state_dict() if isinstance(target, mirror.wrapper.Model) else target.state_dict()
+        for k, v in net.state_dict().items():
+            assert torch.equal(got[k], v), k
+    with pytest.raises(RuntimeError):                                   # strict: a foreign key is an error, as in the reference
+        ck.load_checkpoint(mirror.build('FPNHybridFusion'), {**net.state_dict(), 'bogus.weight': torch.zeros(1)})
+
+
+def test_ensemble_averages_like_the_reference():
+    """test_utils.average_outputs semantics (dict key by key, tensors sum/n, strings: first) and eval-mode members."""
+    from ffpn import checkpoint as ck
+
+    class Member(torch.nn.Module):
+        def __init__(self, bias):
+            super().__init__()
+            self.bn = torch.nn.BatchNorm1d(1)
+            self.bias = bias
+
+        def forward(self, batch):
+            assert not self.training                                    # ensemble members run on running statistics
+            return {'prediction': batch['image'] + self.bias, 'id': f'scan-{self.bias}'}
+
+    ens = ck.Ensemble([Member(b) for b in (0.0, 1.0, 5.0)])
+    ens.train()                                                         # stays in eval mode
+    x = torch.arange(6.).view(2, 3)
+    out = ens({'image': x})
+    assert torch.allclose(out['prediction'], x + 2.0) and out['id'] == 'scan-0.0'
+    assert not out['prediction'].requires_grad
+    with pytest.raises(AssertionError):
+        ck.average_outputs([1, 2], int)
+    with pytest.raises(ValueError):
+        ck.Ensemble([])
