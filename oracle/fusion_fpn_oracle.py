@@ -270,7 +270,7 @@ def fusion_body_forward(sd: StateDict, oct: Tensor, slo: Tensor, interpolate: Op
     oct: (B,1,S,W,H) depth last; slo: (B,1,S',W').  Returns (B,n_classes,S,W,1).
     ``stages`` (optional dict) receives every named intermediate for stage-level parity.
     """
-    P = prefix + '.'
+    P = prefix + '.' if prefix else ''
     n2d = 5 if level5 else 4
     f2d, x = [], slo
     for l in range(1, n2d + 1):
@@ -325,16 +325,22 @@ def fpn_hybrid_fusion_forward(sd: StateDict, batch: Dict[str, Tensor], crop: str
 # --------------------------------------------------------------------------------------
 
 def unet3d_body_forward(sd: StateDict, oct: Tensor, train: bool = True, prefix: str = 'resensnet',
-                        use_1x1: bool = True, rec: Optional[BNRecorder] = None) -> Tensor:
-    """ModifiedUnet3D.forward, original=False, classification=False (models/fpn/unets3D.py:441-485)."""
-    P = prefix + '.'
+                        use_1x1: bool = True, rec: Optional[BNRecorder] = None, original: bool = False,
+                        classification: bool = False) -> Tensor:
+    """ModifiedUnet3D.forward (models/fpn/unets3D.py:441-485).  ``classification`` returns conv5 (:453-454);
+    ``original`` keeps the depth axis after the kernel-8 projection tail instead of averaging it (:458-471; the
+    tail's kernel size comes with the weights, :79-82)."""
+    P = prefix + '.' if prefix else ''
     f3d, x = [], oct
     for l in range(1, 6):
         x = encoder_level_3d(x, sd, f'{P}conv{l}', train, rec)
         f3d.append(x)
         if l < 5:
             x = F.max_pool3d(x, POOLS_3D[l - 1])
-    proj = [projection_block(f3d[l - 1], sd, f'{P}zdimRed{l}', 5 - l, train, rec) for l in range(1, 6)]
+    if classification:
+        return f3d[4]
+    proj = [projection_block(f3d[l - 1], sd, f'{P}zdimRed{l}', 5 - l, train, rec, take_mean=not original)
+            for l in range(1, 6)]
     deeper = proj[4]
     for l in (4, 3, 2, 1):
         deeper = up_block([proj[l - 1]], deeper, sd, f'{P}up_concat{l}', UPFACTORS[l], train, rec)
@@ -347,7 +353,7 @@ def unet2d_body_forward(sd: StateDict, img: Tensor, train: bool = True, prefix: 
                         level5: bool = True, output_features: bool = False,
                         rec: Optional[BNRecorder] = None) -> Tensor:
     """ModifiedUnet2DLevel5.forward (models/fpn/unets2D.py:172-213) / ModifiedUnet2D.forward (:108-144)."""
-    P = prefix + '.'
+    P = prefix + '.' if prefix else ''
     n2d = 5 if level5 else 4
     f2d, x = [], img
     for l in range(1, n2d + 1):
@@ -509,7 +515,7 @@ def make_state_dict(seed: int = 1234, dtype=torch.float32, n_classes: int = 1, p
     sd: StateDict = {}
     order: List[str] = []
     C = CHANNELS
-    P = prefix + '.'
+    P = prefix + '.' if prefix else ''
     rr = randomize_running
     for l in range(5):                                                     # conv1..5
         cin = 1 if l == 0 else C[l - 1]
@@ -537,6 +543,78 @@ def make_state_dict(seed: int = 1234, dtype=torch.float32, n_classes: int = 1, p
     _add_convx(sd, order, f'{P}conv5_2d.0', C[3], C[4], [(1, 3)] * 2, True, seed, dtype, rr)   # registered last
     _add_convx(sd, order, f'{P}conv5_2d.1', C[4], C[4], [(1, 3), (1, 3), (3, 1)], False, seed, dtype, rr)
     return {k: sd[k] for k in order}
+
+
+def fill_like(template: StateDict, seed: int = 1234, dtype=torch.float32, randomize_running: bool = False) -> StateDict:
+    """Deterministic weights for ANY state_dict of the model family (other wirings, directly constructed bodies): same
+    per-key generators as ``make_state_dict`` (``fill_like(make_state_dict(s), s) == make_state_dict(s)``, tested), keyed
+    on the names and shapes of ``template``: >=4-D ``weight`` = conv (xavier normal, weight_init.py:19,25), a
+    ``weight`` with a sibling ``running_mean`` = BatchNorm, other 1-D tensors = conv bias."""
+    sd: StateDict = {}
+    order: List[str] = []
+    for key, v in template.items():
+        if key in sd:
+            continue
+        if key.endswith('.weight') and (key[:-7] + '.running_mean') in template:
+            _add_bn(sd, order, key[:-7], v.numel(), seed, dtype, randomize_running)
+        elif v.dim() >= 4:
+            _add_conv(sd, order, key, tuple(v.shape), seed, dtype)
+        elif v.is_floating_point():
+            g = torch.Generator().manual_seed(_key_seed(seed, key))
+            sd[key] = (0.1 * torch.randn(tuple(v.shape), generator=g)).to(dtype)
+            order.append(key)
+        else:
+            raise KeyError(f'fill_like: unexpected entry {key}')
+    assert list(template.keys()) == [k for k in template if k in sd]
+    return {k: sd[k] for k in template}
+
+
+def wiring_forward(case: dict, sd: StateDict, batch: Dict[str, Tensor], train: bool = True) -> Tensor:
+    """Functional restatement of the other registered wirings / directly constructed bodies, keyed by the case table of
+    ``tests/golden/wiring_cases.py``: FPN / FPNRegression (fusion_nets.py:29-50), FPNClassification (:53-77),
+    FPNHybridFusionRegression (:125-127), FPN2D (:131-147), FPNLateFusion(+Regression) (:150-222), and the bodies
+    ModifiedUnet3D2D (fusion3D2D.py:380-469, feature_fusion 'add' :969-1039), ModifiedUnet3D(original=True)
+    (unets3D.py:441-485) and ModifiedUnet2D (unets2D.py:108-144)."""
+    oct = batch['image'].permute(0, 1, 2, 4, 3)
+    slo = batch['slo'][:, :, :, 0, :]
+    crop = case.get('crop', 'oct')
+    interp = '2d' if 'relative_2d' in crop else None
+    if 'max' in crop and interp is not None:
+        interp += '_max'
+    if case['kind'] == 'body':
+        kw = case['kwargs']
+        if case['cls'] in ('ModifiedUnet3D2D', 'ModifiedUnet3D2DLevel5'):
+            return fusion_body_forward(sd, oct, slo, kw.get('interpolate'), train, prefix='',
+                                       level5=case['cls'].endswith('Level5'), feature_fusion=kw.get('feature_fusion', 'concat'))
+        if case['cls'] == 'ModifiedUnet3D':
+            return unet3d_body_forward(sd, oct, train, prefix='', original=kw.get('original', False))
+        return unet2d_body_forward(sd, slo, train, prefix='', level5=case['cls'].endswith('Level5'),
+                                   output_features=kw.get('output_features', False))
+    name = case['name']
+    if name in ('FPN', 'FPNRegression'):
+        seg = unet3d_body_forward(sd, oct, train).permute(0, 1, 2, 4, 3)
+        return torch.sigmoid(seg) if name == 'FPN' else seg
+    if name == 'FPNClassification':
+        feat = unet3d_body_forward(sd, oct, train, classification=True)
+        pred = F.conv3d(feat, sd['one_one.weight']).mean(dim=(2, 3, 4))        # AdaptiveAvgPool3d((1,1,1)) + squeezes
+        return torch.softmax(pred, dim=-1)
+    if name == 'FPNHybridFusionRegression':
+        return fpn_hybrid_fusion_forward(sd, batch, crop, 'slo', train, sigmoid=False)['prediction']
+    if name == 'FPN2D':
+        seg = torch.sigmoid(unet2d_body_forward(sd, slo, train).permute(0, 1, 2, 4, 3))
+        if seg.shape != batch['mask'].shape:
+            seg = F.interpolate(seg, size=batch['mask'].shape[2:], mode='trilinear')
+        return seg
+    if name in ('FPNLateFusion', 'FPNLateFusionRegression'):
+        a = unet3d_body_forward(sd, oct, train, prefix='resensnet3d', use_1x1=False).permute(0, 1, 2, 4, 3)
+        b = unet2d_body_forward(sd, slo, train, prefix='resensnet2d', output_features=True).permute(0, 1, 2, 4, 3)
+        if interp == '2d':
+            b = F.interpolate(b, size=a.shape[2:], mode='trilinear')
+        elif interp == '2d_max':
+            b = F.adaptive_max_pool3d(b, output_size=a.shape[2:])
+        seg = F.conv3d(torch.cat([a, b], 1), sd['fusion_module.weight'], sd['fusion_module.bias'])
+        return torch.sigmoid(seg) if name == 'FPNLateFusion' else seg
+    raise KeyError(name)
 
 
 def param_keys(sd: StateDict) -> List[str]:

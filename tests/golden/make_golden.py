@@ -3,7 +3,8 @@
 Runs ONLY in the build container (needs ``/root/reference``, read-only, imported unmodified with
 the recipe of SURVEY.md section 8c).  The GPU box never runs this; it reads the committed ``.npz``.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # fusion_*.npz, index_ops.npz, weight_init.npz
+    python tests/golden/make_golden.py wirings    # wiring_<id>.npz (other factory entries / direct bodies)
 
 Fixtures written next to this file:
   fusion_<crop>.npz   FPNHybridFusion fwd+bwd on a tiny batch with weights from
@@ -12,6 +13,9 @@ Fixtures written next to this file:
                       tensors, (sum, l2) of every gradient, BN running-stat updates of a few layers.
   index_ops.npz       MaxPool3d / adaptive_max_pool3d argmax tables and Upsample_Custom3d_nearest
                       index tables from torch / the reference module, incl. ties and NaN.
+  wiring_<id>.npz     the other seven factory entries and the directly constructed bodies (4-level, 'add' fusion,
+                      original=True) of tests/golden/wiring_cases.py: output, loss, every gradient's (sum, l2),
+                      small gradients in full, BN running-stat checksums.
   weight_init.npz     per-tensor (sum, abs-sum) after ``torch.manual_seed(1234)`` + construction +
                       ``weight_init`` (train.py:42,53-56) -- pins the mirror's RNG consumption order.
 """
@@ -40,11 +44,26 @@ def import_reference(crop='relative_2d_max', modality='slo'):
     return cfg.config, factory_classes, loss, weight_init
 
 
+def make_wirings(cfg, ref_loss, O):
+    """wiring_<id>.npz: every case of tests/golden/wiring_cases.py run on the unmodified reference in fp64."""
+    sys.path.insert(0, HERE)
+    import wiring_cases as WC
+    for case in WC.CASES:
+        res = WC.run(case, cfg, ref_loss, O, device='cpu', dtype=torch.float64)
+        fx = WC.to_fixture(res)
+        np.savez_compressed(os.path.join(HERE, f"wiring_{case['id']}.npz"), **fx)
+        print(case['id'], 'loss', fx['loss'], 'out', fx['out'].shape, 'params', len(fx['names']),
+              'without grad', int((fx['grad_l2'] < 0).sum()))
+
+
 def main():
     torch.set_num_threads(8)
+    mode = sys.argv[1] if len(sys.argv) > 1 else 'all'          # read before import_reference() rewrites sys.argv
     cfg, factory, ref_loss, ref_init = import_reference()
     sys.path.insert(0, REPO)
     from oracle import fusion_fpn_oracle as O
+    if mode == 'wirings':
+        return make_wirings(cfg, ref_loss, O)
 
     shapes = dict(B=2, S=8, H=64, W=32, S2=20, W2=48)          # small; S%4==0, W%16==0, H>=64
     for crop in ('relative_2d_max', 'relative_2d', 'oct'):

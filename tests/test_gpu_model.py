@@ -35,12 +35,20 @@ def _loss(mirror, batch, out):
     return crit(batch, out)[0]
 
 
-def _run(mirror, sd, batch, crop, train=True):
+def _run(mirror, sd, batch, crop, train=True, acts=None):
     model = mirror.build('FPNHybridFusion', crop).cuda()
     model.load_state_dict(sd, strict=True)
     model.train(train)
     cb = {k: v.cuda() for k, v in batch.items()}
+    hooks = []
+    if acts is not None:
+        import stagehooks
+        a, hooks = stagehooks.attach(model.resensnet)
     out = model(cb)
+    for h in hooks:
+        h.remove()
+    if acts is not None:
+        acts.update(a)
     return model, cb, out
 
 
@@ -50,9 +58,33 @@ def test_model_matches_golden_and_oracle_fp32(mirror, golden_dir, crop):
     B, S, H, W, S2, W2 = [int(v) for v in fx['shape']]
     sd = O.make_state_dict(seed=int(fx['seed_weights']))
     batch = O.synthetic_batch(B, S, H, W, S2, W2, seed=int(fx['seed_batch']))
-    model, cb, out = _run(mirror, sd, batch, crop)
+    acts = {}
+    model, cb, out = _run(mirror, sd, batch, crop, acts=acts)
     pred = out['prediction']
     assert tuple(pred.shape) == (B, 1, S, 1, W) and pred.dtype == torch.float32
+    # per-stage activation checksums of the reference (sum, abs-sum, square-sum, shape): SURVEY.md App. D.2
+    n_checked = 0
+    for k in fx.files:
+        if not k.startswith('act/'):
+            continue
+        name, ref = k[4:], fx[k]
+        ours = {'zdimRed': 'proj', 'up_concat': 'up'}
+        key = name
+        for a, b in ours.items():
+            key = key.replace(a, b)
+        t = acts[key].double()
+        if name.startswith('zdimRed'):
+            # the depth mean is fused behind the projection: sum(mean) * depth == sum of the reference's pre-mean tensor (>= 0)
+            hrem = int(ref[-1])
+            assert list(t.shape) == [int(v) for v in ref[3:-1]] + [1]
+            assert abs(t.sum().item() * hrem - ref[0]) <= 1e-4 * abs(ref[1]), (name, t.sum().item() * hrem, ref[0])
+        else:
+            assert list(t.shape) == [int(v) for v in ref[3:]], (name, tuple(t.shape))
+            assert abs(t.sum().item() - ref[0]) <= 1e-4 * ref[1], (name, t.sum().item(), ref[0])
+            assert abs(t.abs().sum().item() - ref[1]) <= 1e-4 * ref[1], name
+            assert abs((t ** 2).sum().item() - ref[2]) <= 2e-4 * ref[2], name
+        n_checked += 1
+    assert n_checked == 20
     # golden = the unmodified reference in fp64
     assert rel(pred.cpu(), torch.from_numpy(fx['prediction'])) <= 1e-4
     loss = _loss(mirror, cb, out)
