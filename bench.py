@@ -27,11 +27,46 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'multimodal-fusion-fpn_b200'))
+PKG = os.path.join(ROOT, 'multimodal-fusion-fpn_b200')       # put on sys.path by the GPU arm only: the reference arm must import
+                                                             # oracle/_ref's `models` / `config`, never this repository's
 
-WORKLOAD = dict(name='C2: FPNHybridFusion GA segmentation, batch 8/GPU, image 1x32x128x128, slo 320x128, '
-                     'crop relative_2d_max', B=8, S=32, H=128, W=128, S2=320, W2=128)
+# BASELINE.json configs.  model_elems = conv-boundary traffic model, elements read + written per sample, forward.
+WORKLOADS = {
+    'C1': dict(name='C1: FPNHybridFusion, batch 1, image 1x64x128x128, slo 128x128, crop relative_2d_max', B=1, S=64, H=128, W=128,
+               S2=128, W2=128, model_elems=664.8e6, scaling='weak'),
+    'C2': dict(name='C2: FPNHybridFusion GA segmentation, batch 8/GPU, image 1x32x128x128, slo 320x128, crop relative_2d_max',
+               B=8, S=32, H=128, W=128, S2=320, W2=128, model_elems=367.2e6, scaling='weak'),
+    'C3': dict(name='C3: Level5 fusion FPN at full B-scan depth, batch 8/GPU, image 1x32x496x128, slo 320x128, crop relative_2d_max',
+               B=8, S=32, H=496, W=128, S2=320, W2=128, model_elems=1296.8e6, scaling='weak'),
+    'C4': dict(name='C4: vessel segmentation shapes, batch 16/GPU, image 1x32x128x128, slo 320x128, crop relative_2d_max',
+               B=16, S=32, H=128, W=128, S2=320, W2=128, model_elems=367.2e6, scaling='weak'),
+    'C5': dict(name='C5: data-parallel sweep, GLOBAL batch 64 split over the GPUs, image 1x32x128x128, slo 320x128, '
+                    'crop relative_2d_max', B=64, S=32, H=128, W=128, S2=320, W2=128, model_elems=367.2e6, scaling='strong'),
+}
+WORKLOAD = dict(WORKLOADS['C2'])
 METRIC, UNIT = 'fwd+bwd samples/sec', 'samples/s'
+
+
+def select_workload(name, world):
+    w = dict(WORKLOADS[name])
+    w['id'] = name
+    if name == 'C5':
+        assert 64 % world == 0, 'C5 splits a global batch of 64'
+        w['B'] = 64 // world
+    WORKLOAD.clear()
+    WORKLOAD.update(w)
+    return WORKLOAD
+
+
+def cpu_model():
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.startswith('model name'):
+                    return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
 
 
 def peaks():
@@ -103,41 +138,125 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_rate(steps, warmup, threads=None):
-    """Oracle port (oracle/fusion_fpn_oracle.py: torch CPU ops restating the reference, fp32) on the host cores.
-    Each step = forward + Mix loss + backward of ONE sample of the workload shape."""
-    import torch
-    from oracle import fusion_fpn_oracle as O
+def _host_threads():
     try:
-        avail = len(os.sched_getaffinity(0))
+        return len(os.sched_getaffinity(0))
     except Exception:
-        avail = os.cpu_count()
-    threads = threads or avail
+        return os.cpu_count() or 1
+
+
+REF_DIR = os.path.join(ROOT, 'oracle', '_ref')
+
+
+def _reference_step_fn(batch_size):
+    """-> (kind, step()).  'reference' = the UNMODIFIED reference modules copied to oracle/_ref by oracle/make_ref.py
+    (FPNHybridFusion + weight_init + Mix loss, SURVEY.md section 8c import recipe); 'port' = the oracle restatement, only when
+    that copy is missing.  One step = forward + loss + backward of ``batch_size`` samples of the workload shape, fp32, all host
+    threads.  Nothing of this repository's product is imported here."""
+    import torch
+    threads = _host_threads()
     torch.set_num_threads(threads)
     w = WORKLOAD
+    from oracle import fusion_fpn_oracle as O            # synthetic batch generator (and the fallback port)
+    batch = O.synthetic_batch(batch_size, w['S'], w['H'], w['W'], w['S2'], w['W2'], seed=1234)
+    if os.path.isdir(os.path.join(REF_DIR, 'models')):
+        saved_cwd, saved_argv = os.getcwd(), sys.argv
+        os.chdir(REF_DIR)                                  # the .ini is read cwd-relative (fusion_nets.py:24-26)
+        sys.path[:] = [q for q in sys.path if os.path.abspath(q or '.') != PKG]
+        sys.path.insert(0, REF_DIR)
+        sys.argv = ['x', '--training-dataset', 'hrf_fusion', '--model', 'FPNHybridFusion', '--fusion-modality', 'slo',
+                    '--crop', 'relative_2d_max']
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                import config as _cfg                      # noqa: F401
+                from models.fusion_nets import factory_classes
+                from common import loss as rloss, weight_init as rinit
+                torch.manual_seed(1234)                    # train.py:42
+                model = factory_classes['FPNHybridFusion']()
+                model.apply(rinit.weight_init)             # train.py:56
+            import models.fusion_nets as _fn
+            assert os.path.abspath(_fn.__file__).startswith(REF_DIR), 'the reference arm must run the reference modules'
+        finally:
+            sys.argv = saved_argv
+            os.chdir(saved_cwd)
+        model.train()
+        crit = rloss.Mix({'Dice': rloss.Dice_loss_jointv2('prediction', 'mask'), 'BCE': rloss.BCE_Lossv2('prediction', 'mask')})
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            loss, _ = crit(batch, model(batch))
+            loss.backward()
+            return float(loss)
+        return 'reference', step, threads
     sd = O.make_state_dict(seed=1234)
-    batch = O.synthetic_batch(1, w['S'], w['H'], w['W'], w['S2'], w['W2'], seed=1234)
+
+    def step():
+        return float(O.loss_and_grads(sd, batch)[0])
+    return 'port', step, threads
+
+
+def cpu_reference_rate(steps, warmup, batch_size):
+    """Times the reference arm: -> (samples/s, seconds per step, threads, kind)."""
+    kind, step, threads = _reference_step_fn(batch_size)
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.loss_and_grads(sd, batch)
+        step()
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
-    return 1.0 / sec, sec, threads
+    return batch_size / sec, sec, threads, kind
+
+
+def _reference_batch():
+    """The GPU arm's per-step batch when the host has the memory for it (stock PyTorch keeps ~2.6 GB of activations per C2
+    sample), else the largest power-of-two batch that fits."""
+    w = WORKLOAD
+    per_sample_gb = 2 * 4 * w['model_elems'] * 2.0 / 1e9 / 2          # ~2x the traffic model's elements stay alive, fp32
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available / 1e9
+    except Exception:
+        avail = 32.0
+    b = w['B']
+    while b > 1 and b * per_sample_gb > 0.5 * avail:
+        b //= 2
+    return b
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 8), min(args.warmup, 2)
-    rate, sec, threads = cpu_reference_rate(steps, warmup)
-    sample = (f'oracle port of the reference (torch {__import__("torch").__version__} CPU ops, fp32), {threads} host threads; '
-              f'each step = fwd+loss+bwd of 1 sample of the C2 shape; {steps} timed after {warmup} warm-up')
+    w = WORKLOAD
+    bsz = _reference_batch()
+    steps, warmup = args.steps, args.warmup
+    # bounded: the whole run must end within a few minutes on the host cores -> probe one step, then cut the step count if needed
+    kind, step, threads = _reference_step_fn(bsz)
+    t0 = time.perf_counter()
+    step()
+    probe = time.perf_counter() - t0
+    budget = 240.0
+    if probe * (steps + warmup) > budget:
+        warmup = min(warmup, 1)
+        steps = max(2, min(steps, int(budget / probe) - warmup))
+    ts = []
+    for i in range(max(warmup - 1, 0) + steps):                        # the probe was the first warm-up step
+        t0 = time.perf_counter()
+        step()
+        if i >= max(warmup - 1, 0):
+            ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    rate = bsz / sec
+    import torch
+    what = ('the unmodified reference (oracle/_ref: models/fusion_nets.py FPNHybridFusion + common/loss.py Mix, weight_init, seed 1234)'
+            if kind == 'reference' else 'oracle port of the reference (oracle/_ref missing)')
+    sample = (f'{what}, torch {torch.__version__} CPU fp32, {threads} host threads on {cpu_model()}; each step = fwd+loss+bwd of '
+              f'{bsz} sample(s) of the {w["id"]} shape; {steps} timed after {warmup} warm-up')
     line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
-            'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD['name'], 'per_step_samples': 1},
-            'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': w['scaling'], 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': w['name'], 'per_gpu_batch': w['B'], 'per_step_samples': bsz, 'cpu_model': cpu_model()},
+            'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
             'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
@@ -215,6 +334,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='C2', choices=sorted(WORKLOADS), help='BASELINE.json workload (default C2 = the metric\'s)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -223,6 +343,7 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    select_workload(args.config, world)
     if args.impl == 'reference':
         run_reference(args, rank, world)
         return
@@ -235,6 +356,7 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    sys.path.insert(0, PKG)
     from __graft_entry__ import import_mirror
     cfg, fusion_nets, loss_mod, weight_init = import_mirror()
     import ffpn
@@ -318,7 +440,7 @@ def main():
     value, e2e_value = samples / (ms * 1e-3), samples / (ms_e2e * 1e-3)
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': w['scaling'], 'vs_baseline': None,
             'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': w['name'], 'per_gpu_batch': w['B'], 'global_batch': w['B'] * world,
                        'parallelism': f'dp{world}', 'cuda_graph': use_graph,
@@ -345,14 +467,18 @@ def main():
                                 'algorithmic_bytes_per_launch': top['bytes'], 'sec_per_launch': top['sec']}
             line['kernels'] = [{k: r[k] for k in ('kernel', 'gbs', 'frac', 'sec', 'bytes')} for r in ks]
             # whole-step roofline: conv-boundary traffic model of SURVEY.md section 8d (bf16, fwd+bwd = 3 x fwd)
-            step_bytes = 367.2e6 * 2 * 3 * w['B']
+            step_bytes = w['model_elems'] * 2 * 3 * w['B']
             line['step_roofline'] = {'model_bytes_per_step': step_bytes, 'achieved_gbs': step_bytes / (ms / args.steps * 1e-3) / 1e9,
                                      'frac': step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}
         if world == 1 and not args.no_cpu_baseline:
-            rate, sec, threads = cpu_reference_rate(3, 1)
-            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                    'sample': 'oracle port (torch CPU fp32), fwd+loss+bwd of 1 sample of the C2 shape, '
-                                              '3 timed after 1 warm-up'}
+            trainer.close()
+            del trainer, model
+            torch.cuda.empty_cache()
+            rate, sec, threads, kind = cpu_reference_rate(3, 1, 1)
+            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': kind, 'cpu_model': cpu_model(),
+                                    'sample': ('unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port')
+                                    + f' on torch CPU fp32, fwd+loss+bwd of 1 sample of the {w["id"]} shape per step, 3 timed after '
+                                      '1 warm-up; `bench.py --impl reference` times it at the full batch'}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -57,6 +57,13 @@ void ffpn_destroy(ffpn_ctx* ctx);
 const char* ffpn_last_error(ffpn_ctx* ctx);
 /* number of kernel launches issued through this ctx since creation (bench.py's gpu_launches) */
 int64_t ffpn_launch_count(ffpn_ctx* ctx);
+/* conv calls per kernel family since creation: out4 = {warp-specialised tcgen05, Cin==1 stem, first-generation tcgen05,
+ * CUDA-core}.  The dispatch is not silent: bench.py prints the per-step counts and refuses a bf16 run whose convs left the
+ * tcgen05 / stem kernels. */
+int ffpn_route_counts(ffpn_ctx* ctx, int64_t* out4);
+/* bit 0: built with -DFFPN_DEBUG (the result-invalidating ablation / trace switches FFPN_TC_DEBUG, FFPN_WS_TRACE are
+ * compiled in).  The release library returns 0 and ignores those variables. */
+int ffpn_build_info(void);
 /* bytes of scratch a conv call of this geometry may use (packed bf16 weights for the tcgen05 path) */
 size_t ffpn_conv_workspace_bytes(const ffpn_conv_desc* d);
 
@@ -195,6 +202,11 @@ int ffpn_weight_arena_begin(ffpn_ctx* ctx, void* arena, size_t bytes);
 int ffpn_weight_arena_seal(ffpn_ctx* ctx);
 int ffpn_weight_arena_pack(ffpn_ctx* ctx, void* stream);
 int ffpn_weight_arena_end(ffpn_ctx* ctx);
+/* Images are only recorded into / taken from the arena while lookups are enabled (begin enables them).  The owner of the
+ * arena (FusionTrainer.forward_backward) enables them around its own forward+backward and disables them afterwards, so
+ * conv calls made by anyone else on the same device (an eval forward, another model, weights loaded behind the
+ * trainer's back) pack their image from the CURRENT fp32 weights and can never read a stale one. */
+int ffpn_weight_arena_enable(ffpn_ctx* ctx, int on);
 
 #ifdef __cplusplus
 }

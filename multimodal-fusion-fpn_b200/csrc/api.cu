@@ -63,6 +63,8 @@ extern "C" int ffpn_create(ffpn_ctx** out, int device) {
   c->launches = 0;
   c->err[0] = 0;
   c->arena_state = 0; c->arena = nullptr; c->arena_bytes = c->arena_used = 0; c->njobs = 0; c->arena_elems = 0; c->d_jobs = nullptr; c->d_counter = nullptr;
+  c->fin_slot = 0; c->arena_lookup = 0; c->attr_mask = 0;
+  for (int i = 0; i < 4; i++) c->routes[i] = 0;
   *out = c;
   return 0;
 }
@@ -74,6 +76,18 @@ extern "C" void ffpn_destroy(ffpn_ctx* ctx) {
 }
 extern "C" const char* ffpn_last_error(ffpn_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 extern "C" int64_t ffpn_launch_count(ffpn_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int ffpn_route_counts(ffpn_ctx* ctx, int64_t* out4) {
+  if (!ctx || !out4) return 1;
+  for (int i = 0; i < 4; i++) out4[i] = ctx->routes[i];
+  return 0;
+}
+extern "C" int ffpn_build_info(void) {
+#ifdef FFPN_DEBUG
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 extern "C" size_t ffpn_conv_workspace_bytes(const ffpn_conv_desc* d) {
   if (!d) return 0;
@@ -88,12 +102,16 @@ extern "C" int ffpn_conv_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void*
   if (check_desc(ctx, d, "conv_fwd")) return 1;
   if ((in_scale == nullptr) != (in_shift == nullptr)) FFPN_FAIL(ctx, "conv_fwd: in_scale/in_shift must both be set or both null");
   if (stat_partial != nullptr && stat_rows == nullptr) FFPN_FAIL(ctx, "conv_fwd: stat_rows is null");
-  if (d->impl == 0 && in_scale == nullptr && ffpn_stem_supported(d))
+  if (d->impl == 0 && in_scale == nullptr && ffpn_stem_supported(d)) {
+    ctx->routes[FFPN_ROUTE_STEM]++;
     return ffpn_stem_fwd(ctx, d, x, w, y, stat_partial, stat_rows, (cudaStream_t)stream);
+  }
   const bool tc_ok = ffpn_tc_fwd_supported(d);
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_fwd: tcgen05 kernel does not support this geometry");
   if (tc_ok && d->impl != 1)
     return ffpn_conv_fwd_tc(ctx, d, false, x, in_scale, in_shift, in_relu, w, nullptr, y, stat_partial, stat_rows, ws, ws_bytes, (cudaStream_t)stream);
+  ctx->routes[FFPN_ROUTE_SIMT]++;
+  if (d->dtype == FFPN_BF16) ffpn_log_route("conv_fwd -> CUDA-core kernel", d);
   return ffpn_conv_fwd_simt(ctx, d, x, in_scale, in_shift, in_relu, w, y, stat_partial, stat_rows, (cudaStream_t)stream);
 }
 
@@ -123,6 +141,8 @@ extern "C" int ffpn_conv_dgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const voi
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_dgrad: tcgen05 kernel does not support this geometry");
   if (tc_ok && d->impl != 1)
     return ffpn_conv_fwd_tc(ctx, d, true, dy, nullptr, nullptr, 0, w, addend, dx, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+  ctx->routes[FFPN_ROUTE_SIMT]++;
+  if (d->dtype == FFPN_BF16) ffpn_log_route("conv_dgrad -> CUDA-core kernel", d);
   return ffpn_conv_dgrad_simt(ctx, d, dy, w, addend, dx, (cudaStream_t)stream);
 }
 
@@ -131,14 +151,15 @@ extern "C" int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const voi
                                void* stream) {
   if (check_desc(ctx, d, "conv_wgrad")) return 1;
   if ((in_scale == nullptr) != (in_shift == nullptr)) FFPN_FAIL(ctx, "conv_wgrad: in_scale/in_shift must both be set or both null");
-  if (d->impl == 0 && in_scale == nullptr && ffpn_stem_supported(d))
+  if (d->impl == 0 && in_scale == nullptr && ffpn_stem_supported(d)) {
+    ctx->routes[FFPN_ROUTE_STEM]++;
     return ffpn_stem_wgrad(ctx, d, x, dy, dw, ws, ws_bytes, (cudaStream_t)stream);
+  }
   const bool tc_ok = ffpn_tc_wgrad_supported(d);
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_wgrad: tcgen05 kernel does not support this geometry");
   if (tc_ok && d->impl != 1)
     return ffpn_conv_wgrad_tc(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, ws, ws_bytes, (cudaStream_t)stream);
-  if (d->dtype == FFPN_BF16 && getenv("FFPN_VERBOSE_FALLBACK"))
-    fprintf(stderr, "conv_wgrad -> CUDA-core kernel: B %lld S %lld W %lld H %lld Cin %d Cout %d k %dx%dx%d s %dx%dx%d p %dx%dx%d\n", (long long)d->B,
-            (long long)d->S, (long long)d->W, (long long)d->H, d->Cin, d->Cout, d->kS, d->kW, d->kH, d->sS, d->sW, d->sH, d->pS, d->pW, d->pH);
+  if (d->dtype == FFPN_BF16) ffpn_log_route("conv_wgrad -> CUDA-core kernel", d);
+  ctx->routes[FFPN_ROUTE_SIMT]++;
   return ffpn_conv_wgrad_simt(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, (cudaStream_t)stream);
 }

@@ -1457,10 +1457,10 @@ int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
                        int in_relu, const void* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
   {
     const int r = ffpn_conv_wgrad_ws(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, ws, ws_bytes, st);
-    if (r >= 0) return r;                                 // handled (or failed) by the warp-specialised kernel
+    if (r >= 0) { ctx->routes[FFPN_ROUTE_WS]++; return r; }   // handled (or failed) by the warp-specialised kernel
   }
   ffpn_log_route("conv_wgrad -> first-generation tcgen05 kernel", d);
-  static bool attr_tma = false;
+  ctx->routes[FFPN_ROUTE_GEN1]++;
   if (!(in_scale != nullptr && !in_relu)) {
     WgTmaPlan t = make_wgrad_tma_plan(d, ctx->num_sms);
     CUtensorMap tmx, tmy;
@@ -1468,11 +1468,11 @@ int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
         encode_map4(&tmy, dy, t.ydims, t.ystr, t.ybox, false)) {
       WgTmaParams& q = t.p;
       q.sc = in_scale; q.sh = in_shift; q.dw = dw; q.has_aff = in_scale != nullptr;
-      { const char* e = getenv("FFPN_TC_DEBUG"); q.dbg = e ? atoi(e) : 0; }
-      if (!attr_tma) {
+      q.dbg = ffpn_debug_env("FFPN_TC_DEBUG");
+      if (!(ctx->attr_mask & FFPN_ATTR_WGRAD_TMA)) {
         cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tma: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-        attr_tma = true;
+        ctx->attr_mask |= FFPN_ATTR_WGRAD_TMA;
       }
       q.dw_slice = ws ? wgrad_slices(d, t.grid.x, ws_bytes) : 0;
       if (q.dw_slice) {
@@ -1489,11 +1489,10 @@ int ffpn_conv_wgrad_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
   WgParams& p = w.p;
   p.x = (const bf16*)x; p.dy = (const bf16*)dy; p.sc = in_scale; p.sh = in_shift; p.dw = dw;
   p.relu = in_relu; p.has_aff = in_scale != nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->attr_mask & FFPN_ATTR_WGRAD_TC)) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-    attr_set = true;
+    ctx->attr_mask |= FFPN_ATTR_WGRAD_TC;
   }
   p.dw_slice = ws ? wgrad_slices(d, w.grid.x, ws_bytes) : 0;
   if (p.dw_slice) {
@@ -1562,7 +1561,7 @@ const void* ffpn_tc_pack_weights(ffpn_ctx* ctx, const float* w, void* ws, const 
   ffpn_pack_job j;
   j.w = w; j.total = total; j.Cout = d->Cout; j.Cin = d->Cin; j.ntaps = ntaps; j.Kc = p.Cin; j.Nc = p.Cout; j.Npad = p.Npad; j.KG = KG;
   j.nchunks = nchunks; j.mode = p.packmode; j.sH = d->sH; j.pH = d->pH; j.kH = d->kH; j.tmin = -p.pX;
-  if (ctx->arena_state == 2) {
+  if (ctx->arena_state == 2 && ctx->arena_lookup) {
     for (int i = 0; i < ctx->njobs; i++) {
       const ffpn_pack_job& q = ctx->jobs[i];
       if (q.w == w && q.mode == j.mode && q.KG == KG && q.Npad == j.Npad && q.nchunks == nchunks && q.total == total && q.tmin == j.tmin &&
@@ -1571,7 +1570,7 @@ const void* ffpn_tc_pack_weights(ffpn_ctx* ctx, const float* w, void* ws, const 
     }
   }
   void* out = ws;
-  if (ctx->arena_state == 1 && ctx->njobs < FFPN_MAX_PACK_JOBS && ctx->arena_used + (size_t)total * 2 + 1024 <= ctx->arena_bytes) {
+  if (ctx->arena_state == 1 && ctx->arena_lookup && ctx->njobs < FFPN_MAX_PACK_JOBS && ctx->arena_used + (size_t)total * 2 + 1024 <= ctx->arena_bytes) {
     j.dst = (long long)(ctx->arena_used / 2);
     j.prefix = ctx->arena_elems;
     ctx->jobs[ctx->njobs++] = j;
@@ -1592,6 +1591,12 @@ extern "C" int ffpn_weight_arena_begin(ffpn_ctx* ctx, void* arena, size_t bytes)
   if (arena == nullptr || bytes < (1u << 20) || ((uintptr_t)arena & 1023)) FFPN_FAIL(ctx, "weight_arena_begin: need a 1 KiB-aligned buffer of >= 1 MiB");
   ctx->arena = (char*)arena; ctx->arena_bytes = bytes; ctx->arena_used = 0; ctx->njobs = 0; ctx->arena_elems = 0;
   ctx->arena_state = 1;
+  ctx->arena_lookup = 1;
+  return 0;
+}
+extern "C" int ffpn_weight_arena_enable(ffpn_ctx* ctx, int on) {
+  if (!ctx) return 1;
+  ctx->arena_lookup = on ? 1 : 0;
   return 0;
 }
 extern "C" int ffpn_weight_arena_seal(ffpn_ctx* ctx) {
@@ -1616,6 +1621,7 @@ extern "C" int ffpn_weight_arena_pack(ffpn_ctx* ctx, void* stream) {
 extern "C" int ffpn_weight_arena_end(ffpn_ctx* ctx) {
   if (!ctx) return 1;
   ctx->arena_state = 0; ctx->njobs = 0; ctx->arena = nullptr; ctx->arena_bytes = ctx->arena_used = 0; ctx->arena_elems = 0;
+  ctx->arena_lookup = 0;
   return 0;
 }
 
@@ -1627,9 +1633,10 @@ int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
                      int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
   {
     const int r = ffpn_conv_fwd_ws(ctx, d, transposed, x, in_scale, in_shift, in_relu, w, addend, y, stat_partial, stat_rows, ws, ws_bytes, st);
-    if (r >= 0) return r;                                 // handled (or failed) by the warp-specialised kernel
+    if (r >= 0) { ctx->routes[FFPN_ROUTE_WS]++; return r; }   // handled (or failed) by the warp-specialised kernel
   }
   ffpn_log_route(transposed ? "conv_dgrad -> first-generation tcgen05 kernel" : "conv_fwd -> first-generation tcgen05 kernel", d);
+  ctx->routes[FFPN_ROUTE_GEN1]++;
   Plan pl = ffpn_tc_make_plan(d, transposed, ctx->num_sms);
   if (!pl.ok) FFPN_FAIL(ctx, "conv_tc: geometry not supported");
   TcParams& p = pl.p;
@@ -1642,14 +1649,13 @@ int ffpn_conv_fwd_tc(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
   p.x = (const bf16*)x; p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)wimg;
   p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->attr_mask & FFPN_ATTR_TC)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-    attr_set = true;
+    ctx->attr_mask |= FFPN_ATTR_TC;
   }
-  { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg = ffpn_debug_env("FFPN_TC_DEBUG");
   const dim3 grid(pl.grid, pl.nchunks);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));

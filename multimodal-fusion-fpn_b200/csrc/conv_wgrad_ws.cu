@@ -551,12 +551,11 @@ int ffpn_conv_wgrad_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
   p.sc = in_scale; p.sh = in_shift; p.has_aff = in_scale != nullptr; p.part = (float*)ws;
   p.pair_cin = pair ? d->Cin : 0;
   { const char* e = getenv("FFPN_PDL_EARLY"); p.pdl_early = (e && atoi(e) == 0) ? 0 : 1; }
-  { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
-  static bool attr_set = false;
-  if (!attr_set) {
+  p.dbg = ffpn_debug_env("FFPN_TC_DEBUG");
+  if (!(ctx->attr_mask & FFPN_ATTR_WGRAD_WS)) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_wgrad_ws: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-    attr_set = true;
+    ctx->attr_mask |= FFPN_ATTR_WGRAD_WS;
   }
   {
     static int verbose = -1;

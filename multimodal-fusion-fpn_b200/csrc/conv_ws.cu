@@ -784,29 +784,31 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     if (packed_now) FFPN_CHECK_LAUNCH(ctx, "pack_weights");
   }
   p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)wimg; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
-  { const char* e = getenv("FFPN_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg = ffpn_debug_env("FFPN_TC_DEBUG");
   p.fin_on = 0;
   if (fin != nullptr) {
     if (stat_partial == nullptr) return -1;
     if (ctx->d_counter == nullptr) {
-      if (cudaMalloc(&ctx->d_counter, 256) != cudaSuccess || cudaMemset(ctx->d_counter, 0, 256) != cudaSuccess)
-        FFPN_FAIL(ctx, "conv_ws: cannot allocate the arrival counter");
+      if (cudaMalloc(&ctx->d_counter, FFPN_FIN_SLOTS * sizeof(unsigned)) != cudaSuccess ||
+          cudaMemset(ctx->d_counter, 0, FFPN_FIN_SLOTS * sizeof(unsigned)) != cudaSuccess)
+        FFPN_FAIL(ctx, "conv_ws: cannot allocate the arrival counters");
     }
-    p.fin_on = 1; p.fin = *fin; p.fin_counter = ctx->d_counter;
+    // one counter word per launch in flight: convs running concurrently on branch / wgrad side streams must not share one
+    p.fin_on = 1; p.fin = *fin; p.fin_counter = ctx->d_counter + ctx->fin_slot;
+    ctx->fin_slot = (ctx->fin_slot + 1) % FFPN_FIN_SLOTS;
   }
   p.aff_mod = ((pair || pair2) && !transposed) ? d->Cin : 0;
   { const char* e = getenv("FFPN_PDL_EARLY"); p.pdl_early = (e && atoi(e) == 0) ? 0 : 1; }
   p.pair2 = pair2 ? (transposed ? d->Cin : d->Cout) : 0;
   { const char* e = getenv("FFPN_WS_NT"); p.nt = (e && atoi(e) == 160) ? 160 : WS_NT; }
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->attr_mask & FFPN_ATTR_WS)) {                              // per device: the attribute belongs to the function ON the current device
     cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_ws: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-    attr_set = true;
+    ctx->attr_mask |= FFPN_ATTR_WS;
   }
   {
     static int verbose = -1;
@@ -818,7 +820,7 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
               pl.smem, p.tmem_cols, p.nbuf, pl.grid.x, pl.grid.y, p.NB * p.nD * p.nI);
   }
   static int trace_mode = -1;
-  if (trace_mode < 0) { const char* e = getenv("FFPN_WS_TRACE"); trace_mode = e ? atoi(e) : 0; }
+  if (trace_mode < 0) trace_mode = ffpn_debug_env("FFPN_WS_TRACE");
   p.trace = nullptr;
   if (trace_mode) {
     cudaMalloc(&p.trace, 64 * 16 * sizeof(long long));
@@ -865,5 +867,7 @@ int ffpn_conv_fwd_ws_bn(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, c
   ffpn_bn_fin fin;
   fin.count = count; fin.momentum = momentum; fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.running_mean = rmean;
   fin.running_var = rvar; fin.scale = scale; fin.shift = shift; fin.save_mean = smean; fin.save_invstd = sinvstd;
-  return conv_ws_launch(ctx, d, false, x, in_scale, in_shift, in_relu, w, nullptr, y, stat_partial, stat_rows, ws, ws_bytes, st, &fin);
+  const int r = conv_ws_launch(ctx, d, false, x, in_scale, in_shift, in_relu, w, nullptr, y, stat_partial, stat_rows, ws, ws_bytes, st, &fin);
+  if (r >= 0) ctx->routes[FFPN_ROUTE_WS]++;
+  return r;
 }

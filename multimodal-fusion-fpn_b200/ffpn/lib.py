@@ -7,7 +7,10 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libfusionfpn.so')
+# FFPN_LIB=debug loads the -DFFPN_DEBUG build (make DEBUG=1): only that build honours the result-invalidating
+# ablation switches; bench.py refuses to report numbers from it
+DEBUG_LIB = os.environ.get('FFPN_LIB', '') == 'debug'
+LIB_PATH = os.path.join(_HERE, 'libfusionfpn_dbg.so' if DEBUG_LIB else 'libfusionfpn.so')
 
 F32, BF16 = 0, 1
 STAT_ROWS = 1184
@@ -58,9 +61,12 @@ SIGNATURES = {
     'ffpn_weight_arena_seal': [],
     'ffpn_weight_arena_pack': [_P],
     'ffpn_weight_arena_end': [],
+    'ffpn_weight_arena_enable': [_I],
+    'ffpn_route_counts': [C.POINTER(C.c_int64)],
 }
 NO_CTX = {
     'ffpn_abi_version': ([], C.c_int),
+    'ffpn_build_info': ([], C.c_int),
     'ffpn_create': ([C.POINTER(C.c_void_p), _I], C.c_int),
     'ffpn_destroy': ([_P], None),
     'ffpn_last_error': ([_P], C.c_char_p),
@@ -124,7 +130,8 @@ def ctx(device_index: int):
     return h
 
 
-_SKIP = set(filter(None, os.environ.get('FFPN_TIMING_SKIP', '').split(',')))   # timing experiments only (results invalid)
+# timing experiments only (results invalid): honoured by the debug build alone
+_SKIP = set(filter(None, os.environ.get('FFPN_TIMING_SKIP', '').split(','))) if DEBUG_LIB else set()
 
 
 def call(name: str, device_index: int, *args):
@@ -139,6 +146,20 @@ def call(name: str, device_index: int, *args):
 
 def launch_count(device_index: int = 0) -> int:
     return int(load().ffpn_launch_count(ctx(device_index)))
+
+
+ROUTES = ('tcgen05_ws', 'stem', 'tcgen05_gen1', 'cuda_core')
+
+
+def route_counts(device_index: int = 0) -> dict:
+    """Conv calls per kernel family since the ctx was created (ffpn_route_counts)."""
+    out = (C.c_int64 * 4)()
+    call('ffpn_route_counts', device_index, out)
+    return dict(zip(ROUTES, [int(v) for v in out]))
+
+
+def is_debug_build() -> bool:
+    return bool(load().ffpn_build_info() & 1)
 
 
 def dtype_code(t: torch.dtype) -> int:

@@ -330,3 +330,7 @@ def weight_arena_pack(like: torch.Tensor):
 
 def weight_arena_end(device_index: int):
     lib.call('ffpn_weight_arena_end', device_index)
+
+
+def weight_arena_enable(device_index: int, on: bool):
+    lib.call('ffpn_weight_arena_enable', device_index, int(bool(on)))

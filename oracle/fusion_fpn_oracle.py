@@ -160,13 +160,44 @@ def batch_norm(x: Tensor, sd: StateDict, prefix: str, train: bool,
     return (x - mean.view(shape)) * (inv * w).view(shape) + b.view(shape)
 
 
+# ---- bf16-storage emulation -------------------------------------------------------------------------------------
+# The CUDA path stores activations (and the packed conv weights) as bf16 and accumulates in fp32.  ``bf16_storage()``
+# makes this oracle round at exactly the points where that path stores: the input images, every raw conv output (the
+# BatchNorm statistics are then taken from the rounded values), the BN+ReLU'd operand a conv stages, each block output,
+# the projection's depth mean, the resized 2-D feature; conv weights except the Cin == 1 stems (kept fp32 by the stem
+# kernels) and the head.  Rounding is straight-through for autograd (gradients are those of the rounded forward).
+# This is SURVEY.md App. D.1's "torch op fed the same bf16-rounded inputs" at model level: what is left between this
+# and the kernels is fp32 summation order (and the rounding ties it flips), not storage precision.
+_EMULATE_BF16 = False
+
+
+class bf16_storage:
+    def __enter__(self):
+        global _EMULATE_BF16
+        self.prev, _EMULATE_BF16 = _EMULATE_BF16, True
+        return self
+
+    def __exit__(self, *exc):
+        global _EMULATE_BF16
+        _EMULATE_BF16 = self.prev
+
+
+def _q(t: Tensor) -> Tensor:
+    if not _EMULATE_BF16:
+        return t
+    return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
 def _conv(x: Tensor, w: Tensor, stride, padding) -> Tensor:
-    return F.conv3d(x, w, None, stride, padding) if w.dim() == 5 else F.conv2d(x, w, None, stride, padding)
+    if w.shape[1] != 1:
+        w = _q(w)
+    y = F.conv3d(x, w, None, stride, padding) if w.dim() == 5 else F.conv2d(x, w, None, stride, padding)
+    return _q(y)
 
 
 def convx_block(x: Tensor, sd: StateDict, prefix: str, strides: Sequence, paddings: Sequence,
                 is_residual: bool, train: bool, rec: Optional[BNRecorder] = None,
-                shortcut_stride=None) -> Tensor:
+                shortcut_stride=None, store_out: bool = True) -> Tensor:
     """unet3dConvX / unet2dConvX forward (fusion3D2D.py:717-732, :878-893).
 
     k x [conv(bias=False) -> BN -> ReLU] with the last one conv -> BN only (:597-648);
@@ -181,7 +212,7 @@ def convx_block(x: Tensor, sd: StateDict, prefix: str, strides: Sequence, paddin
         out = _conv(out, sd[p + '.0.weight'], strides[i], paddings[i])
         out = batch_norm(out, sd, p + '.1', train, rec)
         if i < k - 1:
-            out = torch.relu(out)
+            out = _q(torch.relu(out))
     if is_residual:
         res = x
         if prefix + '.downsample.0.weight' in sd:
@@ -190,7 +221,8 @@ def convx_block(x: Tensor, sd: StateDict, prefix: str, strides: Sequence, paddin
             res = _conv(x, wd, st, 0)
             res = batch_norm(res, sd, prefix + '.downsample.1', train, rec)
         out = out + res
-    return torch.relu(out)
+    out = torch.relu(out)
+    return _q(out) if store_out else out
 
 
 def encoder_level_3d(x: Tensor, sd: StateDict, prefix: str, train: bool,
@@ -219,11 +251,11 @@ def projection_block(x: Tensor, sd: StateDict, prefix: str, n_red: int, train: b
     if n_red > 0:
         x = convx_block(x, sd, prefix + '.0', [(1, 1, 2)] * n_red, [(0, 0, 1)] * n_red, True, train, rec,
                         shortcut_stride=(1, 1, 2 ** n_red))
-        x = convx_block(x, sd, prefix + '.1', [(1, 1, 1)], [(0, 0, 0)], False, train, rec)
+        x = convx_block(x, sd, prefix + '.1', [(1, 1, 1)], [(0, 0, 0)], False, train, rec, store_out=not take_mean)
     else:
-        x = convx_block(x, sd, prefix + '.0', [(1, 1, 1)], [(0, 0, 0)], False, train, rec)
+        x = convx_block(x, sd, prefix + '.0', [(1, 1, 1)], [(0, 0, 0)], False, train, rec, store_out=not take_mean)
     if take_mean:
-        x = x.mean(dim=4, keepdim=True)
+        x = _q(x.mean(dim=4, keepdim=True))        # the kernels fuse BN + ReLU + mean and store only the mean
     return x
 
 
@@ -239,7 +271,7 @@ def resize_2d_feature(f2d: Tensor, size: Sequence[int], interpolate: Optional[st
     """2-D feature -> '2-D in 3-D' and resize to the en-face grid (fusion3D2D.py:544-564)."""
     f = f2d[:, :, :, :, None]
     if interpolate == '2d':
-        f = F.interpolate(f, size=tuple(size), mode='trilinear')
+        f = _q(F.interpolate(f, size=tuple(size), mode='trilinear'))
     elif interpolate == '2d_max':
         f = F.adaptive_max_pool3d(f, output_size=tuple(size))
     return f
@@ -272,13 +304,13 @@ def fusion_body_forward(sd: StateDict, oct: Tensor, slo: Tensor, interpolate: Op
     """
     P = prefix + '.' if prefix else ''
     n2d = 5 if level5 else 4
-    f2d, x = [], slo
+    f2d, x = [], _q(slo)
     for l in range(1, n2d + 1):
         x = encoder_level_2d(x, sd, f'{P}conv{l}_2d', train, rec)
         f2d.append(x)
         if l < n2d:
             x = F.max_pool2d(x, POOLS_2D[l - 1])
-    f3d, x = [], oct
+    f3d, x = [], _q(oct)
     for l in range(1, 6):
         x = encoder_level_3d(x, sd, f'{P}conv{l}', train, rec)
         f3d.append(x)
@@ -331,7 +363,7 @@ def unet3d_body_forward(sd: StateDict, oct: Tensor, train: bool = True, prefix: 
     ``original`` keeps the depth axis after the kernel-8 projection tail instead of averaging it (:458-471; the
     tail's kernel size comes with the weights, :79-82)."""
     P = prefix + '.' if prefix else ''
-    f3d, x = [], oct
+    f3d, x = [], _q(oct)
     for l in range(1, 6):
         x = encoder_level_3d(x, sd, f'{P}conv{l}', train, rec)
         f3d.append(x)
@@ -355,7 +387,7 @@ def unet2d_body_forward(sd: StateDict, img: Tensor, train: bool = True, prefix: 
     """ModifiedUnet2DLevel5.forward (models/fpn/unets2D.py:172-213) / ModifiedUnet2D.forward (:108-144)."""
     P = prefix + '.' if prefix else ''
     n2d = 5 if level5 else 4
-    f2d, x = [], img
+    f2d, x = [], _q(img)
     for l in range(1, n2d + 1):
         x = encoder_level_2d(x, sd, f'{P}conv{l}_2d', train, rec)
         f2d.append(x[:, :, :, :, None])

@@ -112,20 +112,36 @@ def run(case, cfg, loss_mod, O, device='cpu', dtype=torch.float64):
                 buffers={k: v.detach() for k, v in model.state_dict().items() if 'running_' in k})
 
 
+NPROJ = 8
+
+
+def grad_projections(key, g):
+    """<g, r_j> for NPROJ fixed standard-normal vectors r_j seeded by the parameter name: large gradients are pinned
+    without storing them (E[(<g-g', r>)^2] = |g-g'|^2, so the projections estimate the error norm)."""
+    h = 1469598103934665603
+    for ch in key.encode():
+        h = ((h ^ ch) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    gen = torch.Generator().manual_seed(h & 0x7FFFFFFF)
+    r = torch.randn(NPROJ, g.numel(), generator=gen, dtype=torch.float64)
+    return (r @ g.double().reshape(-1).cpu()).numpy()
+
+
 def to_fixture(res):
     fx = {'names': np.array(res['names']), 'trainable': np.array(res['trainable']), 'state_keys': np.array(res['state_keys']),
           'out': res['out'].cpu().numpy(), 'loss': float(res['loss'])}
-    gsum, gl2 = [], []
+    gsum, gl2, gproj = [], [], []
     for k in res['names']:
         g = res['grads'][k]
         if g is None:
             gsum.append(0.0); gl2.append(-1.0)                  # -1: the reference produced no gradient (frozen / unused)
+            gproj.append(np.zeros(NPROJ))
             continue
         g = g.double().cpu()
         gsum.append(g.sum().item()); gl2.append(g.norm().item())
+        gproj.append(grad_projections(k, g))
         if g.numel() <= FULL_GRAD_MAX_NUMEL:
             fx['grad/' + k] = g.numpy().astype(np.float32)
-    fx['grad_sum'], fx['grad_l2'] = np.array(gsum), np.array(gl2)
+    fx['grad_sum'], fx['grad_l2'], fx['grad_proj'] = np.array(gsum), np.array(gl2), np.stack(gproj)
     bk = sorted(res['buffers'])
     fx['buffer_keys'] = np.array(bk)
     fx['buffer_sum'] = np.array([res['buffers'][k].double().sum().item() for k in bk])
