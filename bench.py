@@ -195,19 +195,6 @@ def _reference_step_fn(batch_size):
     return 'port', step, threads
 
 
-def cpu_reference_rate(steps, warmup, batch_size):
-    """Times the reference arm: -> (samples/s, seconds per step, threads, kind)."""
-    kind, step, threads = _reference_step_fn(batch_size)
-    ts = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        step()
-        if i >= warmup:
-            ts.append(time.perf_counter() - t0)
-    sec = sum(ts) / len(ts)
-    return batch_size / sec, sec, threads, kind
-
-
 def _reference_batch():
     """The GPU arm's per-step batch when the host has the memory for it (stock PyTorch keeps ~2.6 GB of activations per C2
     sample), else the largest power-of-two batch that fits."""
@@ -228,7 +215,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     w = WORKLOAD
-    bsz = _reference_batch()
+    bsz = args.ref_batch or _reference_batch()
     steps, warmup = args.steps, args.warmup
     # bounded: the whole run must end within a few minutes on the host cores -> probe one step, then cut the step count if needed
     kind, step, threads = _reference_step_fn(bsz)
@@ -336,6 +323,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='C2', choices=sorted(WORKLOADS), help='BASELINE.json workload (default C2 = the metric\'s)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--ref-batch', type=int, default=0, help='reference arm: samples per step (default: the GPU arm\'s batch)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-roofline', action='store_true')
@@ -379,12 +367,17 @@ def main():
     dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
     trainer = FusionTrainer(model, crit, lr=cfg.learning_rate, momentum=0.9, weight_decay=1e-4)
 
+    if ffpn.lib.is_debug_build():
+        raise SystemExit('bench.py refuses the -DFFPN_DEBUG library (FFPN_LIB=debug): its ablation switches invalidate results')
     trainer.step(dev)                                      # first eager step: records the packed-weight arena
     torch.cuda.synchronize()
-    n0 = ffpn.lib.launch_count(local_rank)
+    n0, r0 = ffpn.lib.launch_count(local_rank), ffpn.lib.route_counts(local_rank)
     trainer.step(dev)                                      # steady-state eager step: counts our launches per step
     torch.cuda.synchronize()
     launches_per_step = ffpn.lib.launch_count(local_rank) - n0
+    routes = {k: v - r0[k] for k, v in ffpn.lib.route_counts(local_rank).items()}      # conv calls per kernel family, one step
+    if args.dtype == 'bf16' and routes['cuda_core'] != 0:
+        raise SystemExit(f'bench.py: {routes["cuda_core"]} bf16 conv calls per step left the tcgen05 / stem kernels: {routes}')
     use_graph = not args.no_graph
     if use_graph:
         trainer.capture(dev)
@@ -450,7 +443,7 @@ def main():
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': int(launches_per_step * args.steps)}
+            'gpu_launches': int(launches_per_step * args.steps), 'conv_routes_per_step': routes, 'build': 'release'}
     if rank == 0:
         peak, src = peaks()
         if not args.no_kernel_roofline:
@@ -471,14 +464,17 @@ def main():
             line['step_roofline'] = {'model_bytes_per_step': step_bytes, 'achieved_gbs': step_bytes / (ms / args.steps * 1e-3) / 1e9,
                                      'frac': step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}
         if world == 1 and not args.no_cpu_baseline:
-            trainer.close()
-            del trainer, model
-            torch.cuda.empty_cache()
-            rate, sec, threads, kind = cpu_reference_rate(3, 1, 1)
-            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': kind, 'cpu_model': cpu_model(),
-                                    'sample': ('unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port')
-                                    + f' on torch CPU fp32, fwd+loss+bwd of 1 sample of the {w["id"]} shape per step, 3 timed after '
-                                      '1 warm-up; `bench.py --impl reference` times it at the full batch'}
+            # the reference's modules share their import names (config, models, common) with this repository's mirror, so the
+            # bounded CPU sample runs in a fresh interpreter: bench.py --impl reference at batch 1, 3 timed steps after 1 warm-up
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', w['id'], '--steps', '3',
+                                '--warmup', '1', '--ref-batch', '1'], capture_output=True, text=True, timeout=900,
+                               env={k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')})
+            try:
+                ref_line = json.loads(r.stdout.strip().splitlines()[-1])
+                line['cpu_baseline'] = dict(ref_line['cpu_baseline'], cpu_model=cpu_model())
+            except Exception:
+                line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': _host_threads(), 'kind': 'reference',
+                                        'sample': 'failed: ' + (r.stderr.strip().splitlines() or ['no output'])[-1][:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

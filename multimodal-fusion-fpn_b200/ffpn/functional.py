@@ -226,7 +226,11 @@ class ConvXFunction(torch.autograd.Function):
         dzp_p = to_phys(dzp) if dzp is not None else None
         dz_p = to_phys(dz) if dz is not None else None
         y_last = ys[-1]
-        count = y_last.numel() // y_last.shape[-1]
+        # eval mode: BatchNorm normalised with the running statistics, which do not depend on the batch -> its backward is
+        # dy = g * gamma * invstd without the batch-statistics terms.  The coefficients cP, cQ are proportional to 1/count, so
+        # an infinite count gives exactly torch's eval-mode native_batch_norm_backward (dgamma, dbeta do not involve count).
+        inf = float('inf')
+        count = y_last.numel() // y_last.shape[-1] if spec.training else inf
         g_last = tensors[5 * (k - 1) + 1]
         if spec.tail == 'mean':
             dA = ops.proj_tail_bwd(dz_p, y_last.shape)
@@ -246,7 +250,7 @@ class ConvXFunction(torch.autograd.Function):
         if spec.residual:
             if yd is not None:
                 wd, gd = tensors[5 * k], tensors[5 * k + 1]
-                dgd, dbd, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 2, yd.numel() // yd.shape[-1], gd,
+                dgd, dbd, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 2, yd.numel() // yd.shape[-1] if spec.training else inf, gd,
                                                            affd[2], affd[3], _sink(gd), _sink(tensors[5 * k + 2]))
                 dyd = ops.bn_bwd_apply(G, yd, affd[0], affd[1], False, cA, cP, cQ)
                 grads[5 * k] = _wgrad(xp, dyd, wd.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0), None, None, False, _sink(wd))
@@ -267,7 +271,7 @@ class ConvXFunction(torch.autograd.Function):
                                   _sink(w))
             if i > 0:
                 dA = ops.conv_dgrad(dy, w, inp.shape, spec.kernels[i], spec.strides[i], spec.pads[i])
-                cnt = inp.numel() // inp.shape[-1]
+                cnt = inp.numel() // inp.shape[-1] if spec.training else inf
                 partial, rows = ops.bn_bwd_reduce(dA, inp, a_in, b_in, True)
                 dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, 2, 1, cnt, tensors[5 * (i - 1) + 1],
                                                          affs[i - 1][2], affs[i - 1][3], _sink(tensors[5 * (i - 1) + 1]),
@@ -432,6 +436,8 @@ def pack_oct(oct: torch.Tensor) -> torch.Tensor:
     shape.  The H<->W transpose is done by one kernel instead of a strided read in the first conv."""
     if oct.dim() != 5 or oct.shape[1] != 1:
         raise ValueError(f'expected a (B,1,S,W,H) volume, got {tuple(oct.shape)}')
+    if oct.requires_grad:
+        raise NotImplementedError('gradients with respect to the input volume are not computed by the CUDA path')
     src = oct.permute(0, 1, 2, 4, 3)                       # back to (B,1,S,H,W)
     if src.is_contiguous() and src.dtype == torch.float32:
         p = ops.pack_volume(src, _COMPUTE_DTYPE)           # memory order (B,1,S,W,H); C == 1
@@ -442,4 +448,6 @@ def pack_oct(oct: torch.Tensor) -> torch.Tensor:
 
 def pack_image2d(img: torch.Tensor) -> torch.Tensor:
     """(B,1,S',W') fp32 -> channels-last compute dtype (same logical shape)."""
+    if img.requires_grad:
+        raise NotImplementedError('gradients with respect to the 2-D input image are not computed by the CUDA path')
     return to_logical(to_phys(img.float().contiguous() if img.dtype != torch.float32 else img), 4)

@@ -173,10 +173,11 @@ class ModifiedUnet3D2D(SegmentationNetwork):
             torch._foreach_add_(nbt, 1)
 
     @staticmethod
-    def _level(seq, x, pool=None, need_dx=True):
+    def _level(seq, x, pool=None):
         """One encoder level (two ConvX blocks); the max-pool that follows is fused into the second block's
-        block-end kernel (forward: pooled copy; backward: argmax routing), returning (features, pooled)."""
-        h = seq[0](x, need_dx=need_dx)
+        block-end kernel (forward: pooled copy; backward: argmax routing), returning (features, pooled).  Whether the
+        block computes an input gradient follows ``x.requires_grad`` (ConvXBase.forward)."""
+        h = seq[0](x)
         if pool is None:
             return seq[1](h), None
         return seq[1](h, pool=pool)
@@ -184,16 +185,14 @@ class ModifiedUnet3D2D(SegmentationNetwork):
     def _encode_2d(self, slo, levels):
         feats, x = [], FF.pack_image2d(slo)
         for l in range(1, levels + 1):
-            f, x = self._level(getattr(self, f'conv{l}_2d'), x, getattr(self, f'pool{l}_2d') if l < levels else None,
-                               need_dx=l > 1)
+            f, x = self._level(getattr(self, f'conv{l}_2d'), x, getattr(self, f'pool{l}_2d') if l < levels else None)
             feats.append(f)
         return feats
 
     def _encode_3d(self, oct):
         feats, x = [], FF.pack_oct(oct)
         for l in range(1, 6):
-            f, x = self._level(getattr(self, f'conv{l}'), x, getattr(self, f'pool{l}') if l < 5 else None,
-                               need_dx=l > 1)
+            f, x = self._level(getattr(self, f'conv{l}'), x, getattr(self, f'pool{l}') if l < 5 else None)
             feats.append(f)
         return feats
 
@@ -225,8 +224,7 @@ class ModifiedUnet3D2D(SegmentationNetwork):
         proj, x = [None] * 5, FF.pack_oct(oct)
         shapes = []
         for l in range(1, 6):
-            f, x = self._level(getattr(self, f'conv{l}'), x, getattr(self, f'pool{l}') if l < 5 else None,
-                               need_dx=l > 1)
+            f, x = self._level(getattr(self, f'conv{l}'), x, getattr(self, f'pool{l}') if l < 5 else None)
             if l < 5:
                 sp = FF.fork(FF.side_stream(dev, l), f)
                 with torch.cuda.stream(sp):

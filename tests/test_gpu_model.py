@@ -23,7 +23,9 @@ def rel(a, b):
 
 @pytest.fixture(autouse=True)
 def _exact_mode():
+    import gc
     import ffpn
+    gc.collect()                                       # trainers of earlier tests release the packed-weight arena of the device
     ffpn.set_compute_dtype(torch.float32)
     yield
     ffpn.set_compute_dtype(torch.bfloat16)
@@ -256,6 +258,7 @@ def test_trainer_gradient_sink_and_fused_sgd(mirror, dtype):
         for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
             assert rel(p.data, q.data) <= 1e-5, k
     assert float(tr.flat_g.abs().max()) == 0.0
+    tr.close()
 
 
 def _trainer_grads(mirror, sd, batch, env):
@@ -310,7 +313,7 @@ def test_captured_graph_step_matches_eager_bitwise(mirror):
     batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 32, 16, 32, seed=6).items()}
     crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
                             'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
-    params = []
+    params, buffers = [], []
     for graph in (False, True):
         model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
         model.load_state_dict(sd, strict=True)
@@ -325,8 +328,13 @@ def test_captured_graph_step_matches_eager_bitwise(mirror):
                 tr.step(batch)
         torch.cuda.synchronize()
         params.append(tr.flat_p.clone())
+        buffers.append({k: b.clone() for k, b in model.named_buffers()})
         tr.close()
     assert torch.equal(params[0], params[1]), float((params[0] - params[1]).abs().max())
+    # the capture's warm-up passes must not leave a trace in the BatchNorm running statistics / counters
+    for k in buffers[0]:
+        assert torch.equal(buffers[0][k], buffers[1][k]), k
+    assert int(buffers[1]['resensnet.conv1.0.convBlock.0.1.num_batches_tracked']) == 3
 
 
 def test_prefetched_replay_equals_direct_replay(mirror):
@@ -363,3 +371,116 @@ def test_prefetched_replay_equals_direct_replay(mirror):
         tr.close()
     assert losses[0] == losses[1] and losses[0][0] != losses[0][1]
     assert torch.equal(params[0], params[1])
+
+
+def _crit(mirror):
+    return mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                            'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+
+
+def test_weights_loaded_behind_the_trainer_are_never_stale(mirror):
+    """The packed bf16 weight arena (recorded by the trainer's first step, baked into its CUDA graph) must not serve stale
+    images: (a) conv calls made outside FusionTrainer.forward_backward -- an eval forward of the same model -- pack from the
+    current fp32 weights; (b) load_state_dict while a trainer is alive marks the arena dirty, so the next eager step or graph
+    replay runs on the loaded weights."""
+    import ffpn
+    from ffpn.trainer import FusionTrainer
+    ffpn.set_compute_dtype(torch.bfloat16)
+    sd_a, sd_b = O.make_state_dict(seed=31), O.make_state_dict(seed=32)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 32, 16, 32, seed=6).items()}
+
+    def fresh(sd, train):
+        m = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+        m.load_state_dict(sd, strict=True)
+        m.train(train)
+        return m
+
+    with torch.no_grad():
+        want_eval_b = fresh(sd_b, False)(batch)['prediction'].clone()
+    ref_tr = FusionTrainer(fresh(sd_b, True), _crit(mirror))
+    want_loss_b = ref_tr.step(batch).item()
+    torch.cuda.synchronize()
+    want_params_b = ref_tr.flat_p.clone()
+    ref_tr.close()
+
+    model = fresh(sd_a, True)
+    tr = FusionTrainer(model, _crit(mirror))
+    tr.capture(batch, warmup=2)                                  # arena sealed with A's images; the graph reads the arena
+    assert tr._arena_state == 2
+    model.load_state_dict(sd_b, strict=True)                     # in place: same parameter pointers
+    model.eval()
+    with torch.no_grad():
+        got_eval = model(batch)['prediction']
+    assert torch.equal(got_eval, want_eval_b)                    # (a) an eval forward outside the trainer bypasses the arena
+    model.train()
+    loss = tr.replay()                                           # (b) the replay repacks first, then steps on B's weights
+    torch.cuda.synchronize()
+    assert loss.item() == want_loss_b
+    assert torch.equal(tr.flat_p, want_params_b)
+    tr.close()
+
+
+def test_accumulate_grad_batches_sums_micro_batches(mirror):
+    """train.py:161 accumulate_grad_batches=k: the optimiser sees the MEAN of k micro-batch gradients (each with its own
+    BatchNorm statistics), then one SGD step.  Checked in the fp32 exact mode against plain autograd on a twin model."""
+    from ffpn.trainer import FusionTrainer
+    sd = O.make_state_dict(seed=41)
+    micro = [{k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 32, 16, 32, seed=s).items()} for s in (1, 2)]
+    ref = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+    ref.load_state_dict(sd, strict=True)
+    ref.train()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    for b in micro:
+        (_crit(mirror)(b, ref(b))[0] / 2).backward()
+    g_ref = torch.cat([p.grad.reshape(-1) for p in ref.parameters()]).clone()
+    opt.step()
+    model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    tr = FusionTrainer(model, _crit(mirror), lr=0.1, momentum=0.9, weight_decay=1e-4, accumulate_grad_batches=2)
+    assert not tr._sink
+    tr.step(micro[0])
+    assert tr.steps == 0 and float(tr.flat_g.abs().max()) > 0    # no optimiser step after the first micro-batch
+    g_half = tr.flat_g.clone()
+    tr.forward_backward(micro[1])
+    assert rel(tr.flat_g, g_ref) <= 1e-5 and rel(g_half, g_ref) > 1e-2
+    tr.micro += 1
+    tr.optimizer_step()
+    assert tr.steps == 1 and float(tr.flat_g.abs().max()) == 0.0
+    for (k, p), q in zip(model.named_parameters(), ref.parameters()):
+        assert rel(p.data, q.data) <= 1e-5, k
+    tr.close()
+
+
+def test_eval_mode_backward_is_frozen_batchnorm(mirror):
+    """Gradients under model.eval() (frozen-BatchNorm fine-tuning, saliency): BatchNorm uses the running statistics in
+    forward AND backward (dy = g * gamma * invstd, no batch-statistics terms), like torch's eval-mode
+    native_batch_norm_backward.  Against the oracle's autograd in eval mode."""
+    sd = O.make_state_dict(seed=4, randomize_running=True)
+    batch = O.synthetic_batch(2, 4, 64, 16, 4, 16, seed=2)
+    model, cb, out = _run(mirror, sd, batch, 'oct', train=False)
+    _loss(mirror, cb, out).backward()
+    work = {k: (v.clone().requires_grad_(True) if k in set(O.param_keys(sd)) else v) for k, v in sd.items()}
+    pred = O.fpn_hybrid_fusion_forward(work, batch, 'oct', train=False)['prediction']
+    keys = O.param_keys(sd)
+    grads = dict(zip(keys, torch.autograd.grad(O.mix_loss(pred, batch['mask']), [work[k] for k in keys])))
+    assert rel(out['prediction'].detach().cpu(), pred.detach()) <= 1e-4
+    num = sum((p.grad.cpu().double() - grads[k].double()).norm().item() ** 2 for k, p in model.named_parameters())
+    den = sum(g.double().norm().item() ** 2 for g in grads.values())
+    assert (num / den) ** 0.5 <= 1e-2, (num / den) ** 0.5
+    after = model.state_dict()
+    assert all(torch.equal(after[k].cpu(), sd[k]) for k in sd)
+
+
+def test_fused_finalize_is_safe_with_branch_streams(mirror):
+    """FFPN_FUSED_FIN=1 (BatchNorm finalize by the conv's last CTA) with convs in flight on several streams: every launch
+    has its own arrival counter, so the result is bit-identical to the separate finalize kernel on one stream."""
+    import ffpn
+    ffpn.set_compute_dtype(torch.bfloat16)
+    sd = O.make_state_dict(seed=11)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 8, 64, 64, 40, 64, seed=4).items()}
+    l0, g0, b0 = _trainer_grads(mirror, sd, batch, {'FFPN_STREAMS': '0', 'FFPN_FUSED_FIN': '0'})
+    for _ in range(3):
+        l1, g1, b1 = _trainer_grads(mirror, sd, batch, {'FFPN_STREAMS': '1', 'FFPN_FUSED_FIN': '1'})
+        assert l1 == l0 and torch.equal(g1, g0)
+        assert all(torch.equal(b1[k], b0[k]) for k in b0)

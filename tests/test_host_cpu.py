@@ -169,6 +169,42 @@ def test_dp_gradient_average_world2_gloo():
             assert torch.allclose(torch.from_numpy(r[2][k]), want[k], atol=1e-7)
 
 
+def _bcast_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from ffpn.trainer import FusionTrainer
+    torch.manual_seed(1000 + rank)                               # ranks initialise DIFFERENTLY (unseeded init, per-rank checkpoint ...)
+    net = torch.nn.Sequential(torch.nn.Conv3d(2, 3, 1), torch.nn.BatchNorm3d(3))
+    with torch.no_grad():
+        net[1].running_mean.add_(rank + 1.0)
+        net[1].num_batches_tracked.add_(7 * (rank + 1))
+    before = float(sum(p.double().sum() for p in net.parameters()))
+    tr = FusionTrainer(net, criterion=None)
+    q.put((rank, before, tr.flat_p.clone().numpy(), {k: v.clone().numpy() for k, v in net.state_dict().items()}))
+    dist.destroy_process_group()
+
+
+def test_trainer_broadcasts_rank0_state_world2_gloo():
+    """Replicas that start from different weights / BatchNorm buffers are made equal to rank 0 at FusionTrainer construction
+    (the reference's DataParallel re-replicates device 0's module every step, so its replicas cannot differ)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] != res[1][1]                                # they did start out different
+    assert np.array_equal(res[0][2], res[1][2])
+    for k in res[0][3]:
+        assert np.array_equal(res[0][3][k], res[1][3][k]), k
+    assert float(res[1][3]['1.running_mean'][0]) == 1.0 and int(res[1][3]['1.num_batches_tracked']) == 7    # rank 0's values
+
+
 def test_every_kernel_waits_for_its_predecessor_grid():
     """Programmatic dependent launch is only safe if EVERY kernel launched with the attribute begins with
     griddepcontrol.wait before it touches global memory, and if no launch bypasses ffpn_launch().  Source-level guard:
