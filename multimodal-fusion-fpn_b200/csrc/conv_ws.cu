@@ -20,7 +20,9 @@ constexpr int WS_THREADS = 512;
 constexpr int WS_MAX_STAGES = 6;
 constexpr int WS_NT = 128;            // transform threads: warps 12..15, one per SM sub-partition (FFPN_WS_NT=160 adds warp 3: a fifth warp doubles one scheduler's share)
 constexpr int WS_NEPI = 8;            // epilogue warps 4..11
-constexpr int WS_HDR = 1024 + 8 * 2 * 256 * 4;   // barriers, then one statistics slot per epilogue warp (fixed-order sum: deterministic)
+constexpr int WS_STAT_BYTES = 8 * 2 * 256 * 4;   // one statistics slot per epilogue warp (fixed-order sum: deterministic)
+constexpr int WS_TAB_BYTES = 1024 * 8;           // row table of the epilogue: 8 accumulator blocks x 128 rows x (offset, packed j|y|x)
+constexpr int WS_HDR = 1024 + WS_STAT_BYTES + WS_TAB_BYTES;   // barriers first
 
 struct WsParams {
   int NB, D, Y, X, oD, oY, oX, kD, kY, kX, pD, pY, pX, hl;
@@ -100,7 +102,7 @@ struct WsRing {
 };
 
 // NREG: 16-column chunks whose statistics are accumulated in registers (Npad == 16 * NREG); 0 = shuffle per chunk.
-template <int NREG, bool ADD>
+template <int NREG, bool ADD, bool SPLITC>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ WsParams p,
                                                                 const __grid_constant__ CUtensorMap tmap) {
   pdl_trigger();
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   const uint32_t WBAR = bar0 + 8u * 26u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 240);
   float* stat_s = reinterpret_cast<float*>(smem + 1024);
+  uint2* row_tab = reinterpret_cast<uint2*>(smem + 1024 + WS_STAT_BYTES);
   uint8_t* w_s = smem + WS_HDR;
   uint8_t* stage0 = w_s + (p.w_resident ? ((p.b_total_bytes + 1023u) & ~1023u) : 0u);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       mbar_init(READY(s), (uint32_t)(p.nt >> 5));
       mbar_init(EMPTY(s), 1);
     }
-    for (int b = 0; b < 4; b++) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), WS_NEPI); }
+    for (int b = 0; b < 4; b++) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), SPLITC ? WS_NEPI : WS_NEPI / 2); }
     mbar_init(WBAR, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -261,22 +264,44 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     }
   } else if (warp >= 4 && warp < 4 + WS_NEPI) {
     // ================= epilogue =================
+    // Two warps per TMEM lane quadrant.  SPLITC = false: they take ALTERNATE TILES (tile parity), so the two warps that share an
+    // SM sub-partition are in different phases of their tcgen05.ld -> convert -> store chains and hide each other's latency.
+    // SPLITC = true (N = 64 with statistics): both work on every tile and take half of the 16-column chunks each, which keeps
+    // the per-thread statistics of 32 channels in registers instead of 2 x 16 warp shuffles per item.
     const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int etid = tid - 128;                                    // 0..255 over the epilogue warps
+    // ---- row table: tile-local output position of every accumulator row, once per CTA (the decomposition of a row index into
+    // slice / line / column does not depend on the tile; only the clipping against the tensor edges does) ----
+    {
+      const int nrows_tab = (int)(buf_cols / (uint32_t)p.colstride) * 128;
+      for (int m = etid; m < nrows_tab; m += WS_NEPI * 32) {
+        const int j = m / p.Lr, ii = m - j * p.Lr;
+        const int oyl = p.tma_mode == 0 ? ii / p.Xp : 0, oxl = p.tma_mode == 0 ? ii - oyl * p.Xp : ii;
+        const bool ok = ii < p.L && j < 256 && oyl < 4096 && oxl < 4096;       // ii >= L: rows between two slices of a tile
+        const long long relo = (long long)j * p.outD + (long long)oyl * p.outY + oxl;
+        row_tab[m] = ok ? make_uint2((uint32_t)relo, ((uint32_t)j << 24) | ((uint32_t)oyl << 12) | (uint32_t)oxl) : make_uint2(0xffffffffu, 0u);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(WS_NEPI * 32) : "memory");         // epilogue warps only
+    }
     float* my_stat = stat_s + (warp - 4) * 2 * p.Npad;            // this warp's own slot: plain read-modify-write, no atomics
     float ssum[NREG > 0 ? 16 * NREG : 1], ssq[NREG > 0 ? 16 * NREG : 1];
 #pragma unroll
     for (int i = 0; i < (NREG > 0 ? 16 * NREG : 1); i++) { ssum[i] = 0.f; ssq[i] = 0.f; }
-    const int nch = NREG > 0 ? NREG : (p.Npad >> 4);
+    const int nch_all = p.Npad >> 4;
+    const int nch = NREG > 0 ? NREG : (SPLITC ? (nch_all >> 1) : nch_all);      // 16-column chunks this warp takes per accumulator block
+    const int ch0 = SPLITC ? half * nch : 0;
     constexpr int BATCH = NREG == 2 ? 2 : 4;                                        // TMEM loads in flight per thread
-    const uint32_t magicLr = (uint32_t)(0x100000000ull / (uint32_t)p.Lr) + 1u;     // exact quotients for m * Lr < 2^32
-    const uint32_t magicXp = (uint32_t)(0x100000000ull / (uint32_t)p.Xp) + 1u;
     int tl = 0;
     WsTile tc;
     for (tc.init(p); tc.valid(p); tc.next(p), tl++) {
+      if (!SPLITC && (tl & 1) != half) continue;
       const int buf = tl % p.nbuf;
       if (warp == 4 && lane == 0) WS_TRACE(7, tl);
-      const int my_nmb = (p.dbg & 2) ? 0 : (tc.nmb - half + 1) >> 1;               // accumulator blocks half, half + 2, ...
-      const int nitems = my_nmb * nch;
+      const int nitems = ((p.dbg & 2) ? 0 : tc.nmb) * nch;
+      // clipping of this tile against the tensor (slices, lines, columns, and the line end when X is cut into segments)
+      const int ox_base = p.tma_mode == 0 ? 0 : tc.i0, oy_base = p.tma_mode == 0 ? tc.it * p.tY : 0;
+      const int remD = tc.tD_t, remY = p.oY - oy_base, remX = min(p.oX, p.oXtot - tc.nb * p.xseg) - ox_base;
+      const long long tbase = (long long)tc.nb * p.outNB + (long long)tc.d0 * p.outD + (long long)oy_base * p.outY + ox_base;
       uint32_t raw[BATCH][16];
       long long oposv[BATCH];
       bool validv[BATCH];
@@ -289,14 +314,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           validv[u] = false; oposv[u] = 0;
           if (ADD) addv[ADD ? u : 0][0] = addv[ADD ? u : 0][1] = make_uint4(0u, 0u, 0u, 0u);
           if (idx < nitems) {
-            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
-            const int m = (half + 2 * mbi) * 128 + quad * 32 + lane;
-            const int j = p.Lr == 1 ? m : (int)__umulhi((uint32_t)m, magicLr), ii = m - j * p.Lr;
-            const int i = tc.i0 + ii;
-            // flat / slice modes have Xp >= every i (one line): the reciprocal is only exact while i * Xp < 2^32 (mode 0)
-            const int oy = i < p.Xp ? 0 : (p.Xp == 1 ? i : (int)__umulhi((uint32_t)i, magicXp)), ox = i - oy * p.Xp;
-            validv[u] = (m < tc.M_t) && (j < tc.tD_t) && (ii < tc.L_t) && (oy < p.oY) && (ox < p.oX) && (tc.nb * p.xseg + ox < p.oXtot);
-            oposv[u] = (long long)tc.nb * p.outNB + (long long)(tc.d0 + j) * p.outD + (long long)oy * p.outY + ox;
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? u % NREG : idx - mbi * nch);
+            const uint2 e = row_tab[mbi * 128 + quad * 32 + lane];
+            const int j = (int)(e.y >> 24), oyl = (int)((e.y >> 12) & 0xfffu), oxl = (int)(e.y & 0xfffu);
+            validv[u] = (e.x != 0xffffffffu) && (j < remD) && (oyl < remY) && (oxl < remX);
+            oposv[u] = tbase + (long long)e.x;
             if (ADD && validv[u]) {
               const int cbase = n0 + ch * 16;
               const uint4* ap = reinterpret_cast<const uint4*>(p.addend + oposv[u] * p.Cout + cbase);
@@ -324,8 +346,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         for (int u = 0; u < BATCH; u++) {
           const int idx = it0 + u;
           if (idx < nitems) {
-            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
-            tmem_ld16_nowait(t_tile + (uint32_t)((half + 2 * mbi) * p.colstride + ch * 16), raw[u]);
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? u % NREG : idx - mbi * nch);
+            tmem_ld16_nowait(t_tile + (uint32_t)(mbi * p.colstride + ch * 16), raw[u]);
           }
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         for (int u = 0; u < BATCH; u++) {
           const int idx = it0 + u;
           if (idx < nitems) {
-            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = NREG > 0 ? u % NREG : idx - mbi * nch;
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? u % NREG : idx - mbi * nch);
             const bool valid = validv[u];
             const long long opos = oposv[u];
             float v[16];
@@ -402,14 +424,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     }
     if (NREG > 0 && p.has_stats) {
 #pragma unroll
-      for (int ch = 0; ch < (NREG > 0 ? NREG : 1); ch++) {
+      for (int chl = 0; chl < (NREG > 0 ? NREG : 1); chl++) {
         float a[16], b[16];
 #pragma unroll
-        for (int q = 0; q < 16; q++) { a[q] = ssum[16 * ch + q]; b[q] = ssq[16 * ch + q]; }
+        for (int q = 0; q < 16; q++) { a[q] = ssum[16 * chl + q]; b[q] = ssq[16 * chl + q]; }
         const float ta = warp_transpose_sum16(a, lane);
         const float tb = warp_transpose_sum16(b, lane);
         if ((lane & 1) == 0) {
-          const int c = ch * 16 + transpose_sum_channel(lane);
+          const int c = (ch0 + chl) * 16 + transpose_sum_channel(lane);
           my_stat[c] += ta;
           my_stat[p.Npad + c] += tb;
         }
@@ -450,6 +472,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
             uint8_t* base = stage0 + (size_t)st * p.stage_bytes + (size_t)kgi * p.sub_bytes;
             const uint32_t abase = smem_u32(base);                       // the swizzle is a function of the absolute address
             int rr = r0;
+            if (((rstep * p.pitch) & 1023) == 0) {
+              // a thread's rows are a whole number of swizzle periods (1 KiB) apart: its 16-byte chunk sits at the same swizzled
+              // offset in every one of them, so the loop is a pointer walk -- 8 independent chunks in flight per thread (the four
+              // transform warps have a scheduler each: the loop is bound by dependent-issue latency, not by issue slots)
+              const uint32_t off0 = (uint32_t)r0 * (uint32_t)p.pitch;
+              uint4* q0 = reinterpret_cast<uint4*>(base + off0 + ((((uint32_t)cc ^ ((abase + off0) >> 7)) & cmask) << 4));
+              const int qstep = (rstep * p.pitch) >> 4;
+              const int n = (p.region_rows - r0 + rstep - 1) / rstep;
+              int i = 0;
+              for (; i + 8 <= n; i += 8, q0 += 8 * qstep) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = q0[u * qstep];
+#pragma unroll
+                for (int u = 0; u < 8; u++) q0[u * qstep] = bn_relu_bf16x8(v[u], s, h, 1);
+              }
+              for (; i < n; i++, q0 += qstep) *q0 = bn_relu_bf16x8(*q0, s, h, 1);
+              rr = p.region_rows;
+            }
             for (; rr + 3 * rstep < p.region_rows; rr += 4 * rstep) {
               uint4* q[4];
               uint4 v[4];
@@ -674,7 +715,7 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
         int nst = (int)(avail / stage);
         if (nst > WS_MAX_STAGES) nst = WS_MAX_STAGES;
         if (nst < want_stages) continue;
-        if (nst > 4) nst = 4;
+        { static int cap = -1; if (cap < 0) { const char* e = getenv("FFPN_WS_STAGES"); cap = e ? atoi(e) : 4; } if (nst > cap) nst = cap; }   // tuning
         // two issuer warps need a stage ring each (tile parity): 2 + 2 stages, or 1 + 1 when a tile is one unit
         p.niss = (nst >= 4 || (nst >= 2 && upt == 1)) ? 2 : 1;
         p.nst_ring0 = p.niss == 2 ? (nst + 1) / 2 : nst;
@@ -803,10 +844,11 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   { const char* e = getenv("FFPN_WS_NT"); p.nt = (e && atoi(e) == 160) ? 160 : WS_NT; }
   p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
   if (!(ctx->attr_mask & FFPN_ATTR_WS)) {                              // per device: the attribute belongs to the function ON the current device
-    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_ws: cannot raise dynamic smem: %s", cudaGetErrorString(e));
     ctx->attr_mask |= FFPN_ATTR_WS;
   }
@@ -826,11 +868,13 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     cudaMalloc(&p.trace, 64 * 16 * sizeof(long long));
     cudaMemset(p.trace, 0, 64 * 16 * sizeof(long long));
   }
-  const int nreg = p.has_add ? 0 : (p.has_stats && p.Npad == 16) ? 1 : (p.has_stats && p.Npad == 32) ? 2 : 0;
-  if (p.has_add) ffpn_launch(conv_ws_kernel<0, true>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
-  else if (nreg == 1) ffpn_launch(conv_ws_kernel<1, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
-  else if (nreg == 2) ffpn_launch(conv_ws_kernel<2, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
-  else ffpn_launch(conv_ws_kernel<0, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  // statistics in registers: N = 16 / 32 per warp; N = 64 with the two warps of a quadrant splitting the columns (32 each)
+  const int nreg = p.has_add ? 0 : (p.has_stats && p.Npad == 16) ? 1 : (p.has_stats && (p.Npad == 32 || p.Npad == 64)) ? 2 : 0;
+  if (p.has_add) ffpn_launch(conv_ws_kernel<0, true, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (nreg == 1) ffpn_launch(conv_ws_kernel<1, false, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (nreg == 2 && p.Npad == 64) ffpn_launch(conv_ws_kernel<2, false, true>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (nreg == 2) ffpn_launch(conv_ws_kernel<2, false, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else ffpn_launch(conv_ws_kernel<0, false, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
   FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_ws" : "conv_fwd_ws");
   if (trace_mode) {
     static long long h[64 * 16];
