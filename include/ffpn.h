@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FFPN_ABI_VERSION 1
+#define FFPN_ABI_VERSION 2
 #define FFPN_F32 0
 #define FFPN_BF16 1
 /* rows of a per-block partial-statistics buffer: [FFPN_STAT_ROWS][ncols] floats */
@@ -173,13 +173,27 @@ int ffpn_upsample_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t Si, int64_t W
 int ffpn_slice_copy(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* src, int sstride, int soff,
                     void* dst, int dstride, int doff, void* stream);
 
-/* ---- head: final1 = Conv3d(C -> n, 1x1x1, bias) (fusion3D2D.py:223,579); logits fp32 in the
- *      reference layout (B, n, S, W, 1) ---------------------------------------------------------------- */
-int ffpn_head_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, const void* x,
-                  const float* w, const float* bias, float* logits, void* stream);
-/* dx (activations dtype), dw[n][C] and dbias[n] (fp32, written) from dlogits */
+/* ---- head: final1 = Conv3d(C -> n, 1x1x1, bias) (fusion3D2D.py:223,579), optionally with the wrapper's sigmoid
+ *      (fusion_nets.py:110,118) fused in: act 0 = logits, 1 = sigmoid.  Output fp32 in the reference layout (B, n, S, W, 1). - */
+int ffpn_head_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, int act, const void* x,
+                  const float* w, const float* bias, float* out, void* stream);
+/* dx (activations dtype), dw[n][C] and dbias[n] (fp32, written) from dout = dL/d(out).  pred != NULL: out was the sigmoid and
+ * pred is that output (the gradient of the pre-activation is formed on the fly as dout * pred * (1 - pred)).  ws: scratch of
+ * ffpn_head_bwd_workspace_bytes(C, n) bytes for the two-stage fixed-order weight-gradient reduction. */
+size_t ffpn_head_bwd_workspace_bytes(int C, int n);
 int ffpn_head_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, const void* x,
-                  const float* w, const float* dlogits, void* dx, float* dw, float* dbias, void* stream);
+                  const float* w, const float* dout, const float* pred, void* dx, float* dw, float* dbias, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* ---- training loss: Mix({Dice_loss_jointv2, BCE_Lossv2}) with unit coefficients (common/loss.py:9-90) on the fp32
+ *      prediction and mask, both (B, n, EW) contiguous.  fwd: out[0..2] = loss, dice, bce and out[3 + 2k], out[4 + 2k] = the
+ *      per-channel Dice sums the backward needs (out has 3 + 2n floats).  bwd: dpred = grad_scale[0] * dloss/dpred
+ *      (grad_scale: device scalar, NULL = 1).  Replaces the ~45 ATen launches of the loss and its autograd backward. ------- */
+size_t ffpn_mix_loss_workspace_bytes(int n);
+int ffpn_mix_loss_fwd(ffpn_ctx* ctx, int64_t B, int n, int64_t EW, const float* pred, const float* mask, void* ws,
+                      size_t ws_bytes, float* out, void* stream);
+int ffpn_mix_loss_bwd(ffpn_ctx* ctx, int64_t B, int n, int64_t EW, const float* pred, const float* mask,
+                      const float* stats, const float* grad_scale, float* dpred, void* stream);
 
 /* ---- input packing: fp32 (R, H, W) -> activations dtype (R, W, H)  (the permute of
  *      fusion_nets.py:114 made physical; R = B*S) ----------------------------------------------------- */

@@ -241,8 +241,9 @@ __global__ void slice_copy_kernel(int64_t P, int C, const T* __restrict__ src, i
 }
 
 // logits[b][k][ew] = bias[k] + sum_c x[b,ew,c] * w[k][c]
+// final1 (+ the model's sigmoid, fusion_nets.py:110,118, when act == 1): out[b][k][ew] = act(bias[k] + sum_c w[k][c] x[b][ew][c])
 template <typename T>
-__global__ void head_fwd_kernel(int B, int64_t EW, int C, int n, const T* __restrict__ x, const float* __restrict__ w,
+__global__ void head_fwd_kernel(int B, int64_t EW, int C, int n, int act, const T* __restrict__ x, const float* __restrict__ w,
                                 const float* __restrict__ bias, float* __restrict__ logits) {
   pdl_prologue();
   const int64_t tot = (int64_t)B * EW;
@@ -251,16 +252,24 @@ __global__ void head_fwd_kernel(int B, int64_t EW, int C, int n, const T* __rest
     for (int k = 0; k < n; k++) {
       float s = bias ? bias[k] : 0.f;
       for (int c = 0; c < C; c++) s = fmaf(Elem<T>::ld1(x + i * C + c), w[k * C + c], s);
+      if (act == 1) s = 1.f / (1.f + expf(-s));
       logits[(b * n + k) * EW + ew] = s;
     }
   }
 }
 
+// gradient wrt the pre-activation: dl = dout (act == 0) or dout * p * (1 - p) with p = the forward's sigmoid output
+__device__ __forceinline__ float head_dl(const float* __restrict__ dout, const float* __restrict__ pred, int64_t o) {
+  const float g = dout[o];
+  if (pred == nullptr) return g;
+  const float p = pred[o];
+  return g * p * (1.f - p);
+}
+
 // dx[pos][c] = sum_k dl[k] w[k][c];  dw[k][c] = sum_pos dl[k] x[pos][c];  db[k] = sum_pos dl[k]
-// single block per (k): tiny tensors (<= a few 100K positions); deterministic tree reduction.
 template <typename T>
 __global__ void head_bwd_dx_kernel(int B, int64_t EW, int C, int n, const float* __restrict__ w,
-                                   const float* __restrict__ dl, T* __restrict__ dx) {
+                                   const float* __restrict__ dl, const float* __restrict__ pred, T* __restrict__ dx) {
   pdl_prologue();
   const int64_t tot = (int64_t)B * EW * C;
   for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < tot; i += (int64_t)gridDim.x * TH) {
@@ -268,34 +277,53 @@ __global__ void head_bwd_dx_kernel(int B, int64_t EW, int C, int n, const float*
     const int64_t pos = i / C;
     const int64_t b = pos / EW, ew = pos % EW;
     float s = 0.f;
-    for (int k = 0; k < n; k++) s = fmaf(dl[(b * n + k) * EW + ew], w[k * C + c], s);
+    for (int k = 0; k < n; k++) s = fmaf(head_dl(dl, pred, (b * n + k) * EW + ew), w[k * C + c], s);
     Elem<T>::st1(dx + i, s);
   }
 }
 
+// Two stages, both deterministic: HB_BLOCKS blocks each reduce a slice of the positions for every (k, c) (thread = one
+// (position lane, c) pair, so a warp reads whole channel rows), then one block adds the partials in a fixed order.
+constexpr int HB_BLOCKS = 64;
 template <typename T>
-__global__ void head_bwd_dw_kernel(int B, int64_t EW, int C, int n, const T* __restrict__ x, const float* __restrict__ dl,
-                                   float* __restrict__ dw, float* __restrict__ dbias) {
+__global__ void __launch_bounds__(TH) head_bwd_dw_partial_kernel(int B, int64_t EW, int C, int n, const T* __restrict__ x,
+                                                                const float* __restrict__ dl, const float* __restrict__ pred,
+                                                                float* __restrict__ partial) {
   pdl_prologue();
-  // grid = n * (C + 1) blocks: block (k, c) reduces over all positions; c == C is the bias column
-  __shared__ double red[TH];
-  const int k = blockIdx.x / (C + 1), c = blockIdx.x % (C + 1);
+  __shared__ float red[TH];
+  const int C1 = C + 1;                                   // column C is the bias
+  const int lanes = TH / C1;                              // position lanes per block (C = 16: 15)
+  const int c = threadIdx.x % C1, pl = threadIdx.x / C1;
   const int64_t tot = (int64_t)B * EW;
-  double s = 0.0;
-  for (int64_t i = threadIdx.x; i < tot; i += TH) {
-    const int64_t b = i / EW, ew = i % EW;
-    const float g = dl[(b * n + k) * EW + ew];
-    s += (c < C) ? (double)g * (double)Elem<T>::ld1(x + i * C + c) : (double)g;
-  }
-  red[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = TH / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+  for (int k = 0; k < n; k++) {
+    float s = 0.f;
+    if (pl < lanes) {
+      for (int64_t i = (int64_t)blockIdx.x * lanes + pl; i < tot; i += (int64_t)gridDim.x * lanes) {
+        const int64_t b = i / EW, ew = i - b * EW;
+        const float g = head_dl(dl, pred, (b * n + k) * EW + ew);
+        s = fmaf(g, c < C ? Elem<T>::ld1(x + i * C + c) : 1.f, s);
+      }
+    }
     __syncthreads();
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < C1) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; l++) t += red[l * C1 + threadIdx.x];
+      partial[((int64_t)blockIdx.x * n + k) * C1 + threadIdx.x] = t;
+    }
   }
-  if (threadIdx.x == 0) {
-    if (c < C) dw[k * C + c] = (float)red[0];
-    else dbias[k] = (float)red[0];
+}
+__global__ void __launch_bounds__(TH) head_bwd_dw_final_kernel(int nblocks, int C, int n, const float* __restrict__ partial,
+                                                              float* __restrict__ dw, float* __restrict__ dbias) {
+  pdl_prologue();
+  const int C1 = C + 1;
+  for (int i = threadIdx.x; i < n * C1; i += TH) {
+    const int k = i / C1, c = i % C1;
+    double t = 0.0;
+    for (int r = 0; r < nblocks; r++) t += (double)partial[((int64_t)r * n + k) * C1 + c];
+    if (c < C) dw[k * C + c] = (float)t;
+    else dbias[k] = (float)t;
   }
 }
 
@@ -432,26 +460,37 @@ extern "C" int ffpn_slice_copy(ffpn_ctx* ctx, int dtype, int64_t P, int C, const
   return 0;
 }
 
-extern "C" int ffpn_head_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, const void* x, const float* w,
-                             const float* bias, float* logits, void* stream) {
+extern "C" int ffpn_head_fwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, int act, const void* x, const float* w,
+                             const float* bias, float* out, void* stream) {
+  if (act != 0 && act != 1) FFPN_FAIL(ctx, "head_fwd: unknown activation %d", act);
   const int g = grid_of(ctx, B * EW);
-  if (dtype == FFPN_F32) ffpn_launch(head_fwd_kernel<float>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const float*)x, w, bias, logits);
-  else ffpn_launch(head_fwd_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const bf16*)x, w, bias, logits);
+  if (dtype == FFPN_F32) ffpn_launch(head_fwd_kernel<float>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, act, (const float*)x, w, bias, out);
+  else ffpn_launch(head_fwd_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, act, (const bf16*)x, w, bias, out);
   FFPN_CHECK_LAUNCH(ctx, "head_fwd");
   return 0;
 }
 
+extern "C" size_t ffpn_head_bwd_workspace_bytes(int C, int n) { return (size_t)HB_BLOCKS * n * (C + 1) * sizeof(float); }
+
 extern "C" int ffpn_head_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t EW, int C, int n, const void* x, const float* w,
-                             const float* dlogits, void* dx, float* dw, float* dbias, void* stream) {
+                             const float* dout, const float* pred, void* dx, float* dw, float* dbias, void* ws, size_t ws_bytes,
+                             void* stream) {
+  if (C + 1 > TH) FFPN_FAIL(ctx, "head_bwd: more than %d input channels", TH - 1);
+  if (ws == nullptr || ws_bytes < ffpn_head_bwd_workspace_bytes(C, n)) FFPN_FAIL(ctx, "head_bwd: workspace too small");
   const int g = grid_of(ctx, B * EW * C);
   if (dx != nullptr) {
-    if (dtype == FFPN_F32) ffpn_launch(head_bwd_dx_kernel<float>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, w, dlogits, (float*)dx);
-    else ffpn_launch(head_bwd_dx_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, w, dlogits, (bf16*)dx);
+    if (dtype == FFPN_F32) ffpn_launch(head_bwd_dx_kernel<float>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, w, dout, pred, (float*)dx);
+    else ffpn_launch(head_bwd_dx_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, w, dout, pred, (bf16*)dx);
     FFPN_CHECK_LAUNCH(ctx, "head_bwd_dx");
   }
-  if (dtype == FFPN_F32) ffpn_launch(head_bwd_dw_kernel<float>, n * (C + 1), TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const float*)x, dlogits, dw, dbias);
-  else ffpn_launch(head_bwd_dw_kernel<bf16>, n * (C + 1), TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const bf16*)x, dlogits, dw, dbias);
-  FFPN_CHECK_LAUNCH(ctx, "head_bwd_dw");
+  const int lanes = TH / (C + 1);
+  int nb = (int)((B * EW + lanes - 1) / lanes);
+  if (nb > HB_BLOCKS) nb = HB_BLOCKS;
+  if (dtype == FFPN_F32) ffpn_launch(head_bwd_dw_partial_kernel<float>, nb, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const float*)x, dout, pred, (float*)ws);
+  else ffpn_launch(head_bwd_dw_partial_kernel<bf16>, nb, TH, 0, (cudaStream_t)stream, (int)B, EW, C, n, (const bf16*)x, dout, pred, (float*)ws);
+  FFPN_CHECK_LAUNCH(ctx, "head_bwd_dw_partial");
+  ffpn_launch(head_bwd_dw_final_kernel, 1, TH, 0, (cudaStream_t)stream, nb, C, n, (const float*)ws, dw, dbias);
+  FFPN_CHECK_LAUNCH(ctx, "head_bwd_dw_final");
   return 0;
 }
 

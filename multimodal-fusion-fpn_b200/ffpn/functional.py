@@ -413,21 +413,57 @@ class CatFunction(torch.autograd.Function):
         return tuple(outs)
 
 
+_FUSE_HEAD_ACT = True
+
+
+def fuse_head_activation(on: bool) -> None:
+    """The wrappers' sigmoid (fusion_nets.py:110,118) runs inside the head kernel by default; switch it off to get logits out of
+    ``final1`` (forward hooks on that module, stage-level parity tests)."""
+    global _FUSE_HEAD_ACT
+    _FUSE_HEAD_ACT = bool(on)
+
+
+def head_activation_fused() -> bool:
+    return _FUSE_HEAD_ACT
+
+
 class HeadFunction(torch.autograd.Function):
-    """final1 = nn.Conv3d(C, n_classes, 1) with bias (fusion3D2D.py:223,579) -> fp32 logits (B,n,S,W,1)."""
+    """final1 = nn.Conv3d(C, n_classes, 1) with bias (fusion3D2D.py:223,579) -> fp32 (B,n,S,W,1): logits, or with
+    ``act='sigmoid'`` the prediction itself (fusion_nets.py:110,118 fused into the same kernel, forward and backward)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias):
+    def forward(ctx, x, w, bias, act=None):
         xp = to_phys(x)
-        ctx.save_for_backward(xp, w)
+        out = ops.head_fwd(xp, w, bias, 1 if act == 'sigmoid' else 0)
+        ctx.save_for_backward(xp, w, *([out] if act == 'sigmoid' else []))
         ctx.has_bias = bias is not None
-        return ops.head_fwd(xp, w, bias)
+        return out
 
     @staticmethod
-    def backward(ctx, dlogits):
-        xp, w = ctx.saved_tensors
-        dx, dw, db = ops.head_bwd(xp, w, dlogits.contiguous().float(), need_dx=ctx.needs_input_grad[0])
-        return (to_logical(dx, 5) if dx is not None else None), dw, (db if ctx.has_bias else None)
+    def backward(ctx, dout):
+        xp, w, *rest = ctx.saved_tensors
+        pred = rest[0] if rest else None
+        dx, dw, db = ops.head_bwd(xp, w, dout.contiguous().float(), pred, need_dx=ctx.needs_input_grad[0])
+        return (to_logical(dx, 5) if dx is not None else None), dw, (db if ctx.has_bias else None), None
+
+
+class MixDiceBCEFunction(torch.autograd.Function):
+    """Mix({Dice_loss_jointv2, BCE_Lossv2}) with unit coefficients (common/loss.py:9-90) as two kernels forward and one
+    backward -> (total, dice, bce); only ``total`` carries a gradient (to the prediction)."""
+
+    @staticmethod
+    def forward(ctx, pred, mask):
+        pred_c, mask_c = pred.contiguous(), mask.contiguous().float()
+        stats = ops.mix_loss_fwd(pred_c, mask_c)
+        ctx.save_for_backward(pred_c, mask_c, stats)
+        total, dice, bce = stats[0], stats[1], stats[2]
+        ctx.mark_non_differentiable(dice, bce)
+        return total, dice, bce
+
+    @staticmethod
+    def backward(ctx, g_total, _g_dice, _g_bce):
+        pred_c, mask_c, stats = ctx.saved_tensors
+        return ops.mix_loss_bwd(pred_c, mask_c, stats, g_total.contiguous().float()), None
 
 
 def pack_oct(oct: torch.Tensor) -> torch.Tensor:

@@ -52,8 +52,10 @@ SIGNATURES = {
     'ffpn_upsample_fwd': [_I, _L, _L, _L, _I, _I, _I, _P, _P, _I, _I, _P],
     'ffpn_upsample_bwd': [_I, _L, _L, _L, _I, _I, _I, _P, _I, _I, _P, _P],
     'ffpn_slice_copy': [_I, _L, _I, _P, _I, _I, _P, _I, _I, _P],
-    'ffpn_head_fwd': [_I, _L, _L, _I, _I, _P, _P, _P, _P, _P],
-    'ffpn_head_bwd': [_I, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    'ffpn_head_fwd': [_I, _L, _L, _I, _I, _I, _P, _P, _P, _P, _P],
+    'ffpn_head_bwd': [_I, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P],
+    'ffpn_mix_loss_fwd': [_L, _I, _L, _P, _P, _P, _Z, _P, _P],
+    'ffpn_mix_loss_bwd': [_L, _I, _L, _P, _P, _P, _P, _P, _P],
     'ffpn_pack_volume': [_I, _L, _L, _L, _P, _P, _P],
     'ffpn_cast': [_I, _L, _P, _P, _P],
     'ffpn_sgd_step': [_L, _P, _P, _P, _F, _F, _F, _F, _I, _P],
@@ -72,6 +74,8 @@ NO_CTX = {
     'ffpn_last_error': ([_P], C.c_char_p),
     'ffpn_launch_count': ([_P], C.c_int64),
     'ffpn_conv_workspace_bytes': ([_DP], C.c_size_t),
+    'ffpn_head_bwd_workspace_bytes': ([_I, _I], C.c_size_t),
+    'ffpn_mix_loss_workspace_bytes': ([_I], C.c_size_t),
 }
 EXPORTS = sorted(list(SIGNATURES) + list(NO_CTX))
 
@@ -104,7 +108,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.ffpn_abi_version() != 1:
+        if lib.ffpn_abi_version() != 2:
             raise FfpnError('libfusionfpn.so ABI version mismatch')
         _lib = lib
     return _lib

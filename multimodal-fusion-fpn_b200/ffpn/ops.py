@@ -274,25 +274,49 @@ def slice_copy(src, soff, dst, doff, C_):
              dst.shape[-1], doff, _stream(src))
 
 
-def head_fwd(x, w, bias):
-    """x: (B, S, W, 1, C); w: (n, C, 1, 1, 1) fp32 -> logits fp32 (B, n, S, W, 1) in standard layout."""
+def head_fwd(x, w, bias, act: int = 0):
+    """x: (B, S, W, 1, C); w: (n, C, 1, 1, 1) fp32 -> fp32 (B, n, S, W, 1) in standard layout: logits (act 0) or their
+    sigmoid (act 1)."""
     B, S, W, H, C_ = x.shape
     n = w.shape[0]
-    logits = torch.empty((B, n, S, W, H), dtype=torch.float32, device=x.device)
-    lib.call('ffpn_head_fwd', _dev(x), lib.dtype_code(x.dtype), B, S * W * H, C_, n, _ptr(x), _ptr(w), _ptr(bias),
-             _ptr(logits), _stream(x))
-    return logits
+    out = torch.empty((B, n, S, W, H), dtype=torch.float32, device=x.device)
+    lib.call('ffpn_head_fwd', _dev(x), lib.dtype_code(x.dtype), B, S * W * H, C_, n, int(act), _ptr(x), _ptr(w), _ptr(bias),
+             _ptr(out), _stream(x))
+    return out
 
 
-def head_bwd(x, w, dlogits, need_dx=True):
+def head_bwd(x, w, dout, pred=None, need_dx=True):
+    """dout = dL/d(output of head_fwd); pred = that output when it was the sigmoid (act 1), else None."""
     B, S, W, H, C_ = x.shape
     n = w.shape[0]
     dx = torch.empty_like(x) if need_dx else None
     dw = torch.empty_like(w)
     db = torch.empty(n, dtype=torch.float32, device=x.device)
-    lib.call('ffpn_head_bwd', _dev(x), lib.dtype_code(x.dtype), B, S * W * H, C_, n, _ptr(x), _ptr(w), _ptr(dlogits),
-             _ptr(dx), _ptr(dw), _ptr(db), _stream(x))
+    nws = int(lib.load().ffpn_head_bwd_workspace_bytes(C_, n))
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+    lib.call('ffpn_head_bwd', _dev(x), lib.dtype_code(x.dtype), B, S * W * H, C_, n, _ptr(x), _ptr(w), _ptr(dout), _ptr(pred),
+             _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), nws, _stream(x))
     return dx, dw, db
+
+
+def mix_loss_fwd(pred, mask):
+    """pred, mask: (B, n, ...) fp32 contiguous -> stats tensor [loss, dice, bce, inter_0, union_0, ...] (3 + 2n floats)."""
+    B, n = pred.shape[0], pred.shape[1]
+    EW = pred.numel() // (B * n)
+    out = torch.empty(3 + 2 * n, dtype=torch.float32, device=pred.device)
+    nws = int(lib.load().ffpn_mix_loss_workspace_bytes(n))
+    ws = torch.empty(nws, dtype=torch.uint8, device=pred.device)
+    lib.call('ffpn_mix_loss_fwd', _dev(pred), B, n, EW, _ptr(pred), _ptr(mask), _ptr(ws), nws, _ptr(out), _stream(pred))
+    return out
+
+
+def mix_loss_bwd(pred, mask, stats, grad_scale):
+    B, n = pred.shape[0], pred.shape[1]
+    EW = pred.numel() // (B * n)
+    dpred = torch.empty_like(pred)
+    lib.call('ffpn_mix_loss_bwd', _dev(pred), B, n, EW, _ptr(pred), _ptr(mask), _ptr(stats), _ptr(grad_scale), _ptr(dpred),
+             _stream(pred))
+    return dpred
 
 
 def pack_volume(src, dtype):

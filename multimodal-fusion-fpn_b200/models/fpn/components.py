@@ -212,9 +212,13 @@ class MaxPool2d(nn.MaxPool2d):
 
 
 class HeadConv3d(nn.Conv3d):
-    """final1: Conv3d(C -> n_classes, 1x1x1, bias) producing fp32 logits (reference fusion3D2D.py:223)."""
+    """final1: Conv3d(C -> n_classes, 1x1x1, bias) producing fp32 logits (reference fusion3D2D.py:223).  A task wrapper
+    whose ``last_activation`` is the stock sigmoid sets ``fused_activation = 'sigmoid'`` for the duration of its forward: the
+    same kernel then emits the prediction (``fusion_nets.py:110,118``), and the backward folds p(1-p) in."""
+
+    fused_activation = None
 
     def forward(self, input):
         if FF.k3(self.kernel_size) != (1, 1, 1):
             raise NotImplementedError('the head kernel is 1x1x1')
-        return FF.HeadFunction.apply(input, self.weight, self.bias)
+        return FF.HeadFunction.apply(input, self.weight, self.bias, self.fused_activation)

@@ -33,6 +33,24 @@ class FPNConfig(nn.Module):
             self.config.read(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fpn', _INI + '.ini'))
 
 
+class _fused_sigmoid:
+    """Context: run ``head`` (a HeadConv3d) with the sigmoid fused in when ``wrapper`` still has the stock sigmoid
+    ``last_activation`` (the Regression subclasses override it) -> ``.on`` tells the caller to skip its own activation."""
+
+    def __init__(self, wrapper, stock, head):
+        self.head = head
+        self.on = head is not None and FF.head_activation_fused() and type(wrapper).last_activation is stock
+
+    def __enter__(self):
+        if self.on:
+            self.head.fused_activation = 'sigmoid'
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.head.fused_activation = None
+
+
 def _interpolate_mode():
     """config.crop -> how 2-D features reach the en-face grid (reference :102-107)."""
     mode = '2d' if 'relative_2d' in config.crop else None
@@ -51,8 +69,9 @@ class FPN(FPNConfig):
 
     def forward(self, x):
         oct = x['image'].permute(0, 1, 2, 4, 3)               # (B,1,S,H,W) -> Z x W x H
-        seg = self.resensnet(oct).permute(0, 1, 2, 4, 3)
-        return {'prediction': self.last_activation(seg)}
+        with _fused_sigmoid(self, FPN.last_activation, self.resensnet.final1 if self.resensnet.use_1x1 else None) as f:
+            seg = self.resensnet(oct).permute(0, 1, 2, 4, 3)
+        return {'prediction': seg if f.on else self.last_activation(seg)}
 
 
 @add_class
@@ -96,8 +115,9 @@ class FPNHybridFusion(FPNConfig):
     def forward(self, x):
         oct = x['image'].permute(0, 1, 2, 4, 3)               # Z x W x H
         slo = x[config.fusion_modality][:, :, :, 0, :]
-        seg = self.resensnet(oct, slo).permute(0, 1, 2, 4, 3)
-        return {'prediction': self.last_activation(seg)}
+        with _fused_sigmoid(self, FPNHybridFusion.last_activation, self.resensnet.final1) as f:
+            seg = self.resensnet(oct, slo).permute(0, 1, 2, 4, 3)
+        return {'prediction': seg if f.on else self.last_activation(seg)}
 
 
 @add_class
@@ -113,7 +133,14 @@ class FPN2D(FPNConfig):
 
     def forward(self, x):
         fused = x[config.fusion_modality][:, :, :, 0, :]
-        seg = torch.sigmoid(self.resensnet(fused).permute(0, 1, 2, 4, 3))
+        head = self.resensnet.final1[0]
+        head.fused_activation = 'sigmoid' if FF.head_activation_fused() else None
+        try:
+            seg = self.resensnet(fused).permute(0, 1, 2, 4, 3)
+        finally:
+            head.fused_activation = None
+        if not FF.head_activation_fused():
+            seg = torch.sigmoid(seg)
         if seg.shape != x['mask'].shape:
             seg = F.interpolate(seg, size=x['mask'].shape[2:], mode='trilinear')
         return {'prediction': seg}
@@ -140,12 +167,13 @@ class FPNLateFusion(FPNConfig):
         fused = x[config.fusion_modality][:, :, :, 0, :]
         f2d = self.resensnet2d(fused)                          # (B,16,S',W',1)
         f2d = FF.Resize2DFunction.apply(f2d[:, :, :, :, 0], tuple(oct_feat.shape[2:4]), self.interpolate)
-        seg = self.fuse_features(oct_feat, f2d)
-        return {'prediction': self.last_activation(seg)}
+        fuse = FF.head_activation_fused() and type(self).last_activation is FPNLateFusion.last_activation
+        seg = self.fuse_features(oct_feat, f2d, 'sigmoid' if fuse else None)
+        return {'prediction': seg if fuse else self.last_activation(seg)}
 
-    def fuse_features(self, oct_seg: Tensor, fused_seg: Tensor):
+    def fuse_features(self, oct_seg: Tensor, fused_seg: Tensor, act=None):
         cat = FF.CatFunction.apply(oct_seg, fused_seg)
-        seg = FF.HeadFunction.apply(cat, self.fusion_module.weight, self.fusion_module.bias)
+        seg = FF.HeadFunction.apply(cat, self.fusion_module.weight, self.fusion_module.bias, act)
         return seg.permute(0, 1, 2, 4, 3)
 
 

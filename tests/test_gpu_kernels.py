@@ -286,6 +286,55 @@ def test_proj_tail_and_head(ops, dt):
     dx, dw, db = ops.head_bwd(phys(x.cuda()).to(dt), w.cuda(), dl.cuda())
     assert rel(logical(dx.float()).cpu(), xr.grad) <= tol(dt)
     assert rel(dw.cpu(), wr.grad) <= 1e-5 and rel(db.cpu(), br.grad) <= 1e-5
+    # head with the wrappers' sigmoid fused in (fusion_nets.py:110,118), forward and backward
+    xr.grad = wr.grad = br.grad = None
+    refp = torch.sigmoid(F.conv3d(xr, wr, br))
+    pred = ops.head_fwd(phys(x.cuda()).to(dt), w.cuda(), bias.cuda(), act=1)
+    assert rel(pred.cpu(), refp.detach()) <= 1e-6
+    refp.backward(dl)
+    dx, dw, db = ops.head_bwd(phys(x.cuda()).to(dt), w.cuda(), dl.cuda(), pred)
+    assert rel(logical(dx.float()).cpu(), xr.grad) <= tol(dt)
+    assert rel(dw.cpu(), wr.grad) <= 1e-5 and rel(db.cpu(), br.grad) <= 1e-5
+    # a head over more positions than one reduction block handles (two-stage weight-gradient reduction), run-to-run identical
+    x2 = torch.randn(3, C, 40, 64, 1, generator=g).to(dt).float()
+    dl2 = torch.randn(3, n, 40, 64, 1, generator=g)
+    xr2, wr2, br2 = x2.clone().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    F.conv3d(xr2, wr2, br2).backward(dl2)
+    r1 = ops.head_bwd(phys(x2.cuda()).to(dt), w.cuda(), dl2.cuda())
+    r2 = ops.head_bwd(phys(x2.cuda()).to(dt), w.cuda(), dl2.cuda())
+    assert rel(r1[1].cpu(), wr2.grad) <= 1e-5 and rel(r1[2].cpu(), br2.grad) <= 1e-5
+    assert torch.equal(r1[1], r2[1]) and torch.equal(r1[2], r2[2])
+
+
+@pytest.mark.parametrize('n', [1, 3])
+def test_fused_mix_loss_matches_oracle(ops, mirror, n):
+    """Mix({Dice_loss_jointv2, BCE_Lossv2}) (common/loss.py:9-90) as three kernels: value and gradient against the oracle's
+    restatement to 1e-6, the reference-shaped Mix module takes the fused path on CUDA tensors, saturated predictions hit
+    torch's clamps (log >= -100, p(1-p) >= 1e-12)."""
+    from oracle import fusion_fpn_oracle as O
+    g = torch.Generator().manual_seed(23 + n)
+    pred = torch.rand(4, n, 16, 1, 64, generator=g)
+    pred[0, 0, 0, 0, :4] = torch.tensor([0.0, 1.0, 1e-30, 1 - 1e-7])
+    mask = (torch.rand(4, n, 16, 1, 64, generator=g) > 0.5).float()
+    pr = pred.clone().requires_grad_(True)
+    ref = O.mix_loss(pr, mask)
+    (ref * 0.5).backward()
+    crit = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask'),
+                            'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
+    pc = pred.clone().cuda().requires_grad_(True)
+    n0 = __import__('ffpn').lib.launch_count(0)
+    total, parts = crit({'mask': mask.cuda()}, {'prediction': pc})
+    (total * 0.5).backward()
+    torch.cuda.synchronize()
+    assert __import__('ffpn').lib.launch_count(0) - n0 == 3            # partial sums, finalize, backward
+    assert abs(total.item() - ref.item()) <= 1e-6
+    assert abs(parts['Dice'].item() - O.dice_loss(pred, mask).item()) <= 1e-6
+    assert abs(parts['BCE'].item() - O.bce_loss(pred, mask).item()) <= 1e-6 * max(1.0, O.bce_loss(pred, mask).item())
+    assert torch.allclose(pc.grad.cpu(), pr.grad, rtol=1e-5, atol=1e-9)
+    # generic path (not the training pair): unchanged semantics
+    only = mirror.loss.Mix({'Dice': mirror.loss.Dice_loss_jointv2('prediction', 'mask')})
+    t2, _ = only({'mask': mask.cuda()}, {'prediction': pred.cuda()})
+    assert abs(t2.item() - O.dice_loss(pred, mask).item()) <= 1e-6
 
 
 def test_pack_volume_and_sgd(ops):

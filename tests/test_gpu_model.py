@@ -45,8 +45,14 @@ def _run(mirror, sd, batch, crop, train=True, acts=None):
     hooks = []
     if acts is not None:
         import stagehooks
+        from ffpn import functional as FF
         a, hooks = stagehooks.attach(model.resensnet)
-    out = model(cb)
+        FF.fuse_head_activation(False)                  # the hook on final1 must see logits, like the reference's
+    try:
+        out = model(cb)
+    finally:
+        if acts is not None:
+            FF.fuse_head_activation(True)
     for h in hooks:
         h.remove()
     if acts is not None:
@@ -484,3 +490,21 @@ def test_fused_finalize_is_safe_with_branch_streams(mirror):
         l1, g1, b1 = _trainer_grads(mirror, sd, batch, {'FFPN_STREAMS': '1', 'FFPN_FUSED_FIN': '1'})
         assert l1 == l0 and torch.equal(g1, g0)
         assert all(torch.equal(b1[k], b0[k]) for k in b0)
+
+
+def test_fused_head_activation_equals_separate_sigmoid(mirror):
+    """final1 + sigmoid in one kernel (default) against final1 -> torch.sigmoid: same prediction, same gradients."""
+    from ffpn import functional as FF
+    sd = O.make_state_dict(seed=51)
+    batch = O.synthetic_batch(2, 4, 64, 32, 16, 32, seed=5)
+    res = []
+    for fused in (True, False):
+        FF.fuse_head_activation(fused)
+        try:
+            model, cb, out = _run(mirror, sd, batch, 'relative_2d_max')
+            _loss(mirror, cb, out).backward()
+        finally:
+            FF.fuse_head_activation(True)
+        res.append((out['prediction'].detach().clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters()])))
+    assert rel(res[0][0], res[1][0]) <= 1e-6
+    assert rel(res[0][1], res[1][1]) <= 1e-5
