@@ -111,6 +111,50 @@ def to_phys(x: torch.Tensor) -> torch.Tensor:
     return p
 
 
+class CatSlot:
+    """A channel slice [coff, coff + C) of a pre-allocated concat buffer (physical (B, S, W, 1, Ctot)).  The producers of a
+    decoder level's inputs -- the projection tail, the 2-D feature resize, the nearest upsample of the deeper level -- write
+    their result straight into their slot, so ``torch.cat([proj3D, feat2D, up], 1)`` (fusion3D2D.py:572,966) is never executed
+    as a copy; in backward the consumers' gradient is read back slice by slice, in place."""
+
+    def __init__(self, buf: torch.Tensor, coff: int, C: int):
+        self.buf, self.coff, self.C = buf, int(coff), int(C)
+
+    def view(self) -> torch.Tensor:
+        """Logical (B, C, S, W, 1) view of the slot (channel-strided, no copy), tagged so that UpCat/Cat recognise it."""
+        return to_logical(self.buf[..., self.coff:self.coff + self.C], 5)
+
+
+def tag_slot(t: torch.Tensor, slot):
+    """Mark ``t`` (the tensor an autograd Function returned for a slot) so that cat()/upcat() recognise it as already in place."""
+    if slot is not None:
+        t._ffpn_slot = slot
+    return t
+
+
+def resize2d(x, size, mode, slot=None):
+    """2-D feature -> en-face grid (fusion3D2D.py:544-564), optionally straight into a concat slot."""
+    return tag_slot(Resize2DFunction.apply(x, size, mode, slot), slot)
+
+
+def new_cat_buffer(like_phys_shape, Ctot: int, dtype, device) -> torch.Tensor:
+    B, S, W = like_phys_shape[0], like_phys_shape[1], like_phys_shape[2]
+    return torch.empty((B, S, W, 1, Ctot), dtype=dtype, device=device)
+
+
+def phys_slice(x: torch.Tensor):
+    """logical (B,C,S,W,1) tensor that is either channels-last contiguous or a channel slice of a wider channels-last tensor
+    -> (physical tensor to hand to a kernel, row stride in elements or None when contiguous).  Anything else is made
+    contiguous (boundary case)."""
+    p = x.permute(0, 2, 3, 4, 1)
+    if p.dtype == _COMPUTE_DTYPE and p.shape[3] == 1 and p.stride(4) == 1 and not p.is_contiguous():
+        ct = p.stride(2)
+        if ct >= p.shape[4] and p.stride(1) == p.shape[2] * ct and p.stride(0) == p.shape[1] * p.shape[2] * ct \
+                and (p.storage_offset() * p.element_size()) % 16 == 0 and ct % 8 == 0:
+            return p, ct
+    return to_phys(x), None
+
+
 def to_logical(p: torch.Tensor, ndim: int) -> torch.Tensor:
     if ndim == 5:
         return p.permute(0, 4, 1, 2, 3)
@@ -142,6 +186,7 @@ class ConvXSpec:
     eps: float
     need_dx: bool
     ndim: int
+    out: Optional[object] = None     # CatSlot: tail == 'mean' writes the projected map straight into a concat buffer
 
 
 def _wgrad(inp, dy, w_shape, kernel, stride, pad, a_in, b_in, relu, out):
@@ -187,7 +232,11 @@ class ConvXFunction(torch.autograd.Function):
         zp = None
         if spec.tail == 'mean':
             assert not spec.residual and spec.pool is None
-            z = ops.proj_tail_fwd(ys[-1], a, b)
+            if spec.out is not None:
+                ops.proj_tail_fwd(ys[-1], a, b, out=spec.out.buf, coff=spec.out.coff)
+                z = None
+            else:
+                z = ops.proj_tail_fwd(ys[-1], a, b)
         else:
             if spec.residual:
                 z = ops.block_end_fwd(ys[-1], a, b, yd if yd is not None else xp, None if affd is None else affd[0],
@@ -199,11 +248,13 @@ class ConvXFunction(torch.autograd.Function):
         ctx.spec = spec
         ctx.x_shape = tuple(xp.shape)
         ctx.nt = len(tensors)
-        flat = [xp, z] + ys + [t for aff in affs for t in aff]
+        flat = [xp, z if z is not None else xp] + ys + [t for aff in affs for t in aff]     # (the mean tail's backward does not read z)
         if yd is not None:
             flat += [yd] + list(affd)
         ctx.save_for_backward(*flat, *tensors)
         ctx.nflat = len(flat)
+        if z is None:
+            return spec.out.view()
         zl = to_logical(z, spec.ndim)
         if spec.pool is not None:
             return zl, to_logical(zp, spec.ndim)
@@ -224,7 +275,11 @@ class ConvXFunction(torch.autograd.Function):
             affd = flat[3 + 5 * k: 7 + 5 * k]
         grads = [None] * ctx.nt
         dzp_p = to_phys(dzp) if dzp is not None else None
-        dz_p = to_phys(dz) if dz is not None else None
+        dz_stride = None
+        if spec.tail == 'mean':
+            dz_p, dz_stride = phys_slice(dz)           # the gradient of a concat buffer's slice is read in place
+        else:
+            dz_p = to_phys(dz) if dz is not None else None
         y_last = ys[-1]
         # eval mode: BatchNorm normalised with the running statistics, which do not depend on the batch -> its backward is
         # dy = g * gamma * invstd without the batch-statistics terms.  The coefficients cP, cQ are proportional to 1/count, so
@@ -233,7 +288,7 @@ class ConvXFunction(torch.autograd.Function):
         count = y_last.numel() // y_last.shape[-1] if spec.training else inf
         g_last = tensors[5 * (k - 1) + 1]
         if spec.tail == 'mean':
-            dA = ops.proj_tail_bwd(dz_p, y_last.shape)
+            dA = ops.proj_tail_bwd(dz_p, y_last.shape, ostride=dz_stride)
             partial, rows = ops.bn_bwd_reduce(dA, y_last, affs[-1][0], affs[-1][1], True)
             dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, 2, 1, count, g_last, affs[-1][2], affs[-1][3],
                                                      _sink(g_last), _sink(tensors[5 * (k - 1) + 2]))
@@ -329,66 +384,121 @@ class Resize2DFunction(torch.autograd.Function):
     (fusion3D2D.py:544-564).  Input (B,C,S',W') logical; output (B,C,S,W,1)."""
 
     @staticmethod
-    def forward(ctx, x, size, mode):
+    def forward(ctx, x, size, mode, slot=None):
         xp = to_phys(x)
-        out, idx = ops.resize2d_fwd(xp, int(size[0]), int(size[1]), mode)
         ctx.mode, ctx.x_shape, ctx.in_ndim = mode, tuple(xp.shape), x.dim()
+        if slot is not None:
+            _, idx = ops.resize2d_fwd(xp, int(size[0]), int(size[1]), mode, out=slot.buf, coff=slot.coff)
+            ctx.save_for_backward(idx if idx is not None else torch.empty(0, device=xp.device))
+            return slot.view()
+        out, idx = ops.resize2d_fwd(xp, int(size[0]), int(size[1]), mode)
         ctx.save_for_backward(idx if idx is not None else torch.empty(0, device=xp.device))
         return to_logical(out, 5)
 
     @staticmethod
     def backward(ctx, dout):
         (idx,) = ctx.saved_tensors
-        dx = ops.resize2d_bwd(to_phys(dout), ctx.x_shape, ctx.mode, idx if idx.numel() else None)
-        return to_logical(dx, ctx.in_ndim), None, None
+        dp, stride = phys_slice(dout)
+        dx = ops.resize2d_bwd(dp, ctx.x_shape, ctx.mode, idx if idx.numel() else None, ostride=stride)
+        return to_logical(dx, ctx.in_ndim), None, None, None
+
+
+def _slots_in_place(tensors, buf, first_off=0):
+    """True when every tensor is the tagged view of consecutive slots of ``buf`` starting at channel ``first_off``."""
+    off = first_off
+    for t in tensors:
+        slot = getattr(t, '_ffpn_slot', None)
+        if slot is None or slot.buf is not buf or slot.coff != off or t.shape[1] != slot.C:
+            return False
+        off += slot.C
+    return True
+
+
+def common_cat_buffer(tensors):
+    """The first CatSlot of the concat buffer shared by all of ``tensors`` if each is the tagged view of consecutive slots from
+    channel 0, else None."""
+    slot = getattr(tensors[0], '_ffpn_slot', None) if tensors else None
+    if slot is None or not _slots_in_place(tensors, slot.buf):
+        return None
+    return slot
+
+
+def _slice_grads(dc, shapes, in_place):
+    """Gradient of the leading concat members: channel-slice VIEWS of dc when the producers read them in place, else copies."""
+    outs, off = [], 0
+    for sh in shapes:
+        if in_place:
+            outs.append(to_logical(dc[..., off:off + sh[-1]], 5))
+        else:
+            g = torch.empty(sh, dtype=dc.dtype, device=dc.device)
+            ops.slice_copy(dc, off, g, 0, sh[-1])
+            outs.append(to_logical(g, 5))
+        off += sh[-1]
+    return outs, off
 
 
 class UpCatFunction(torch.autograd.Function):
-    """Upsample_Custom3d_nearest(deeper) and torch.cat([skip..., up], 1) (fusion3D2D.py:956-966,
-    components.py:72-76, :259-268) written straight into one concat buffer."""
+    """Upsample_Custom3d_nearest(deeper) and torch.cat([skip..., up], 1) (fusion3D2D.py:956-966, components.py:72-76,
+    :259-268).  ``buf``: the level's pre-allocated concat buffer whose leading slots the skips' producers have ALREADY filled
+    (CatSlot) -- then only the upsample runs, into the last slot, and the backward hands the skips' gradients out as views.
+    Without it the skips are copied into a fresh buffer."""
 
     @staticmethod
-    def forward(ctx, factor, deeper, *skips):
+    def forward(ctx, factor, deeper, holder, *skips):
+        buf = holder.buf if holder is not None else None      # a CatSlot (plain object): the buffer is not an autograd input
         dp = to_phys(deeper)
-        sp = [to_phys(s) for s in skips]
         fS, fW = int(factor[0]), int(factor[1])
         B, Si, Wi, H, Cd = dp.shape
         if H != 1 or int(factor[2]) != 1:
             raise ValueError('the decoder upsamples en-face maps only (depth 1, factor (fS, fW, 1))')
         So, Wo = Si * fS, Wi * fW
-        for s in sp:
-            if tuple(s.shape[:4]) != (B, So, Wo, 1):
-                raise RuntimeError(f'Sizes of tensors must match except in dimension 1: skip {tuple(s.shape)} vs '
-                                   f'upsampled {(B, So, Wo, 1, Cd)}')
-        Ctot = sum(s.shape[-1] for s in sp) + Cd
-        cat = torch.empty((B, So, Wo, 1, Ctot), dtype=dp.dtype, device=dp.device)
-        off = 0
-        for s in sp:
-            ops.slice_copy(s, 0, cat, off, s.shape[-1])
-            off += s.shape[-1]
+        in_place = buf is not None
+        if in_place:
+            sshapes = [(B, So, Wo, 1, int(s.shape[1])) for s in skips]
+            for s in skips:
+                if tuple(s.shape) != (B, s.shape[1], So, Wo, 1):
+                    raise RuntimeError(f'Sizes of tensors must match except in dimension 1: skip {tuple(s.shape)} vs '
+                                       f'upsampled {(B, Cd, So, Wo, 1)}')
+            off = sum(sh[-1] for sh in sshapes)
+            if tuple(buf.shape) != (B, So, Wo, 1, off + Cd):
+                raise RuntimeError(f'concat buffer {tuple(buf.shape)} does not fit {(B, So, Wo, 1, off + Cd)}')
+            cat = buf
+        else:
+            sp = [to_phys(s) for s in skips]
+            for s in sp:
+                if tuple(s.shape[:4]) != (B, So, Wo, 1):
+                    raise RuntimeError(f'Sizes of tensors must match except in dimension 1: skip {tuple(s.shape)} vs '
+                                       f'upsampled {(B, So, Wo, 1, Cd)}')
+            sshapes = [tuple(s.shape) for s in sp]
+            cat = torch.empty((B, So, Wo, 1, sum(s.shape[-1] for s in sp) + Cd), dtype=dp.dtype, device=dp.device)
+            off = 0
+            for s in sp:
+                ops.slice_copy(s, 0, cat, off, s.shape[-1])
+                off += s.shape[-1]
         ops.upsample_fwd(dp, fS, fW, out=cat, coff=off)
-        ctx.meta = (fS, fW, tuple(dp.shape), [tuple(s.shape) for s in sp])
+        ctx.meta = (fS, fW, tuple(dp.shape), sshapes, in_place)
         return to_logical(cat, 5)
 
     @staticmethod
     def backward(ctx, dcat):
-        fS, fW, dshape, sshapes = ctx.meta
+        fS, fW, dshape, sshapes, in_place = ctx.meta
         dc = to_phys(dcat)
-        outs, off = [], 0
-        for sh in sshapes:
-            g = torch.empty(sh, dtype=dc.dtype, device=dc.device)
-            ops.slice_copy(dc, off, g, 0, sh[-1])
-            outs.append(to_logical(g, 5))
-            off += sh[-1]
+        outs, off = _slice_grads(dc, sshapes, in_place)
         dd = ops.upsample_bwd(dc, dshape, fS, fW, coff=off)
-        return (None, to_logical(dd, 5)) + tuple(outs)
+        return (None, to_logical(dd, 5), None) + tuple(outs)
 
 
 class CatFunction(torch.autograd.Function):
-    """torch.cat(tensors, 1) for channels-last en-face maps (fusion3D2D.py:572)."""
+    """torch.cat(tensors, 1) for channels-last en-face maps (fusion3D2D.py:572).  ``buf``: see UpCatFunction (all members
+    already in place -> no kernel at all)."""
 
     @staticmethod
-    def forward(ctx, *xs):
+    def forward(ctx, holder, *xs):
+        buf = holder.buf if holder is not None else None
+        if buf is not None:
+            ctx.shapes = [tuple(buf.shape[:4]) + (int(x.shape[1]),) for x in xs]
+            ctx.in_place = True
+            return to_logical(buf, 5)
         ps = [to_phys(x) for x in xs]
         Ctot = sum(p.shape[-1] for p in ps)
         cat = torch.empty(tuple(ps[0].shape[:4]) + (Ctot,), dtype=ps[0].dtype, device=ps[0].device)
@@ -399,18 +509,23 @@ class CatFunction(torch.autograd.Function):
             ops.slice_copy(p, 0, cat, off, p.shape[-1])
             off += p.shape[-1]
         ctx.shapes = [tuple(p.shape) for p in ps]
+        ctx.in_place = False
         return to_logical(cat, 5)
 
     @staticmethod
     def backward(ctx, dcat):
-        dc = to_phys(dcat)
-        outs, off = [], 0
-        for sh in ctx.shapes:
-            g = torch.empty(sh, dtype=dc.dtype, device=dc.device)
-            ops.slice_copy(dc, off, g, 0, sh[-1])
-            outs.append(to_logical(g, 5))
-            off += sh[-1]
-        return tuple(outs)
+        outs, _ = _slice_grads(to_phys(dcat), ctx.shapes, ctx.in_place)
+        return (None,) + tuple(outs)
+
+
+def cat(*xs):
+    """torch.cat(xs, 1); free when the members are the consecutive slots of one concat buffer."""
+    return CatFunction.apply(common_cat_buffer(xs), *xs)
+
+
+def upcat(factor, deeper, *skips):
+    """cat([*skips, upsample(deeper)], 1); the skips are not copied when they are the leading slots of one concat buffer."""
+    return UpCatFunction.apply(factor, deeper, common_cat_buffer(skips) if skips else None, *skips)
 
 
 _FUSE_HEAD_ACT = True

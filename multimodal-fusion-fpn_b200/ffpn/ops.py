@@ -219,11 +219,13 @@ def proj_tail_fwd(y, a, b, out=None, coff=0):
     return out
 
 
-def proj_tail_bwd(dout, y_shape, coff=0):
+def proj_tail_bwd(dout, y_shape, coff=0, ostride=None):
+    """dout: (B,S,W,1,C) contiguous, or (``ostride`` given) a channel slice of a wider channels-last tensor whose rows are
+    ``ostride`` elements apart (read in place, no copy)."""
     B, S, W, H, C_ = y_shape
     dA = torch.empty(tuple(y_shape), dtype=dout.dtype, device=dout.device)
-    lib.call('ffpn_proj_tail_bwd', _dev(dout), lib.dtype_code(dout.dtype), B * S * W, H, C_, _ptr(dout), dout.shape[-1], coff,
-             _ptr(dA), _stream(dout))
+    lib.call('ffpn_proj_tail_bwd', _dev(dout), lib.dtype_code(dout.dtype), B * S * W, H, C_, _ptr(dout),
+             dout.shape[-1] if ostride is None else ostride, coff, _ptr(dA), _stream(dout))
     return dA
 
 
@@ -242,12 +244,12 @@ def resize2d_fwd(x, So, Wo, mode, out=None, coff=0):
     return out, idx
 
 
-def resize2d_bwd(dout, x_shape, mode, idx, coff=0):
+def resize2d_bwd(dout, x_shape, mode, idx, coff=0, ostride=None):
     B, Si, Wi, _, C_ = x_shape
     So, Wo = dout.shape[1], dout.shape[2]
     dx = torch.empty(tuple(x_shape), dtype=dout.dtype, device=dout.device)
     lib.call('ffpn_resize2d_bwd', _dev(dout), lib.dtype_code(dout.dtype), RESIZE_MODES[mode], B, Si, Wi, So, Wo, C_,
-             _ptr(dout), dout.shape[-1], coff, _ptr(idx), _ptr(dx), _stream(dout))
+             _ptr(dout), dout.shape[-1] if ostride is None else ostride, coff, _ptr(idx), _ptr(dx), _stream(dout))
     return dx
 
 

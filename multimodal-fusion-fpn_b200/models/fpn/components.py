@@ -68,9 +68,10 @@ class ConvXBase(nn.Module):
             bns.append(self.downsample[1])
         return bns
 
-    def forward(self, x, pool=None, tail='relu', need_dx=True):
+    def forward(self, x, pool=None, tail='relu', need_dx=True, out=None):
         """``pool``: a MaxPool module to fuse behind the block (returns ``(out, pooled)``);
-        ``tail='mean'``: fuse the projection's BN+ReLU+mean(dim=4) (returns the (B,C,S,W,1) mean)."""
+        ``tail='mean'``: fuse the projection's BN+ReLU+mean(dim=4) (returns the (B,C,S,W,1) mean), written straight into
+        the concat slot ``out`` (ffpn.functional.CatSlot) when one is given."""
         if not self._is_batchnorm:
             raise NotImplementedError('is-batchnorm=False has no CUDA path (the reference .ini pins is-batchnorm=True)')
         if self.drop is not None:
@@ -92,10 +93,11 @@ class ConvXBase(nn.Module):
             pads=tuple(FF.p3(c.padding) for c in convs), residual=bool(self.is_residual), has_ds=has_ds,
             ds_stride=ds_stride, pool=None if pool is None else FF.k3(pool.kernel_size), tail=tail,
             training=self.training, momentum=0.1 if bn0.momentum is None else float(bn0.momentum), eps=float(bn0.eps),
-            need_dx=bool(need_dx and x.requires_grad), ndim=x.dim())
+            need_dx=bool(need_dx and x.requires_grad), ndim=x.dim(), out=out if tail == 'mean' else None)
         if self.training and not self._nbt_managed:
             torch._foreach_add_([b.num_batches_tracked for b in self._bn_modules()], 1)
-        return FF.ConvXFunction.apply(spec, x, *tensors)
+        res = FF.ConvXFunction.apply(spec, x, *tensors)
+        return FF.tag_slot(res, spec.out) if spec.out is not None else res
 
 
 class unet3dConvX(ConvXBase):
@@ -134,7 +136,7 @@ class unet3dUp2modified(nn.Module):
     def _cat(self, skips, deeper):
         if not isinstance(self.up, Upsample_Custom3d_nearest):
             raise NotImplementedError('is-deconv=True has no CUDA path (shape-inconsistent in the reference too)')
-        return FF.UpCatFunction.apply(self.up.int_factor(), deeper, *skips)
+        return FF.upcat(self.up.int_factor(), deeper, *skips)
 
     def forward(self, inputs1, inputs2):
         return self.conv(self._cat([inputs1], inputs2))
@@ -166,7 +168,7 @@ class Upsample_Custom3d_nearest(nn.Module):
         if f[2] != 1 or input.shape[-1] != 1:
             raise NotImplementedError('the CUDA path upsamples en-face maps (depth 1) only')
         # idx = ceil((i+1)/f) - 1 == i // f for integer f: identical to the reference's gather
-        return FF.UpCatFunction.apply(f, input)
+        return FF.upcat(f, input)
 
     def __repr__(self):
         info = 'scale_factor=' + str(self.scale_factor) if self.scale_factor is not None else 'size=' + str(self.size)
@@ -184,7 +186,7 @@ class Upsample_Custom2d_nearest(nn.Module):
 
     def forward(self, input):
         f = tuple(int(v) for v in self.scale_factor)
-        out = FF.UpCatFunction.apply((f[0], f[1], 1), input[:, :, :, :, None])
+        out = FF.upcat((f[0], f[1], 1), input[:, :, :, :, None])
         return out[:, :, :, :, 0]
 
     def __repr__(self):

@@ -196,19 +196,49 @@ class ModifiedUnet3D2D(SegmentationNetwork):
             feats.append(f)
         return feats
 
-    def _project(self, feat, l, take_mean=True):
-        """zdimRed<l> then torch.mean(dim=4, keepdim=True); the mean is fused into the last block's tail."""
+    def _project(self, feat, l, take_mean=True, slot=None):
+        """zdimRed<l> then torch.mean(dim=4, keepdim=True); the mean is fused into the last block's tail and written
+        straight into ``slot`` (a concat buffer's channel slice) when one is given."""
         seq = getattr(self, f'zdimRed{l}')
         x = feat
         for blk in list(seq)[:-1]:
             x = blk(x)
-        return seq[-1](x, tail='mean' if take_mean else 'relu')
+        return seq[-1](x, tail='mean' if take_mean else 'relu', out=slot if take_mean else None)
 
-    def _resize_2d(self, f2d, like):
-        """conv_2d[:,:,:,:,None] then None | trilinear | adaptive max to the en-face grid of ``like``."""
-        return FF.Resize2DFunction.apply(f2d, tuple(like.shape[2:4]), self.interpolate)
+    def _resize_2d(self, f2d, size, slot=None):
+        """conv_2d[:,:,:,:,None] then None | trilinear | adaptive max to the en-face grid ``size``."""
+        return FF.resize2d(f2d, tuple(size), self.interpolate, slot)
 
-    def _decode(self, proj, r2d, deeper):
+    def _cat_slots(self, oct, levels2d):
+        """Concat buffers of the decoder, allocated up front: level l holds [projected conv_l | resized conv_l_2d | upsampled
+        deeper level] (fusion3D2D.py:956-966), level 5 of the Level5 body [conv5 | conv5_2d] (:572).  Their producers write
+        into the slots, so no ``cat`` copy and no stand-alone projected tensor exist.  -> {level: (slot3d, slot2d)} and the
+        en-face size per level; None for feature_fusion='add' (the sum is a new tensor)."""
+        B, _, S, W, _H = oct.shape
+        ch = self.channels
+        sizes = [(S, W), (S, W // 2), (S, W // 4), (S // 2, W // 8), (S // 4, W // 16)]
+        if self.feature_fusion != 'concat' or not oct.is_cuda:
+            return None, sizes
+        dt = FF.get_compute_dtype()
+        slots = {}
+        for l in (1, 2, 3, 4):
+            deeper = ch[l] * (2 if (l == 4 and levels2d == 5) else 1)
+            buf = torch.empty((B, sizes[l - 1][0], sizes[l - 1][1], 1, 2 * ch[l - 1] + deeper), dtype=dt, device=oct.device)
+            slots[l] = (FF.CatSlot(buf, 0, ch[l - 1]), FF.CatSlot(buf, ch[l - 1], ch[l - 1]))
+        if levels2d == 5:
+            buf = torch.empty((B, sizes[4][0], sizes[4][1], 1, 2 * ch[4]), dtype=dt, device=oct.device)
+            slots[5] = (FF.CatSlot(buf, 0, ch[4]), FF.CatSlot(buf, ch[4], ch[4]))
+        return slots, sizes
+
+    def _forward_serial(self, oct, slo, levels2d):
+        slots, sizes = self._cat_slots(oct, levels2d)
+        s3 = (lambda l: slots[l][0] if slots and l in slots else None)
+        s2 = (lambda l: slots[l][1] if slots and l in slots else None)
+        f2d = self._encode_2d(slo, levels2d)
+        f3d = self._encode_3d(oct)
+        proj = [self._project(f3d[l - 1], l, slot=s3(l)) for l in range(1, 6)]
+        r2d = [self._resize_2d(f2d[l], sizes[l], s2(l + 1)) for l in range(levels2d)]
+        deeper = FF.cat(proj[4], r2d[4]) if levels2d == 5 else proj[4]
         for l in (4, 3, 2, 1):
             deeper = getattr(self, f'up_concat{l}')(proj[l - 1], r2d[l - 1], deeper)
         return self.final1(deeper)
@@ -218,26 +248,27 @@ class ModifiedUnet3D2D(SegmentationNetwork):
         on its own, the 3-D encoder -> level-5 projection -> decoder chain on the caller's stream.  Each up block waits
         only for the two skips it reads, so the large level-1 projection overlaps the deep (latency-bound) levels."""
         dev = oct.device
+        slots, sizes = self._cat_slots(oct, levels2d)       # before any fork: every stream below is ordered after the allocation
+        s3 = (lambda l: slots[l][0] if slots and l in slots else None)
+        s2 = (lambda l: slots[l][1] if slots and l in slots else None)
         s2d = FF.fork(FF.side_stream(dev, 0), slo)
         with torch.cuda.stream(s2d):
             f2d = self._encode_2d(slo, levels2d)
+            r2d = [self._resize_2d(f2d[l], sizes[l], s2(l + 1)) for l in range(levels2d)]
         proj, x = [None] * 5, FF.pack_oct(oct)
-        shapes = []
         for l in range(1, 6):
             f, x = self._level(getattr(self, f'conv{l}'), x, getattr(self, f'pool{l}') if l < 5 else None)
             if l < 5:
                 sp = FF.fork(FF.side_stream(dev, l), f)
                 with torch.cuda.stream(sp):
-                    proj[l - 1] = self._project(f, l)
+                    proj[l - 1] = self._project(f, l, slot=s3(l))
             else:
-                proj[4] = self._project(f, 5)
-            shapes.append(tuple(proj[l - 1].shape[2:4]))
-        with torch.cuda.stream(s2d):
-            r2d = [FF.Resize2DFunction.apply(f2d[l], shapes[l], self.interpolate) for l in range(levels2d)]
+                proj[4] = self._project(f, 5, slot=s3(5))
+            assert tuple(proj[l - 1].shape[2:4]) == sizes[l - 1], (tuple(proj[l - 1].shape), sizes[l - 1])
         deeper = proj[4]
         if levels2d == 5:
             FF.join(s2d, r2d[4])
-            deeper = FF.CatFunction.apply(proj[4], r2d[4])
+            deeper = FF.cat(proj[4], r2d[4])
         for l in (4, 3, 2, 1):
             FF.join(FF.side_stream(dev, l), proj[l - 1])
             if l == 4 and levels2d < 5:
@@ -250,11 +281,7 @@ class ModifiedUnet3D2D(SegmentationNetwork):
         self._bump_bn_counters()
         if oct.is_cuda and FF.streams_enabled():
             return self._forward_branches(oct, slo, 4)
-        f2d = self._encode_2d(slo, 4)
-        f3d = self._encode_3d(oct)
-        proj = [self._project(f3d[l - 1], l) for l in range(1, 6)]
-        r2d = [self._resize_2d(f2d[l], proj[l]) for l in range(4)]
-        return self._decode(proj, r2d, proj[4])
+        return self._forward_serial(oct, slo, 4)
 
 
 class ModifiedUnet3D2DLevel5(ModifiedUnet3D2D):
@@ -274,9 +301,4 @@ class ModifiedUnet3D2DLevel5(ModifiedUnet3D2D):
         self._bump_bn_counters()
         if oct.is_cuda and FF.streams_enabled():
             return self._forward_branches(oct, slo, 5)
-        f2d = self._encode_2d(slo, 5)
-        f3d = self._encode_3d(oct)
-        proj = [self._project(f3d[l - 1], l) for l in range(1, 6)]
-        r2d = [self._resize_2d(f2d[l], proj[l]) for l in range(5)]
-        deeper = FF.CatFunction.apply(proj[4], r2d[4])
-        return self._decode(proj, r2d, deeper)
+        return self._forward_serial(oct, slo, 5)

@@ -172,7 +172,7 @@ class FPNLateFusion(FPNConfig):
         return {'prediction': seg if fuse else self.last_activation(seg)}
 
     def fuse_features(self, oct_seg: Tensor, fused_seg: Tensor, act=None):
-        cat = FF.CatFunction.apply(oct_seg, fused_seg)
+        cat = FF.cat(oct_seg, fused_seg)
         seg = FF.HeadFunction.apply(cat, self.fusion_module.weight, self.fusion_module.bias, act)
         return seg.permute(0, 1, 2, 4, 3)
 
