@@ -95,6 +95,47 @@ def join_side_streams() -> None:
             _USED_SIDE.discard(st)
 
 
+def fork_from(side: 'torch.cuda.Stream', event: 'torch.cuda.Event', *tensors) -> 'torch.cuda.Stream':
+    """``side`` continues after ``event`` (recorded earlier on the current stream) instead of after everything enqueued so
+    far: a branch issued late in program order still starts early on the device (and in a captured graph)."""
+    side.wait_event(event)
+    _USED_SIDE.add(side)
+    for t in tensors:
+        t.record_stream(side)
+    return side
+
+
+def used_side_streams(device):
+    return [st for st in _USED_SIDE if st.device == device]
+
+
+# ---- gradient buckets ------------------------------------------------------------------------------------
+# FusionTrainer overlaps the gradient all-reduce + SGD of everything but the first two encoder levels with the backward of
+# those levels (SURVEY.md section 8e).  The body marks the boundary in its forward: the marker's backward runs when the
+# gradient has flowed back through level 3, i.e. after every kernel writing an "early" gradient has been issued.
+_BUCKET_HOOK = [None]
+
+
+def set_bucket_hook(fn) -> None:
+    _BUCKET_HOOK[0] = fn
+
+
+class _BucketMarker(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        if _BUCKET_HOOK[0] is not None:
+            _BUCKET_HOOK[0]()
+        return g
+
+
+def bucket_marker(x: torch.Tensor) -> torch.Tensor:
+    return _BucketMarker.apply(x) if (_BUCKET_HOOK[0] is not None and x.requires_grad) else x
+
+
 # ---- layout helpers ------------------------------------------------------------------------------------
 def to_phys(x: torch.Tensor) -> torch.Tensor:
     """logical (B,C,S,W,H) / (B,C,S,W) -> physical (B,S,W,H,C) contiguous in the compute dtype."""

@@ -15,10 +15,29 @@ import torch.distributed as dist
 from torch import nn
 
 
-def flatten_parameters(model: nn.Module, device=None):
-    """Move all parameters into one flat fp32 buffer (parameters become views); returns (flat_p, flat_g)."""
-    params = [p for p in model.parameters()]
+LATE_STAGES = ('conv1', 'conv2', 'zdimRed1', 'zdimRed2')     # backward reaches these last (fusion3D2D.py forward order)
+
+
+def late_parameter_names(model: nn.Module):
+    """Parameters whose gradients are produced AFTER the bucket marker of the fusion bodies (the first two 3-D encoder levels
+    and their projective blocks): everything else can be all-reduced and stepped while their backward still runs."""
+    late = set()
+    for name, _ in model.named_parameters():
+        parts = name.split('.')
+        if len(parts) > 1 and parts[0] == 'resensnet' and parts[1] in LATE_STAGES:
+            late.add(name)
+    return late
+
+
+def flatten_parameters(model: nn.Module, device=None, late_names=None):
+    """Move all parameters into one flat fp32 buffer (parameters become views); returns (flat_p, flat_g).  ``late_names``:
+    these parameters are laid out at the END of the buffers (second gradient bucket); ``flat_p.n_early`` tells where it starts."""
+    named = list(model.named_parameters())
+    if late_names:
+        named = [(k, p) for k, p in named if k not in late_names] + [(k, p) for k, p in named if k in late_names]
+    params = [p for _, p in named]
     n = sum(p.numel() for p in params)
+    n_early = sum(p.numel() for k, p in named if not (late_names and k in late_names))
     device = params[0].device if device is None else device
     flat_p = torch.empty(n, dtype=torch.float32, device=device)
     flat_g = torch.zeros(n, dtype=torch.float32, device=device)
@@ -29,6 +48,7 @@ def flatten_parameters(model: nn.Module, device=None):
         p.data = flat_p[off:off + k].view(p.shape)
         p.grad = flat_g[off:off + k].view(p.shape)
         off += k
+    flat_p.n_early = n_early
     return flat_p, flat_g
 
 
@@ -81,8 +101,15 @@ class FusionTrainer:
         self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
         self.group = group
         self.accumulate = max(1, int(accumulate_grad_batches))     # train.py:161
-        self.flat_p, self.flat_g = flatten_parameters(model)
+        # two gradient buckets: [everything else | conv1, conv2, zdimRed1, zdimRed2]; the first one is
+        # all-reduced and stepped on a communication stream while the backward of the second still runs
+        late = late_parameter_names(model) if self.accumulate == 1 and not os.environ.get('FFPN_NO_BUCKETS') else set()
+        self.flat_p, self.flat_g = flatten_parameters(model, late_names=late)
+        self.n_early = self.flat_p.n_early if late else 0       # 0: single bucket
         self.mom = torch.zeros_like(self.flat_p)
+        self._comm_stream = None
+        self._early_done = False       # the early bucket's all-reduce + SGD were issued by the bucket hook of this backward
+        self._bucket_checked = False   # first step: verify that no early gradient is written after the marker
         broadcast_replica_state(model, self.flat_p, self.mom, group)
         # weights replaced behind the trainer's back (load_state_dict / load_checkpoint copy in place, same pointers): the
         # packed bf16 images of the arena are regenerated before the next forward or replay
@@ -128,12 +155,18 @@ class FusionTrainer:
         # another model) packs its weights from the current fp32 values and cannot see a stale image
         if self._arena_state:
             ops.weight_arena_enable(dev, True)
+        self._early_done = False
+        if self.n_early and self._optimizer_in_backward:
+            functional.set_bucket_hook(self._on_early_bucket_ready)
         try:
             out = self.model(batch)
             loss, _ = self.criterion(batch, out)
             (loss / self.accumulate if self.accumulate > 1 else loss).backward()
             functional.join_side_streams()     # the sink is written from every branch stream
+            if self._early_done:
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
         finally:
+            functional.set_bucket_hook(None)
             functional.set_grad_sink(None)
             if self._arena_state == 1:
                 ops.weight_arena_seal(dev)
@@ -141,6 +174,43 @@ class FusionTrainer:
             if self._arena_state:
                 ops.weight_arena_enable(dev, False)
         return loss.detach()
+
+    # -- gradient buckets ---------------------------------------------------------------------------------
+    _optimizer_in_backward = False     # set by step() / capture(): forward_backward() alone must not touch the weights
+
+    def _on_early_bucket_ready(self):
+        """Bucket marker (runs inside backward, when the gradient has flowed back through encoder level 3): every kernel that
+        writes a gradient of the first bucket has been issued.  All-reduce + SGD of that bucket go to the communication
+        stream, ordered after all of those kernels, and overlap the backward of levels 2 and 1."""
+        from . import functional
+        if self._early_done:
+            return
+        cur = torch.cuda.current_stream()
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.flat_p.device)
+        if not self._bucket_checked:
+            # verification pass (first step): snapshot the first bucket after everything ISSUED so far has run; at the end of the
+            # step the snapshot must equal the final gradients, i.e. nothing issued later writes into this bucket
+            for st in functional.used_side_streams(self.flat_p.device):
+                cur.wait_stream(st)
+            self._early_snapshot = (self.flat_g[:self.n_early].clone(), cur)
+            return
+        comm = self._comm_stream
+        comm.wait_stream(cur)
+        for st in functional.used_side_streams(self.flat_p.device):
+            comm.wait_stream(st)
+        with torch.cuda.stream(comm):
+            self._reduce_and_step(0, self.n_early)
+        self._early_done = True
+
+    def _reduce_and_step(self, a: int, b: int):
+        from . import ops
+        g = self.flat_g[a:b]
+        scale = allreduce_mean_(g, self.group)
+        ops.sgd_step(self.flat_p[a:b], g, self.mom[a:b], self.lr, self.momentum, self.weight_decay, scale, self.steps == 0 and not self._in_capture)
+        g.zero_()
+
+    _in_capture = False
 
     def _dev(self) -> int:
         return self.flat_p.device.index if self.flat_p.device.index is not None else 0
@@ -174,18 +244,39 @@ class FusionTrainer:
             pass
 
     def optimizer_step(self):
+        """All-reduce (sum; 1/world folded into the SGD kernel) + SGD + re-packing of the bf16 weight images.  When the bucket
+        hook already handled the first bucket during backward, only the second one (the first two encoder levels) is left."""
         from . import ops
-        scale = allreduce_mean_(self.flat_g, self.group)
-        ops.sgd_step(self.flat_p, self.flat_g, self.mom, self.lr, self.momentum, self.weight_decay, scale,
-                     self.steps == 0)
+        if self._early_done:
+            self._reduce_and_step(self.n_early, self.flat_p.numel())
+            self._early_done = False
+        else:
+            self._reduce_and_step(0, self.flat_p.numel())
         if self._arena_state == 2:
-            ops.weight_arena_pack(self.flat_p)         # keep the arena images in step with the weights (eval forwards use them)
+            ops.weight_arena_pack(self.flat_p)         # keep the arena images in step with the weights
         self.steps += 1
-        self.flat_g.zero_()
+
+    def _verify_buckets(self):
+        """First step only: the gradients of the first bucket must not change after the marker fired (else the layout
+        assumption does not hold for this model and the trainer falls back to a single bucket)."""
+        snap = getattr(self, '_early_snapshot', None)
+        self._bucket_checked = True
+        if snap is None:
+            self.n_early = 0                          # the marker never fired (a body without one): single bucket
+            return
+        self._early_snapshot = None
+        if not torch.equal(snap[0], self.flat_g[:self.n_early]):
+            self.n_early = 0
 
     def step(self, batch):
         """Eager training step (forward, loss, backward, all-reduce, SGD)."""
-        loss = self.forward_backward(batch)
+        self._optimizer_in_backward = self.accumulate == 1
+        try:
+            loss = self.forward_backward(batch)
+        finally:
+            self._optimizer_in_backward = False
+        if self.n_early and not self._bucket_checked and self.accumulate == 1:
+            self._verify_buckets()
         self.micro += 1
         if self.micro % self.accumulate == 0:
             self.optimizer_step()
@@ -193,9 +284,11 @@ class FusionTrainer:
 
     # -- CUDA graph --------------------------------------------------------------------------------------
     def capture(self, example_batch, warmup: int = 3, include_optimizer: Optional[bool] = None):
-        """Capture forward+loss+backward (and SGD when there is no collective) on static input buffers."""
-        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        self._fused_opt = (world == 1 and self.accumulate == 1) if include_optimizer is None else include_optimizer
+        """Capture the whole optimisation step on static input buffers: forward + loss + backward, the bucketed gradient
+        all-reduce (NCCL, captured on the communication stream, overlapping the backward of the first two encoder levels), SGD
+        and the re-packing of the bf16 weight images.  ``include_optimizer=False`` (or gradient accumulation) captures
+        forward + backward only and leaves the optimiser to ``replay()``."""
+        self._fused_opt = (self.accumulate == 1) if include_optimizer is None else (include_optimizer and self.accumulate == 1)
         self._static = {k: v.clone() for k, v in example_batch.items()}
         # The warm-up passes (>= 1: the packed-weight arena must be sealed before the capture, its cudaMalloc / memcpy cannot be
         # captured) are real training-mode forwards: they would momentum-update every BatchNorm running statistic and bump
@@ -207,7 +300,14 @@ class FusionTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.forward_backward(self._static)
+                # bucket hook in "verify" mode on the first pass (it only snapshots the first bucket's gradients)
+                self._optimizer_in_backward = self._fused_opt and not self._bucket_checked
+                try:
+                    self.forward_backward(self._static)
+                finally:
+                    self._optimizer_in_backward = False
+                if self.n_early and not self._bucket_checked and self._fused_opt:
+                    self._verify_buckets()
                 self.flat_g.zero_()
             for b, s in zip(self.model.buffers(), saved):
                 b.copy_(s)
@@ -215,14 +315,18 @@ class FusionTrainer:
         torch.cuda.synchronize()
         first = self.steps == 0
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._static_loss = self.forward_backward(self._static)
-            if self._fused_opt:
-                from . import ops
-                ops.sgd_step(self.flat_p, self.flat_g, self.mom, self.lr, self.momentum, self.weight_decay, 1.0, False)
-                if self._arena_state == 2:
-                    ops.weight_arena_pack(self.flat_p)
-                self.flat_g.zero_()
+        self._in_capture = True
+        self._optimizer_in_backward = self._fused_opt
+        try:
+            with torch.cuda.graph(self._graph):
+                self._static_loss = self.forward_backward(self._static)
+                if self._fused_opt:
+                    self.optimizer_step()
+        finally:
+            self._in_capture = False
+            self._optimizer_in_backward = False
+        if self._fused_opt:
+            self.steps -= 1                  # optimizer_step() counted the capture itself; replay() counts the real steps
         self._first_graph_step = first
         return self
 

@@ -189,10 +189,12 @@ class ModifiedUnet3D2D(SegmentationNetwork):
             feats.append(f)
         return feats
 
-    def _encode_3d(self, oct):
+    def _encode_3d(self, oct, mark_bucket=False):
         feats, x = [], FF.pack_oct(oct)
         for l in range(1, 6):
             f, x = self._level(getattr(self, f'conv{l}'), x, getattr(self, f'pool{l}') if l < 5 else None)
+            if l == 2 and mark_bucket:
+                x = FF.bucket_marker(x)
             feats.append(f)
         return feats
 
@@ -234,8 +236,8 @@ class ModifiedUnet3D2D(SegmentationNetwork):
         slots, sizes = self._cat_slots(oct, levels2d)
         s3 = (lambda l: slots[l][0] if slots and l in slots else None)
         s2 = (lambda l: slots[l][1] if slots and l in slots else None)
-        f2d = self._encode_2d(slo, levels2d)
-        f3d = self._encode_3d(oct)
+        f3d = self._encode_3d(oct, mark_bucket=True)
+        f2d = self._encode_2d(slo, levels2d)                # after the 3-D encoder: see _forward_branches
         proj = [self._project(f3d[l - 1], l, slot=s3(l)) for l in range(1, 6)]
         r2d = [self._resize_2d(f2d[l], sizes[l], s2(l + 1)) for l in range(levels2d)]
         deeper = FF.cat(proj[4], r2d[4]) if levels2d == 5 else proj[4]
@@ -251,13 +253,13 @@ class ModifiedUnet3D2D(SegmentationNetwork):
         slots, sizes = self._cat_slots(oct, levels2d)       # before any fork: every stream below is ordered after the allocation
         s3 = (lambda l: slots[l][0] if slots and l in slots else None)
         s2 = (lambda l: slots[l][1] if slots and l in slots else None)
-        s2d = FF.fork(FF.side_stream(dev, 0), slo)
-        with torch.cuda.stream(s2d):
-            f2d = self._encode_2d(slo, levels2d)
-            r2d = [self._resize_2d(f2d[l], sizes[l], s2(l + 1)) for l in range(levels2d)]
+        start = torch.cuda.Event()
+        start.record()
         proj, x = [None] * 5, FF.pack_oct(oct)
         for l in range(1, 6):
             f, x = self._level(getattr(self, f'conv{l}'), x, getattr(self, f'pool{l}') if l < 5 else None)
+            if l == 2:
+                x = FF.bucket_marker(x)                     # backward: everything behind this point has issued its gradients
             if l < 5:
                 sp = FF.fork(FF.side_stream(dev, l), f)
                 with torch.cuda.stream(sp):
@@ -265,6 +267,13 @@ class ModifiedUnet3D2D(SegmentationNetwork):
             else:
                 proj[4] = self._project(f, 5, slot=s3(5))
             assert tuple(proj[l - 1].shape[2:4]) == sizes[l - 1], (tuple(proj[l - 1].shape), sizes[l - 1])
+        # The 2-D encoder is ISSUED after the 3-D one but starts at `start` on its own stream: on the device (and in a captured
+        # graph) it runs concurrently from the beginning, while autograd -- which replays nodes newest first -- issues its
+        # backward before the 3-D encoder's, so that its gradients are complete when the bucket marker fires.
+        s2d = FF.fork_from(FF.side_stream(dev, 0), start, slo)
+        with torch.cuda.stream(s2d):
+            f2d = self._encode_2d(slo, levels2d)
+            r2d = [self._resize_2d(f2d[l], sizes[l], s2(l + 1)) for l in range(levels2d)]
         deeper = proj[4]
         if levels2d == 5:
             FF.join(s2d, r2d[4])

@@ -508,3 +508,38 @@ def test_fused_head_activation_equals_separate_sigmoid(mirror):
         res.append((out['prediction'].detach().clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters()])))
     assert rel(res[0][0], res[1][0]) <= 1e-6
     assert rel(res[0][1], res[1][1]) <= 1e-5
+
+
+def test_no_concat_copies_and_bucketed_step(mirror, monkeypatch):
+    """(a) NS-1: the hybrid model's step launches no slice_copy (producers write into the concat slots, gradients are read in
+    place).  (b) the trainer's two gradient buckets: after the verification step the first bucket is reduced + stepped from
+    inside backward; parameters equal the single-bucket trainer's bit for bit."""
+    import ffpn
+    from ffpn import ops
+    from ffpn.trainer import FusionTrainer
+    ffpn.set_compute_dtype(torch.bfloat16)
+    sd = O.make_state_dict(seed=61)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 32, 16, 32, seed=6).items()}
+
+    def boom(*a, **k):
+        raise AssertionError('slice_copy launched: a concat member was copied')
+    params = []
+    for buckets in (True, False):
+        if not buckets:
+            monkeypatch.setenv('FFPN_NO_BUCKETS', '1')
+        model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        tr = FusionTrainer(model, _crit(mirror))
+        assert (tr.n_early > 0) == buckets
+        if buckets:
+            monkeypatch.setattr(ops, 'slice_copy', boom)
+        for i in range(3):
+            tr.step(batch)
+            if buckets and i == 0:
+                assert tr._bucket_checked and 0 < tr.n_early < tr.flat_p.numel()       # layout verified, two buckets kept
+        torch.cuda.synchronize()
+        params.append({k: p.detach().clone() for k, p in model.named_parameters()})
+        tr.close()
+    for k in params[0]:
+        assert torch.equal(params[0][k], params[1][k]), k
