@@ -249,27 +249,32 @@ def run_reference(args, rank, world):
 
 
 def kernel_roofline(torch, ops, peak_gbs, peak_src, iters=20):
-    """Time the dominant kernels alone (CUDA events on the launching stream, inputs >> L2 at the C2 shape)."""
-    w = WORKLOAD
-    B, S, W_, H = w['B'], w['S'], w['W'], w['H']
-    res = []
-    g = torch.Generator(device='cuda').manual_seed(0)
-
-    # packed-weight arena as in the training step (images recorded on the first call, looked up afterwards): the timed
-    # region holds the kernel itself, not the per-call weight-packing launch the step does not make either
-    arena_buf = torch.empty((8 << 20) + 1024, dtype=torch.uint8, device='cuda')
-    arena = arena_buf[(-arena_buf.data_ptr()) % 1024:][:8 << 20]          # the library wants a 1 KiB-aligned buffer
+    """Time the hot kernels alone at the C2 shapes (tools/kernel_cases.py: the same named cases the ncu captures under profiles/
+    use): CUDA events on the launching stream, inputs >> L2.  Convolutions run with their packed weights in the arena, as in the
+    training step (the timed region holds the kernel, not a per-call weight-packing launch the step does not make either)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import kernel_cases as KC
+    cases = KC.build(torch, ops)
+    tflops_peak = 1653.8
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        with open(pk) as f:
+            tflops_peak = json.load(f).get('bf16_tflops', tflops_peak)             # burst figure: kernels timed alone
+    traffic = {}
+    tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f)
+    arena_buf = torch.empty((16 << 20) + 1024, dtype=torch.uint8, device='cuda')
+    arena = arena_buf[(-arena_buf.data_ptr()) % 1024:][:16 << 20]          # the library wants a 1 KiB-aligned buffer
     dev_index = torch.cuda.current_device()
-    state = {'sealed': False}
-    ops.weight_arena_begin(arena)
-
-    def timeit(fn):
-        if state['sealed']:                               # a new kernel: record its weight image, then replay
-            ops.weight_arena_end(dev_index)
-            ops.weight_arena_begin(arena)
+    res = []
+    for name in KC.DEFAULT_BENCH:
+        fn, nbytes, flops = cases[name]['make']()
+        ops.weight_arena_begin(arena)                     # record this case's weight image, then replay from the arena
         fn()
         ops.weight_arena_seal(dev_index)
-        state['sealed'] = True
+        ops.weight_arena_enable(dev_index, True)
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -279,40 +284,19 @@ def kernel_roofline(torch, ops, peak_gbs, peak_src, iters=20):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters * 1e-3
-
-    dt = torch.bfloat16
-    C = 16
-    x = torch.randn(B, S, W_, H, C, device='cuda', generator=g).to(dt)
-    wt = torch.randn(C, C, 1, 3, 3, device='cuda', generator=g) * 0.1
-    sc = torch.ones(C, device='cuda'); sh = torch.zeros(C, device='cuda')
-    nbytes = 2 * x.numel() * 2
-    t = timeit(lambda: ops.conv_fwd(x, wt, (1, 3, 3), (1, 1, 1), (0, 1, 1), sc, sh, True))
-    res.append(dict(kernel='conv_fwd (1,3,3) 16->16 level-1 (BN+ReLU on load, stats epilogue)', bytes=nbytes, sec=t))
-    wz = torch.randn(C, C, 1, 1, 3, device='cuda', generator=g) * 0.1
-    t = timeit(lambda: ops.conv_fwd(x, wz, (1, 1, 3), (1, 1, 2), (0, 0, 1), sc, sh, True))
-    res.append(dict(kernel='projection conv (1,1,3) s(1,1,2) 16->16 level-1', bytes=int(x.numel() * 2 * 1.5), sec=t))
-    y = torch.randn_like(x)
-    dw = torch.zeros_like(wt)
-    t = timeit(lambda: ops.conv_wgrad(x, y, wt.shape, (1, 3, 3), (1, 1, 1), (0, 1, 1), sc, sh, True, out=dw))
-    res.append(dict(kernel='conv_wgrad (1,3,3) 16->16 level-1 (BN+ReLU on load, all 9 taps per MMA) + partial-tile reduce', bytes=nbytes, sec=t))
-    t = timeit(lambda: ops.conv_dgrad(y, wt, tuple(x.shape), (1, 3, 3), (1, 1, 1), (0, 1, 1)))
-    res.append(dict(kernel='conv_dgrad (1,3,3) 16->16 level-1', bytes=nbytes, sec=t))
-    for lvl, Cl in ((2, 32), (3, 64)):
-        xl = torch.randn(B, S, W_ >> (lvl - 1), H >> (lvl - 1), Cl, device='cuda', generator=g).to(dt)
-        wl = torch.randn(Cl, Cl, 1, 3, 3, device='cuda', generator=g) * 0.05
-        scl = torch.ones(Cl, device='cuda'); shl = torch.zeros(Cl, device='cuda')
-        t = timeit(lambda: ops.conv_fwd(xl, wl, (1, 3, 3), (1, 1, 1), (0, 1, 1), scl, shl, True))
-        res.append(dict(kernel=f'conv_fwd (1,3,3) {Cl}->{Cl} level-{lvl}', bytes=2 * xl.numel() * 2, sec=t))
-    t = timeit(lambda: ops.block_end_fwd(y, sc, sh, x))
-    res.append(dict(kernel='block_end_fwd (BN apply + residual + ReLU) level-1', bytes=3 * x.numel() * 2, sec=t))
-    t = timeit(lambda: ops.bn_bwd_reduce(y, x, sc, sh, True))
-    res.append(dict(kernel='bn_bwd_reduce level-1', bytes=2 * x.numel() * 2, sec=t))
-    ops.weight_arena_end(dev_index)
-    for r in res:
-        r['gbs'] = r['bytes'] / r['sec'] / 1e9
-        r['frac'] = r['gbs'] / peak_gbs
-    return res
+        ops.weight_arena_end(dev_index)
+        sec = e0.elapsed_time(e1) / iters * 1e-3
+        ai = flops / max(nbytes, 1)
+        bound = 'tensor' if ai > KC.RIDGE_FLOP_PER_BYTE else 'hbm'
+        gbs, tfs = nbytes / sec / 1e9, flops / sec / 1e12
+        t = traffic.get(name, {})
+        res.append(dict(kernel=name, note=cases[name]['note'], bound=bound, sec=sec, bytes=nbytes, flops=flops, flop_per_byte=ai,
+                        gbs=gbs, tflops=tfs, frac=(tfs / tflops_peak) if bound == 'tensor' else (gbs / peak_gbs),
+                        frac_hbm=gbs / peak_gbs, frac_tensor=tfs / tflops_peak,
+                        ncu=({k: t[k] for k in ('dram_bytes', 'duration_us', 'tensor_pipe_pct', 'dram_pct', 'file') if k in t} or None)))
+        del fn
+        torch.cuda.empty_cache()
+    return res, tflops_peak
 
 
 def main():
@@ -448,17 +432,15 @@ def main():
         peak, src = peaks()
         if not args.no_kernel_roofline:
             trainer.close()                                 # detach the trainer's arena: the kernel timings below use their own
-            ks = kernel_roofline(torch, ops, peak, src)
-            top = ks[0]
-            traffic = None                                  # dram bytes per launch from the committed ncu --set full capture
-            tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-            if os.path.exists(tp):
-                with open(tp) as f:
-                    traffic = json.load(f).get('conv_fwd_l1_dram_bytes_per_launch')
-            line['roofline'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['gbs'], 'peak': peak, 'unit': 'GB/s',
-                                'frac': top['frac'], 'traffic': traffic, 'peak_source': src,
+            ks, tflops_peak = kernel_roofline(torch, ops, peak, src)
+            top = ks[0]                                     # conv_fwd_l1: the kernel with the largest share of the step
+            line['roofline'] = {'bound': top['bound'], 'kernel': top['kernel'] + ': ' + top['note'], 'achieved': top['gbs'], 'peak': peak,
+                                'unit': 'GB/s', 'frac': top['frac'], 'traffic': (top['ncu'] or {}).get('dram_bytes'),
+                                'traffic_source': (top['ncu'] or {}).get('file'), 'peak_source': src,
                                 'algorithmic_bytes_per_launch': top['bytes'], 'sec_per_launch': top['sec']}
-            line['kernels'] = [{k: r[k] for k in ('kernel', 'gbs', 'frac', 'sec', 'bytes')} for r in ks]
+            line['kernels'] = [{k: r[k] for k in ('kernel', 'bound', 'gbs', 'tflops', 'frac', 'frac_hbm', 'frac_tensor', 'sec', 'bytes',
+                                                  'flops', 'flop_per_byte', 'ncu')} for r in ks]
+            line['peaks'] = {'hbm_gbs': peak, 'bf16_tflops_burst': tflops_peak, 'ridge_flop_per_byte': 212.0}
             # whole-step roofline: conv-boundary traffic model of SURVEY.md section 8d (bf16, fwd+bwd = 3 x fwd)
             step_bytes = w['model_elems'] * 2 * 3 * w['B']
             line['step_roofline'] = {'model_bytes_per_step': step_bytes, 'achieved_gbs': step_bytes / (ms / args.steps * 1e-3) / 1e9,
@@ -477,7 +459,13 @@ def main():
                                         'sample': 'failed: ' + (r.stderr.strip().splitlines() or ['no output'])[-1][:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured step holds NCCL kernels; tearing the communicator down under a live CUDA graph can block at exit.  Every
+        # rank has printed / reduced what it had to: synchronise, then leave without the destructor chain.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -612,7 +612,7 @@ struct WsPlan {
   int box[4];
 };
 
-WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
+WsPlan make_ws_plan_with(const ffpn_conv_desc* d, bool transposed, int num_sms, int npad_override, int nmb_limit) {
   WsPlan w;
   memset(&w, 0, sizeof(w));
   w.base = ffpn_tc_make_plan(d, transposed, num_sms);
@@ -629,6 +629,7 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
     static int nsplit = -1;
     if (nsplit < 0) { const char* e = getenv("FFPN_WS_NSPLIT"); nsplit = e ? atoi(e) : 128; }
     if (nsplit > 0 && p.Cout >= 2 * nsplit && p.Cout % nsplit == 0) { p.Npad = nsplit; w.nchunks = p.Cout / nsplit; }
+    if (npad_override > 0 && npad_override < p.Npad && p.Cout % npad_override == 0) { p.Npad = npad_override; w.nchunks = p.Cout / npad_override; }
   }
   const int ntaps = p.kD * p.kY * p.kX;
   if (ntaps > 27 || p.Cin % 16 != 0) return w;
@@ -652,6 +653,7 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   int nmb_cap = (512 / p.nbuf) / p.colstride;
   if (nmb_cap > 8) nmb_cap = 8;
   { const char* e = getenv("FFPN_WS_NMBCAP"); if (e && atoi(e) >= 1 && atoi(e) < nmb_cap) nmb_cap = atoi(e); }                                // tuning
+  if (nmb_limit > 0 && nmb_limit < nmb_cap) nmb_cap = nmb_limit;
   if (nmb_cap < 1) return w;
   const size_t budget = 227 * 1024 - WS_HDR - 1024;
   const size_t w_total = (size_t)ntaps * p.Cin * p.Npad * 2;
@@ -752,6 +754,34 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
     }
   }
   return w;
+}
+
+// Small problems (deep encoder levels, the en-face decoder): the default plan takes the largest tile and the widest N chunk,
+// which leaves most of the 148 SMs idle (up_concat4: 16 tiles x 1 chunk, every CTA streaming 1.8 MB of weights).  With
+// FFPN_WS_SPREAD=1, when the default plan gives fewer CTAs than SMs, smaller tiles and narrower N chunks (>= 32 columns: a K=16
+// MMA costs ~40 cycles for any N <= 32) are tried and the plan with the most CTAs wins.  Measured on B200 (same box): alone,
+// up_concat4 forward 59.2 -> 35.5 us and level-5 31.5 -> 28.4 us; but the C2 training step gets SLOWER, 9.33 -> 9.44 ms, because
+// there these kernels already overlap the large level-1/2 kernels of the other branch streams and the extra CTAs take SMs
+// away from them.  Hence off by default; it is the right setting for a single-stream / small-batch inference use.
+WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
+  WsPlan best = make_ws_plan_with(d, transposed, num_sms, 0, 0);
+  static int spread = -1;
+  if (spread < 0) { const char* e = getenv("FFPN_WS_SPREAD"); spread = (e && atoi(e) == 1) ? 1 : 0; }
+  if (!best.ok || !spread) return best;
+  auto ctas = [&](const WsPlan& w) { const int c = (int)(w.grid.x * w.grid.y); return c < num_sms ? c : num_sms; };
+  if (ctas(best) >= num_sms) return best;
+  const int npads[3] = {0, 64, 32};                      // 0: the default chunk width
+  for (int ni = 0; ni < 3; ni++) {
+    if (npads[ni] != 0 && (npads[ni] >= best.p.Npad || best.p.Cout % npads[ni] != 0)) continue;
+    for (int nmb = 8; nmb >= 1; nmb >>= 1) {
+      if (ni == 0 && nmb == 8) continue;                   // = the default plan
+      WsPlan cand = make_ws_plan_with(d, transposed, num_sms, npads[ni], nmb);
+      if (!cand.ok) continue;
+      if (ctas(cand) > ctas(best)) best = cand;
+      if (ctas(best) >= num_sms) return best;
+    }
+  }
+  return best;
 }
 
 bool encode_ws_map(CUtensorMap* m, const WsPlan& w, const void* x, bool nan_fill) {

@@ -6,7 +6,61 @@ namespace {
 
 constexpr int TH = 256;
 
-// out[ew, coff + c] = mean_h relu(a*y[ew,h,c] + b)
+// Projection tail: out[ew, coff + c] = mean_h relu(a[c] * y[ew, h, c] + b[c])  (BatchNorm + ReLU + torch.mean(dim=4),
+// fusion3D2D.py:527-536).  One thread owns a 16-byte channel chunk (8 bf16 / 4 fp32) of one en-face position and walks
+// the surviving depth taps with vector loads: consecutive threads read consecutive chunks, so a warp streams whole
+// channels-last rows; coefficients live in registers.  C % VEC != 0 falls back to the scalar kernel below.
+template <typename T>
+__global__ void __launch_bounds__(TH) proj_tail_fwd_vec_kernel(int64_t EW, int H, int C, const T* __restrict__ y,
+                                                              const float* __restrict__ a, const float* __restrict__ b,
+                                                              T* __restrict__ out, int ostride, int coff) {
+  pdl_prologue();
+  constexpr int VEC = Elem<T>::VEC;
+  const int cvecs = C / VEC;
+  const int64_t n = EW * cvecs;
+  const float inv = 1.f / (float)H;
+  for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
+    const int cv = (int)(i % cvecs);
+    const int64_t ew = i / cvecs;
+    float sa[VEC], sb[VEC], acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; j++) { sa[j] = a[cv * VEC + j]; sb[j] = b[cv * VEC + j]; acc[j] = 0.f; }
+    const T* src = y + (ew * H) * C + cv * VEC;
+    for (int h = 0; h < H; h++) {
+      float v[VEC];
+      Elem<T>::load(src + (int64_t)h * C, v);
+#pragma unroll
+      for (int j = 0; j < VEC; j++) {
+        const float t = fmaf(v[j], sa[j], sb[j]);
+        acc[j] += (t < 0.f) ? 0.f : t;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; j++) acc[j] *= inv;
+    Elem<T>::store(out + ew * ostride + coff + cv * VEC, acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TH) proj_tail_bwd_vec_kernel(int64_t EW, int H, int C, const T* __restrict__ dout, int ostride,
+                                                              int coff, T* __restrict__ dA) {
+  pdl_prologue();
+  constexpr int VEC = Elem<T>::VEC;
+  const int cvecs = C / VEC;
+  const int64_t n = EW * cvecs;
+  const float inv = 1.f / (float)H;
+  for (int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x; i < n; i += (int64_t)gridDim.x * TH) {
+    const int cv = (int)(i % cvecs);
+    const int64_t ew = i / cvecs;
+    float g[VEC];
+    Elem<T>::load(dout + ew * ostride + coff + cv * VEC, g);
+#pragma unroll
+    for (int j = 0; j < VEC; j++) g[j] *= inv;
+    T* dst = dA + (ew * H) * C + cv * VEC;
+    for (int h = 0; h < H; h++) Elem<T>::store(dst + (int64_t)h * C, g);
+  }
+}
+
 template <typename T>
 __global__ void proj_tail_fwd_kernel(int64_t EW, int H, int C, const T* __restrict__ y, const float* __restrict__ a,
                                      const float* __restrict__ b, T* __restrict__ out, int ostride, int coff) {
@@ -382,7 +436,12 @@ inline int grid_of(ffpn_ctx* ctx, int64_t n) { return ffpn_grid_for(n, TH, ctx->
 extern "C" int ffpn_proj_tail_fwd(ffpn_ctx* ctx, int dtype, int64_t EW, int64_t H, int C, const void* y, const float* a,
                                   const float* b, void* out, int ostride, int coff, void* stream) {
   if (H <= 0) FFPN_FAIL(ctx, "proj_tail_fwd: empty depth");
-  if (dtype == FFPN_F32) ffpn_launch(proj_tail_fwd_kernel<float>, grid_of(ctx, EW * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const float*)y, a, b, (float*)out, ostride, coff);
+  const int vec = dtype == FFPN_F32 ? 4 : 8;
+  if (C % vec == 0 && ostride % vec == 0 && coff % vec == 0) {
+    const int g = grid_of(ctx, EW * (C / vec));
+    if (dtype == FFPN_F32) ffpn_launch(proj_tail_fwd_vec_kernel<float>, g, TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const float*)y, a, b, (float*)out, ostride, coff);
+    else ffpn_launch(proj_tail_fwd_vec_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const bf16*)y, a, b, (bf16*)out, ostride, coff);
+  } else if (dtype == FFPN_F32) ffpn_launch(proj_tail_fwd_kernel<float>, grid_of(ctx, EW * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const float*)y, a, b, (float*)out, ostride, coff);
   else ffpn_launch(proj_tail_fwd_kernel<bf16>, grid_of(ctx, EW * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const bf16*)y, a, b, (bf16*)out, ostride, coff);
   FFPN_CHECK_LAUNCH(ctx, "proj_tail_fwd");
   return 0;
@@ -390,7 +449,12 @@ extern "C" int ffpn_proj_tail_fwd(ffpn_ctx* ctx, int dtype, int64_t EW, int64_t 
 
 extern "C" int ffpn_proj_tail_bwd(ffpn_ctx* ctx, int dtype, int64_t EW, int64_t H, int C, const void* dout, int ostride,
                                   int coff, void* dA, void* stream) {
-  if (dtype == FFPN_F32) ffpn_launch(proj_tail_bwd_kernel<float>, grid_of(ctx, EW * H * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const float*)dout, ostride, coff, (float*)dA);
+  const int vec = dtype == FFPN_F32 ? 4 : 8;
+  if (C % vec == 0 && ostride % vec == 0 && coff % vec == 0) {
+    const int g = grid_of(ctx, EW * (C / vec));
+    if (dtype == FFPN_F32) ffpn_launch(proj_tail_bwd_vec_kernel<float>, g, TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const float*)dout, ostride, coff, (float*)dA);
+    else ffpn_launch(proj_tail_bwd_vec_kernel<bf16>, g, TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const bf16*)dout, ostride, coff, (bf16*)dA);
+  } else if (dtype == FFPN_F32) ffpn_launch(proj_tail_bwd_kernel<float>, grid_of(ctx, EW * H * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const float*)dout, ostride, coff, (float*)dA);
   else ffpn_launch(proj_tail_bwd_kernel<bf16>, grid_of(ctx, EW * H * C), TH, 0, (cudaStream_t)stream, EW, (int)H, C, (const bf16*)dout, ostride, coff, (bf16*)dA);
   FFPN_CHECK_LAUNCH(ctx, "proj_tail_bwd");
   return 0;
