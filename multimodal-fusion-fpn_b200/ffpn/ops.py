@@ -93,6 +93,11 @@ def conv_fwd_bn(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, gamma, b
         y, partial, rows = conv_fwd(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, want_stats=training)
         return y, bn_finalize(partial, rows, y.numel() // y.shape[-1], gamma, beta, running_mean, running_var, momentum, eps, training)
     _chk(x, 'x')
+    if not training:
+        # eval(): the coefficients depend only on (gamma, beta, running statistics) -> computed once per BatchNorm and reused
+        # until one of those tensors changes (tensor version counters); the forward is then the conv alone, no finalize launch
+        y, _, _ = conv_fwd(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, want_stats=False)
+        return y, eval_bn_coefficients(gamma, beta, running_mean, running_var, eps)
     cout = w.shape[0]
     d = make_desc(x.shape, cout, kernel, stride, pad, x.dtype)
     y = torch.empty((d.B, d.oS, d.oW, d.oH, cout), dtype=x.dtype, device=x.device)
@@ -106,6 +111,26 @@ def conv_fwd_bn(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, gamma, b
              float(momentum), float(eps), int(bool(training)), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(ws), nws,
              _stream(x))
     return y, (out[0], out[1], out[2], out[3])
+
+
+_EVAL_BN_CACHE = {}
+
+
+def eval_bn_coefficients(gamma, beta, running_mean, running_var, eps):
+    """(scale, shift, mean, invstd) of an eval-mode BatchNorm, cached per module: key = the buffers' identity, validity = their
+    version counters (any in-place update -- a training step, load_state_dict -- bumps them).  Not used while a CUDA graph is
+    being captured (a cached tensor must not be created inside a capture)."""
+    key = (running_mean.data_ptr(), running_var.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps))
+    ver = (running_mean._version, running_var._version, gamma._version, beta._version)
+    hit = _EVAL_BN_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    out = bn_finalize(None, 0, 1.0, gamma, beta, running_mean, running_var, 0.0, eps, False)
+    if not torch.cuda.is_current_stream_capturing():
+        if len(_EVAL_BN_CACHE) > 4096:
+            _EVAL_BN_CACHE.clear()
+        _EVAL_BN_CACHE[key] = (ver, out)
+    return out
 
 
 def conv_dgrad(dy, w, x_shape, kernel, stride, pad, addend=None):

@@ -543,3 +543,44 @@ def test_no_concat_copies_and_bucketed_step(mirror, monkeypatch):
         tr.close()
     for k in params[0]:
         assert torch.equal(params[0][k], params[1][k]), k
+
+
+def test_ensemble_of_five_checkpoints_full_volume(mirror, tmp_path):
+    """the evaluation regime of the reference (validate_ensemble.py:221-263, test_utils.py:21-38,
+    354-360): five checkpoints in the reference's .ckpt layout, members in eval() mode (BatchNorm on running statistics), one
+    full-volume batch-1 forward each, sigmoid outputs averaged -- against the oracle's average, in the fp32 exact mode and in
+    bf16.  Also: eval forwards cache the BatchNorm coefficients (no finalize launch from the second forward on)."""
+    import ffpn
+    from ffpn import checkpoint as ck
+    S, H, W, S2, W2 = 16, 128, 128, 64, 128                       # batch-1 volume on a 16-multiple en-face grid (training_config.py:103-106)
+    batch = O.synthetic_batch(1, S, H, W, S2, W2, seed=77)
+    paths, sds = [], []
+    for i in range(5):
+        sd = O.make_state_dict(seed=200 + i, randomize_running=True)
+        net = mirror.build('FPNHybridFusion', 'relative_2d_max')
+        net.load_state_dict(sd, strict=True)
+        path = str(tmp_path / f'epoch={i}-Dice=0.9{i}.ckpt')
+        ck.save_checkpoint(mirror.wrapper.Model(net, None, None, None, None, []), path, epoch=i)
+        paths.append(path)
+        sds.append(sd)
+    want = sum(O.fpn_hybrid_fusion_forward(sd, batch, 'relative_2d_max', train=False)['prediction'] for sd in sds) / 5
+    cb = {k: v.cuda() for k, v in batch.items()}
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 5e-2)):
+        ffpn.set_compute_dtype(dtype)
+        ens = ck.Ensemble.from_checkpoints(lambda: mirror.build('FPNHybridFusion', 'relative_2d_max'), paths, device='cuda')
+        assert not ens.training and all(not m.training for m in ens.members)
+        out = ens(cb)['prediction']
+        n0 = ffpn.lib.launch_count(0)
+        out2 = ens(cb)['prediction']
+        n1 = ffpn.lib.launch_count(0)
+        ens(cb)
+        n2 = ffpn.lib.launch_count(0)
+        assert tuple(out.shape) == (1, 1, S, 1, W)
+        assert rel(out.cpu(), want) <= tol, (dtype, rel(out.cpu(), want))
+        assert torch.equal(out, out2)
+        assert n2 - n1 == n1 - n0                                  # steady state
+        assert (n1 - n0) // 5 <= 260                               # per member: 92 convs (+ their weight packing), block ends, pools, tails -- no BatchNorm finalize (91 fewer)
+        for m, sd in zip(ens.members, sds):                        # eval must not touch the buffers
+            after = m.state_dict()
+            assert all(torch.equal(after[k].cpu(), sd[k]) for k in sd)
+    ffpn.set_compute_dtype(torch.bfloat16)
