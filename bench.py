@@ -360,8 +360,8 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = ffpn.lib.launch_count(local_rank) - n0
     routes = {k: v - r0[k] for k, v in ffpn.lib.route_counts(local_rank).items()}      # conv calls per kernel family, one step
-    if args.dtype == 'bf16' and routes['cuda_core'] != 0:
-        raise SystemExit(f'bench.py: {routes["cuda_core"]} bf16 conv calls per step left the tcgen05 / stem kernels: {routes}')
+    if args.dtype == 'bf16' and (routes['cuda_core'] != 0 or routes['tcgen05_gen1'] != 0):
+        raise SystemExit(f'bench.py: bf16 conv calls left the warp-specialised tcgen05 / stem kernels: {routes}')
     use_graph = not args.no_graph
     if use_graph:
         trainer.capture(dev)

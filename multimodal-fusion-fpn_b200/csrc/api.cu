@@ -108,8 +108,11 @@ extern "C" int ffpn_conv_fwd(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void*
   }
   const bool tc_ok = ffpn_tc_fwd_supported(d);
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_fwd: tcgen05 kernel does not support this geometry");
-  if (tc_ok && d->impl != 1)
-    return ffpn_conv_fwd_tc(ctx, d, false, x, in_scale, in_shift, in_relu, w, nullptr, y, stat_partial, stat_rows, ws, ws_bytes, (cudaStream_t)stream);
+  if (tc_ok && d->impl != 1) {
+    const int r = ffpn_conv_fwd_tc(ctx, d, false, x, in_scale, in_shift, in_relu, w, nullptr, y, stat_partial, stat_rows, ws, ws_bytes, (cudaStream_t)stream);
+    if (r >= 0) return r;
+    if (d->impl == 2) FFPN_FAIL(ctx, "conv_fwd: the tcgen05 kernel declined this call (input transform without ReLU, or workspace too small)");
+  }
   ctx->routes[FFPN_ROUTE_SIMT]++;
   if (d->dtype == FFPN_BF16) ffpn_log_route("conv_fwd -> CUDA-core kernel", d);
   return ffpn_conv_fwd_simt(ctx, d, x, in_scale, in_shift, in_relu, w, y, stat_partial, stat_rows, (cudaStream_t)stream);
@@ -139,8 +142,11 @@ extern "C" int ffpn_conv_dgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const voi
   if (check_desc(ctx, d, "conv_dgrad")) return 1;
   const bool tc_ok = ffpn_tc_dgrad_supported(d);
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_dgrad: tcgen05 kernel does not support this geometry");
-  if (tc_ok && d->impl != 1)
-    return ffpn_conv_fwd_tc(ctx, d, true, dy, nullptr, nullptr, 0, w, addend, dx, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+  if (tc_ok && d->impl != 1) {
+    const int r = ffpn_conv_fwd_tc(ctx, d, true, dy, nullptr, nullptr, 0, w, addend, dx, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+    if (r >= 0) return r;
+    if (d->impl == 2) FFPN_FAIL(ctx, "conv_dgrad: the tcgen05 kernel declined this call (workspace too small)");
+  }
   ctx->routes[FFPN_ROUTE_SIMT]++;
   if (d->dtype == FFPN_BF16) ffpn_log_route("conv_dgrad -> CUDA-core kernel", d);
   return ffpn_conv_dgrad_simt(ctx, d, dy, w, addend, dx, (cudaStream_t)stream);
@@ -157,8 +163,11 @@ extern "C" int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const voi
   }
   const bool tc_ok = ffpn_tc_wgrad_supported(d);
   if (d->impl == 2 && !tc_ok) FFPN_FAIL(ctx, "conv_wgrad: tcgen05 kernel does not support this geometry");
-  if (tc_ok && d->impl != 1)
-    return ffpn_conv_wgrad_tc(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, ws, ws_bytes, (cudaStream_t)stream);
+  if (tc_ok && d->impl != 1) {
+    const int r = ffpn_conv_wgrad_tc(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, ws, ws_bytes, (cudaStream_t)stream);
+    if (r >= 0) return r;
+    if (d->impl == 2) FFPN_FAIL(ctx, "conv_wgrad: the tcgen05 kernel declined this call (input transform without ReLU, or workspace too small)");
+  }
   if (d->dtype == FFPN_BF16) ffpn_log_route("conv_wgrad -> CUDA-core kernel", d);
   ctx->routes[FFPN_ROUTE_SIMT]++;
   return ffpn_conv_wgrad_simt(ctx, d, x, in_scale, in_shift, in_relu, dy, dw, (cudaStream_t)stream);

@@ -348,6 +348,8 @@ struct WgWsPlan {
 };
 
 bool chan_ok(int c) { return c == 16 || c == 32 || c == 64 || (c > 64 && c % 64 == 0); }
+// input channels are tiled (blockIdx.y), so any multiple of 16 works there: 48 = 3 x 16, 96 = 3 x 32 (the two-input decoders)
+bool cin_ok(int c) { return c >= 16 && c % 16 == 0; }
 
 WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
   WgWsPlan w;
@@ -356,7 +358,7 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
   if (!w.base.ok) return w;
   const TcParams& c = w.base.p;
   if (c.sX != 1 || c.nsets != 1) return w;
-  if (!chan_ok(d->Cin) || !chan_ok(d->Cout)) return w;
+  if (!cin_ok(d->Cin) || !chan_ok(d->Cout)) return w;
   WgWsParams& p = w.p;
   p.NB = c.NB; p.D = c.D; p.Y = c.Y; p.X = c.X; p.oD = c.oD; p.oY = c.oY; p.oX = c.oX;
   p.kD = c.kD; p.kY = c.kY; p.kX = c.kX; p.pD = c.pD; p.pY = c.pY; p.pX = c.pX; p.hl = c.hl;
@@ -385,8 +387,10 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
   p.M = p.co_t == 16 ? 64 : 128;
   p.sA = p.co_t <= 64 ? (p.M / p.co_t < p.kA ? p.M / p.co_t : p.kA) : 1;
   p.passesA = (p.kA + p.sA - 1) / p.sA;
-  for (int ci_cand = p.Cin < 256 ? p.Cin : 256; ci_cand >= 16; ci_cand = (ci_cand > 64 ? (ci_cand > 128 ? 128 : 64) : 0)) {
+  // input-channel tile: the whole Cin when it is one swizzle row (16 / 32 / 64) or a multiple of 64 up to 256, else 128, 64, 32, 16
+  for (int ci_cand = p.Cin < 256 ? p.Cin : 256; ci_cand >= 16; ci_cand = (ci_cand > 128 ? 128 : ci_cand > 64 ? 64 : ci_cand > 32 ? 32 : ci_cand > 16 ? 16 : 0)) {
   if (p.Cin % ci_cand != 0) continue;
+  if (ci_cand > 64 ? (ci_cand % 64 != 0) : !(ci_cand == 16 || ci_cand == 32 || ci_cand == 64)) continue;
   p.ci_t = ci_cand;
   p.n_ci = p.Cin / p.ci_t;
   p.Cx = p.ci_t < 64 ? p.ci_t : 64; p.nxs = p.ci_t / p.Cx; p.pitch_x = p.Cx * 2;
@@ -474,13 +478,14 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
   return w;
 }
 
-bool encode_wg_map(CUtensorMap* m, const WgWsPlan& w, const void* base, bool is_x, bool nan_fill) {
+bool encode_wg_map(CUtensorMap* m, const WgWsPlan& w, const void* base, bool is_x, bool nan_fill, int in_mult = 1) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   const WgWsParams& p = w.p;
   const TcParams& c = w.base.p;
   const int C = is_x ? p.Cin : p.Cout;
-  const cuuint64_t cb = (cuuint64_t)C * 2;
+  if (in_mult != 1 && (p.tma_mode != 2 || !is_x)) return false;          // strided 1x1x1 shortcut: input rows in_mult * Cin apart
+  const cuuint64_t cb = (cuuint64_t)C * 2 * (cuuint64_t)in_mult;
   const long long sY = is_x ? c.inY : c.outY, sD = is_x ? c.inD : c.outD, sNB = is_x ? c.inNB : c.outNB;
   const int eX = is_x ? p.X : p.oX, eY = is_x ? p.Y : p.oY, eD = is_x ? p.D : p.oD;
   cuuint64_t dims[5], strides[4];
@@ -524,15 +529,17 @@ bool wgws_enabled() {
 
 bool ffpn_wgrad_ws_supported(const ffpn_conv_desc* d) {
   ffpn_conv_desc dp;
-  const bool pair = ffpn_make_pair_desc(d, &dp);
-  return d->dtype == FFPN_BF16 && wgws_enabled() && make_wgrad_ws_plan(pair ? &dp : d, 148).ok;
+  int mult = 1;
+  const bool view = ffpn_make_strided111_desc(d, &dp, &mult) || ffpn_make_pair_desc(d, &dp);
+  return d->dtype == FFPN_BF16 && wgws_enabled() && make_wgrad_ws_plan(view ? &dp : d, 148).ok;
 }
 
 size_t ffpn_wgrad_ws_workspace_bytes(const ffpn_conv_desc* d) {
   if (d->dtype != FFPN_BF16) return 0;
   ffpn_conv_desc dp;
-  const bool pair = ffpn_make_pair_desc(d, &dp);
-  WgWsPlan pl = make_wgrad_ws_plan(pair ? &dp : d, 148);
+  int mult = 1;
+  const bool view = ffpn_make_strided111_desc(d, &dp, &mult) || ffpn_make_pair_desc(d, &dp);
+  WgWsPlan pl = make_wgrad_ws_plan(view ? &dp : d, 148);
   return pl.ok ? pl.ws_bytes : 0;
 }
 
@@ -542,11 +549,13 @@ int ffpn_conv_wgrad_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, co
   if (!wgws_enabled()) return -1;
   if (in_scale != nullptr && !in_relu) return -1;
   ffpn_conv_desc dp;
-  const bool pair = ffpn_make_pair_desc(d, &dp);
-  WgWsPlan pl = make_wgrad_ws_plan(pair ? &dp : d, ctx->num_sms);
+  int in_mult = 1;
+  const bool strided111 = ffpn_make_strided111_desc(d, &dp, &in_mult);
+  const bool pair = !strided111 && ffpn_make_pair_desc(d, &dp);
+  WgWsPlan pl = make_wgrad_ws_plan((pair || strided111) ? &dp : d, ctx->num_sms);
   if (!pl.ok || ws == nullptr || ws_bytes < pl.ws_bytes) return -1;
   CUtensorMap tmx, tmy;
-  if (!encode_wg_map(&tmx, pl, x, true, in_scale != nullptr) || !encode_wg_map(&tmy, pl, dy, false, false)) return -1;
+  if (!encode_wg_map(&tmx, pl, x, true, in_scale != nullptr, in_mult) || !encode_wg_map(&tmy, pl, dy, false, false)) return -1;
   WgWsParams& p = pl.p;
   p.sc = in_scale; p.sh = in_shift; p.has_aff = in_scale != nullptr; p.part = (float*)ws;
   p.pair_cin = pair ? d->Cin : 0;

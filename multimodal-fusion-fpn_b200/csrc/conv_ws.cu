@@ -784,12 +784,13 @@ WsPlan make_ws_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   return best;
 }
 
-bool encode_ws_map(CUtensorMap* m, const WsPlan& w, const void* x, bool nan_fill) {
+bool encode_ws_map(CUtensorMap* m, const WsPlan& w, const void* x, bool nan_fill, int in_mult = 1) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   const WsParams& p = w.p;
   const TcParams& c = w.base.p;
-  const cuuint64_t cb = (cuuint64_t)p.Cin * 2;
+  if (in_mult != 1 && p.tma_mode != 2) return false;                    // the strided row pitch exists for the flat 1x1x1 view only
+  const cuuint64_t cb = (cuuint64_t)p.Cin * 2 * (cuuint64_t)in_mult;    // bytes between consecutive input positions
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4], es[4] = {1, 1, 1, 1};
   dims[0] = (cuuint64_t)p.Cin;
@@ -826,14 +827,16 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   if (!ws_enabled()) return -1;
   if (in_scale != nullptr && !in_relu) return -1;                       // NaN-fill halo needs the ReLU
   ffpn_conv_desc dp;
-  const bool pair = ffpn_make_pair_desc(d, &dp);                         // depth-strided projection conv -> stride-1 on the pair view
+  int in_mult = 1;
+  const bool strided111 = !transposed && ffpn_make_strided111_desc(d, &dp, &in_mult);   // strided 1x1x1 shortcut -> flat conv over a strided view
+  const bool pair = !strided111 && ffpn_make_pair_desc(d, &dp);          // depth-strided projection conv -> stride-1 on the pair view
   int pair2_on = -1;                                                      // read per call: tests toggle it
   // Measured on B200 (same box): level-1 16->16 forward 82.3 us plain vs 84.6 us on the pair view, level-2 32->32 54.1 vs 90.2 us, step 9.88
   // vs 10.13 ms -- the MMA / shared-memory work drops as predicted but the epilogue (N = 2 Cout columns per row, statistics by
   // shuffles) becomes the bound.  Correct (parity suite green with it on) but off unless FFPN_WS_PAIR2=1.
   if (pair2_on < 0) { const char* e = getenv("FFPN_WS_PAIR2"); pair2_on = (e && atoi(e) == 1) ? 1 : 0; }
-  bool pair2 = !pair && pair2_on && fin == nullptr && ffpn_make_pair2_desc(d, &dp);   // narrow 3-tap stride-1 conv -> pair view of input and output
-  WsPlan pl = make_ws_plan((pair || pair2) ? &dp : d, transposed, ctx->num_sms);
+  bool pair2 = !pair && !strided111 && pair2_on && fin == nullptr && ffpn_make_pair2_desc(d, &dp);   // narrow 3-tap stride-1 conv -> pair view of input and output
+  WsPlan pl = make_ws_plan((pair || pair2 || strided111) ? &dp : d, transposed, ctx->num_sms);
   if (pair2 && (!pl.ok || pl.nchunks != 1 || pl.p.kgu != 1 || pl.p.upt != 1 || pl.p.kX != 3)) {   // one resident K-group expected
     pair2 = false;
     pl = make_ws_plan(d, transposed, ctx->num_sms);
@@ -843,7 +846,7 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   const size_t need = (size_t)pl.nchunks * p.b_total_bytes;
   if (ws == nullptr || ws_bytes < need) return -1;
   CUtensorMap tmap;
-  if (!encode_ws_map(&tmap, pl, x, in_scale != nullptr)) return -1;
+  if (!encode_ws_map(&tmap, pl, x, in_scale != nullptr, in_mult)) return -1;
   const void* wimg;
   {
     TcParams q = pl.base.p;                                             // geometry + packmode of the shared packer
@@ -851,7 +854,7 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     if (pair) q.packmode = transposed ? 4 : 3;
     if (pair2) q.packmode = transposed ? 6 : 5;
     bool packed_now = false;
-    wimg = ffpn_tc_pack_weights(ctx, w, ws, d, q, pl.nchunks, p.Kc, st, &packed_now);   // d: the ORIGINAL descriptor (weight layout)
+    wimg = ffpn_tc_pack_weights(ctx, w, ws, strided111 ? &dp : d, q, pl.nchunks, p.Kc, st, &packed_now);   // d: the ORIGINAL descriptor (weight layout)
     if (packed_now) FFPN_CHECK_LAUNCH(ctx, "pack_weights");
   }
   p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)wimg; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
@@ -922,6 +925,16 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   }
   if (stat_rows) *stat_rows = (int)pl.grid.x;
   return 0;
+}
+
+// Would conv_ws_launch take this geometry (host-side planning only, no launch)?
+bool ffpn_conv_ws_supported(const ffpn_conv_desc* d, bool transposed, bool has_aff, bool relu) {
+  if (d->dtype != FFPN_BF16 || !ws_enabled()) return false;
+  if (has_aff && !relu) return false;
+  ffpn_conv_desc dp;
+  int mult = 1;
+  const bool view = (!transposed && ffpn_make_strided111_desc(d, &dp, &mult)) || ffpn_make_pair_desc(d, &dp);
+  return make_ws_plan(view ? &dp : d, transposed, 148).ok;
 }
 
 int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,

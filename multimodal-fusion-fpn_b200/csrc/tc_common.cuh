@@ -160,6 +160,20 @@ static inline bool ffpn_make_pair_desc(const ffpn_conv_desc* d, ffpn_conv_desc* 
   return true;
 }
 
+// The projection's shortcut, a 1x1x1 conv with stride (1,1,s) (fusion3D2D.py:317-326), reads every s-th depth position:
+// x[.., H, C] seen as x'[.., H/s, s*C] with only the first C channels of each row used -- a plain 1x1x1 conv over H/s
+// positions whose input rows are s*C elements apart.  The TMA tensor map expresses the row pitch, so the warp-specialised
+// flat (1x1x1) path runs it unchanged; *mult is the pitch multiplier for the input map.
+static inline bool ffpn_make_strided111_desc(const ffpn_conv_desc* d, ffpn_conv_desc* ds, int* mult) {
+  if (d->dtype != FFPN_BF16 || d->kS != 1 || d->kW != 1 || d->kH != 1 || d->sS != 1 || d->sW != 1 || d->sH <= 1 || d->pS != 0 ||
+      d->pW != 0 || d->pH != 0 || d->H % d->sH != 0 || d->oH != d->H / d->sH)
+    return false;
+  *ds = *d;
+  ds->H = d->H / d->sH; ds->sH = 1;
+  *mult = d->sH;
+  return true;
+}
+
 // Narrow stride-1 convs with three taps along the contiguous axis, (kS=1, kW, 3) pad (.,.,1), are shared-memory bound on the
 // tensor core's reads of the tap views.  On the pair view of input AND output -- x'[.., H/2, 2Cin],
 // y'[.., H/2, 2Cout] -- the conv is again a 3-tap stride-1 conv, W'[(ho,co)][(hi,ci)][t'] = W[co][ci][dx] with

@@ -525,8 +525,7 @@ def test_no_concat_copies_and_bucketed_step(mirror, monkeypatch):
         raise AssertionError('slice_copy launched: a concat member was copied')
     params = []
     for buckets in (True, False):
-        if not buckets:
-            monkeypatch.setenv('FFPN_NO_BUCKETS', '1')
+        monkeypatch.setenv('FFPN_BUCKETS', '1' if buckets else '0')
         model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
         model.load_state_dict(sd, strict=True)
         model.train()
