@@ -120,17 +120,19 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) conv_wgrad_ws_kernel(const __g
         int x1, x2, x3, y1, y2, y3;
         if (p.tma_mode == 0) { x1 = -p.hl + tc.nb * p.xseg; x2 = tc.it * p.tY - p.pY; x3 = tc.dt; y1 = 0; y2 = tc.it * p.tY; y3 = tc.dt; }
         else if (p.tma_mode == 1) { x1 = tc.it * p.L; x2 = tc.dt * p.tD - p.pD; x3 = tc.nb; y1 = x1; y2 = tc.dt * p.tD; y3 = tc.nb; }
-        else { x1 = 0; x2 = (tc.it * p.L) >> 8; x3 = 0; y1 = 0; y2 = x2; y3 = 0; }
+        else { x1 = tc.it * p.L; x2 = 0; x3 = 0; y1 = x1; y2 = 0; y3 = 0; }
+        const int nbox = p.tma_mode == 2 ? (p.L >> 8) : 1;        // flat: one box of 256 positions at a time
         if (!(p.dbg & 4))
         for (int j = 0; j < p.nys; j++)        // dy sub-tiles land 8 rows in: the rows before stay zero (shifted views)
         {
           const uint32_t ydst = dst + (uint32_t)(j * p.ysub_bytes) + 8u * (uint32_t)p.pitch_y;
           if (p.xseg) tma_load_5d(ydst, &tmy, co0 + j * p.Cy, 0, tc.nb, y2, y3, FULL(s));
-          else tma_load_4d(ydst, &tmy, co0 + j * p.Cy, y1, y2, y3, FULL(s));
+          else for (int b = 0; b < nbox; b++) tma_load_4d(ydst + (uint32_t)(b * 256 * p.pitch_y), &tmy, co0 + j * p.Cy, y1 + b * 256, y2, y3, FULL(s));
         }
         if (!(p.dbg & 4))
         for (int j = 0; j < p.nxs; j++)
-          tma_load_4d(dst + ybytes + (uint32_t)(j * p.xsub_bytes), &tmx, ci0 + j * p.Cx, x1, x2, x3, FULL(s));
+          for (int b = 0; b < nbox; b++)
+            tma_load_4d(dst + ybytes + (uint32_t)(j * p.xsub_bytes) + (uint32_t)(b * 256 * p.pitch_x), &tmx, ci0 + j * p.Cx, x1 + b * 256, x2, x3, FULL(s));
         if (++s == p.nstages) { s = 0; ph ^= 1u; wrapped = true; }
       }
     }
@@ -367,7 +369,7 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
   if (p.ntaps > 27) return w;
   const bool flat = (p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1 && p.kD == 1);
   if (p.kD > 1) { if (p.kY != 1 || p.kX != 1) return w; p.tma_mode = 1; p.kA = 1; p.kB = p.kD; }
-  else if (flat) { if (p.X % 256 != 0) return w; p.tma_mode = 2; p.kA = 1; p.kB = 1; }
+  else if (flat) { p.tma_mode = 2; p.kA = 1; p.kB = 1; }
   else {
     p.tma_mode = 0; p.kA = p.kX; p.kB = p.kY;
     if (p.Xp > 256) {
@@ -424,7 +426,7 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
         p.L = Lp;
       } else if (p.tma_mode == 2) {
         int nblk = Lmax / 256; if (nblk < 1) continue;
-        if (nblk * 256 > p.X) nblk = p.X / 256;
+        if (nblk * 256 > p.X) nblk = (p.X + 255) / 256;         // ragged tail: rows past the end are zero-filled by the TMA unit
         L = nblk * 256; Ls = 0; region_x = L;
         p.L = L;
       } else {
@@ -469,7 +471,7 @@ WgWsPlan make_wgrad_ws_plan(const ffpn_conv_desc* d, int num_sms) {
       w.xbox[0] = p.Cx; w.ybox[0] = p.Cy;
       if (p.tma_mode == 0) { w.xbox[1] = p.Xp; w.xbox[2] = tY + p.kY - 1; w.xbox[3] = 1; w.ybox[1] = p.Xp; w.ybox[2] = tY; w.ybox[3] = 1; }
       else if (p.tma_mode == 1) { w.xbox[1] = p.L; w.xbox[2] = tD + p.kD - 1; w.xbox[3] = 1; w.ybox[1] = p.L; w.ybox[2] = tD; w.ybox[3] = 1; }
-      else { w.xbox[1] = 256; w.xbox[2] = L / 256; w.xbox[3] = 1; w.ybox[1] = 256; w.ybox[2] = L / 256; w.ybox[3] = 1; }
+      else { w.xbox[1] = 256; w.xbox[2] = 1; w.xbox[3] = 1; w.ybox[1] = 256; w.ybox[2] = 1; w.ybox[3] = 1; }
       w.ok = true;
       return w;
     }
@@ -508,8 +510,8 @@ bool encode_wg_map(CUtensorMap* m, const WgWsPlan& w, const void* base, bool is_
     dims[1] = eX; dims[2] = eD; dims[3] = p.NB;
     strides[0] = cb; strides[1] = (cuuint64_t)sD * cb; strides[2] = (cuuint64_t)(p.NB > 1 ? sNB : sD * eD) * cb;
   } else {
-    dims[1] = 256; dims[2] = eX / 256; dims[3] = 1;
-    strides[0] = cb; strides[1] = 256 * cb; strides[2] = (cuuint64_t)eX * cb;
+    dims[1] = (cuuint64_t)eX; dims[2] = 1; dims[3] = 1;      // flat: positions are one dimension, loaded 256 at a time
+    strides[0] = cb; strides[1] = (cuuint64_t)eX * cb; strides[2] = (cuuint64_t)eX * cb;
   }
   for (int i = 0; i < 4; i++) box[i] = (cuuint32_t)(is_x ? w.xbox[i] : w.ybox[i]);
   const int pitch = is_x ? p.pitch_x : p.pitch_y;

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         int c1, c2, c3;
         if (p.tma_mode == 0) { c1 = -p.hl + tc.nb * p.xseg; c2 = tc.it * p.tY - p.pY; c3 = tc.d0; }
         else if (p.tma_mode == 1) { c1 = tc.i0; c2 = tc.d0 - p.pD; c3 = tc.nb; }
-        else { c1 = 0; c2 = tc.i0 >> p.fshift; c3 = 0; }
+        else { c1 = tc.i0; c2 = 0; c3 = 0; }
         for (int uk = 0; uk < p.upt; uk++) {
           const int s = ring.stage(r, p);
           if (r ? wrapped1 : wrapped0) mbar_wait(EMPTY(s), ring.phase(r) ^ 1u);
@@ -176,8 +176,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           const uint32_t dst = smem_u32(stage0) + (uint32_t)s * (uint32_t)p.stage_bytes;
           mbar_expect_tx(FULL(s), (p.dbg & 4) ? 0u : p.tx_bytes);
           if (!(p.dbg & 4)) {
-            for (int kgi = 0; kgi < p.kgu; kgi++)
-              tma_load_4d(dst + (uint32_t)(kgi * p.sub_bytes), &tmap, (uk * p.kgu + kgi) * p.Kc, c1, c2, c3, FULL(s));
+            for (int kgi = 0; kgi < p.kgu; kgi++) {
+              if (p.tma_mode == 2) {                       // flat: one box of 2^fshift positions at a time (rows past the end are filled)
+                for (int b = 0; b < (p.L >> p.fshift); b++)
+                  tma_load_4d(dst + (uint32_t)(kgi * p.sub_bytes) + (uint32_t)((b << p.fshift) * p.pitch), &tmap, (uk * p.kgu + kgi) * p.Kc,
+                              c1 + (b << p.fshift), 0, 0, FULL(s));
+              } else {
+                tma_load_4d(dst + (uint32_t)(kgi * p.sub_bytes), &tmap, (uk * p.kgu + kgi) * p.Kc, c1, c2, c3, FULL(s));
+              }
+            }
             if (!p.w_resident) bulk_g2s(dst + (uint32_t)p.a_unit_bytes, wp + (size_t)uk * p.b_unit_bytes, p.b_unit_bytes, FULL(s));
           }
           if (ring.advance(r, p)) { if (r) wrapped1 = true; else wrapped0 = true; }
@@ -685,13 +692,13 @@ WsPlan make_ws_plan_with(const ffpn_conv_desc* d, bool transposed, int num_sms, 
           region = (tD + p.kD - 1) * L; mode = 1;
           if (tD + p.kD - 1 > 256 || L > 256) continue;
         } else if (p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1) {
-          const int unit = (max_rows >= 256 && p.X % 256 == 0) ? 256 : 128;
-          if (p.X % unit != 0) break;
+          // flat 1x1x1: the positions are ONE tensor-map dimension, loaded unit (<= 256, the TMA box limit) rows at a time;
+          // a ragged tail (X not a multiple of the unit) is filled by the TMA unit and clipped by the epilogue
+          const int unit = (max_rows >= 256 && p.X >= 256) ? 256 : 128;
           int nblk = max_rows / unit; if (nblk < 1) continue;
-          if (nblk * unit > p.X) nblk = p.X / unit;
+          if (nblk * unit > p.X) nblk = (p.X + unit - 1) / unit;
           L = nblk * unit; Lr = L; tD = 1; region = L; mode = 2;
           p.fshift = unit == 256 ? 8 : 7;
-          if (nblk > 256) continue;
         } else {
           if (p.Xp > 256) break;
           tY = max_rows / p.Xp;
@@ -747,7 +754,7 @@ WsPlan make_ws_plan_with(const ffpn_conv_desc* d, bool transposed, int num_sms, 
         w.box[0] = Kc;
         if (mode == 0) { w.box[1] = p.Xp; w.box[2] = tY + p.kY - 1; w.box[3] = tD; }
         else if (mode == 1) { w.box[1] = L; w.box[2] = tD + p.kD - 1; w.box[3] = 1; }
-        else { w.box[1] = 1 << p.fshift; w.box[2] = L >> p.fshift; w.box[3] = 1; }
+        else { w.box[1] = 1 << p.fshift; w.box[2] = 1; w.box[3] = 1; }
         w.ok = true;
         return w;
       }
@@ -802,8 +809,8 @@ bool encode_ws_map(CUtensorMap* m, const WsPlan& w, const void* x, bool nan_fill
     strides[0] = cb; strides[1] = (cuuint64_t)c.inD * cb;
     strides[2] = (cuuint64_t)(p.NB > 1 ? c.inNB : (long long)c.inD * p.D) * cb;
   } else {
-    dims[1] = 1u << p.fshift; dims[2] = (cuuint64_t)p.X >> p.fshift; dims[3] = 1;
-    strides[0] = cb; strides[1] = ((cuuint64_t)1 << p.fshift) * cb; strides[2] = (cuuint64_t)p.X * cb;
+    dims[1] = (cuuint64_t)p.X; dims[2] = 1; dims[3] = 1;
+    strides[0] = cb; strides[1] = (cuuint64_t)p.X * cb; strides[2] = (cuuint64_t)p.X * cb;
   }
   for (int i = 0; i < 4; i++) box[i] = (cuuint32_t)w.box[i];
   const CUtensorMapSwizzle sw = p.pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;

@@ -41,7 +41,8 @@ CASES = [
     ('l1_311', 16, 16, (3, 1, 1), (1, 0, 0), (2, 8, 16, 128)),
     ('l3_311', 64, 64, (3, 1, 1), (1, 0, 0), (2, 12, 32, 32)),
     ('l5_311', 256, 256, (3, 1, 1), (1, 0, 0), (2, 8, 8, 8)),
-    ('sc_111', 16, 32, (1, 1, 1), (0, 0, 0), (2, 3, 20, 24)),
+    ('sc_111', 16, 32, (1, 1, 1), (0, 0, 0), (2, 3, 20, 24)),            # 2880 positions: ragged tail of the flat tiles
+    ('sc_111_tiny', 64, 32, (1, 1, 1), (0, 0, 0), (1, 2, 5, 7)),           # 70 positions: less than one TMA box
     ('sc_111_big', 128, 256, (1, 1, 1), (0, 0, 0), (1, 4, 8, 8)),
     # flat mode with > 2^16 positions (regression: reciprocal division in the epilogue must stay exact)
     ('sc_111_p160k', 16, 32, (1, 1, 1), (0, 0, 0), (8, 320, 64, 1)),
@@ -71,8 +72,7 @@ CASES = [
 
 
 # (case, which calls) the tcgen05 kernels decline -> CUDA-core route (impl 0); everything else must run on tensor cores (impl 2)
-GENERIC = {'sc_111': ('fwd', 'dgrad', 'wgrad'), 'odd_133': ('wgrad',), 'wide_133_301': ('wgrad',), 'sc_111_big': ('wgrad',),
-           'proj_114': (), 'sc_s16_496': ()}
+GENERIC = {'odd_133': ('wgrad',), 'wide_133_301': ('wgrad',)}
 
 
 def _impl(name, call):
