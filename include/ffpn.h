@@ -64,6 +64,10 @@ int ffpn_route_counts(ffpn_ctx* ctx, int64_t* out4);
 /* bit 0: built with -DFFPN_DEBUG (the result-invalidating ablation / trace switches FFPN_TC_DEBUG, FFPN_WS_TRACE are
  * compiled in).  The release library returns 0 and ignores those variables. */
 int ffpn_build_info(void);
+/* Host-only plan introspection (no GPU needed): writes a one-line description of how the forward (transposed = 0), dgrad
+ * (transposed = 1) or weight gradient (transposed = 2) of this conv runs on the warp-specialised tcgen05 kernels, or that it is
+ * not taken by them ("not on the warp-specialised kernel ..."). */
+int ffpn_conv_plan_info(const ffpn_conv_desc* d, int transposed, char* buf, size_t n);
 /* bytes of scratch a conv call of this geometry may use (packed bf16 weights for the tcgen05 path) */
 size_t ffpn_conv_workspace_bytes(const ffpn_conv_desc* d);
 

@@ -176,116 +176,9 @@ Plan ffpn_tc_make_plan(const ffpn_conv_desc* d, bool transposed, int num_sms) {
   const int hr = qmax + p.hl;
   p.Xp = p.oX + hr;
   p.Qout = (p.oY - 1) * p.Xp + p.oX;
-  const int ntaps = p.kD * p.kY * p.kX;
-  const int maxinner = (p.kY - 1) * p.Xp + hr;
-  p.colstride = p.Npad < 32 ? 32 : p.Npad;
-  // K-group: largest of Cin(<=64)/64/32/16 whose weight image fits 72 KB
-  int KG = 64;
-  while (KG > 16 && (Cin % KG != 0 || (size_t)ntaps * KG * p.Npad * 2 > 72 * 1024)) KG >>= 1;
-  if (Cin % KG != 0) return pl;
-  if ((size_t)ntaps * KG * p.Npad * 2 > 200 * 1024) return pl;
-  p.KG = KG; p.nkg = Cin / KG;
-  p.b_bytes = (unsigned)((size_t)ntaps * KG * p.Npad * 2);
-  const uint32_t hdr = (HDR_STATS + 16 * p.Npad * 4 + 127) & ~127u;
-  const size_t fixed = hdr + 8 * 32 * SCR_STRIDE * 4 + (size_t)(p.nkg > 1 ? 2 : 1) * p.b_bytes;
-  // Tile size: bounded by the TMEM columns and shared memory of the target occupancy.  Several CTAs per SM is
-  // what overlaps one CTA's staging / epilogue with another's MMAs, so small-N layers aim for 4 CTAs per SM.
-  if (ntaps > 27) return pl;
-  // {CTAs per SM, TMEM columns per CTA}: two accumulator buffers (tile parity) share the columns
-  // budgets: {CTAs per SM, TMEM columns per CTA, buffers}.  First the single-buffer 4-CTA/SM variant (narrow layers with
-  // resident weights), then the two-stage pipeline with two accumulator buffers sharing the columns.
-  const int budgets[3][3] = {{4, 128, 1}, {2, 256, 2}, {1, 512, 2}};
-  for (int bi = 0; bi < 3; bi++) {
-    const int per_sm = budgets[bi][0], nbuf = budgets[bi][2];
-    if (nbuf == 1 && (p.nkg != 1 || p.colstride > 32)) continue;
-    int nmb_max = budgets[bi][1] / nbuf / p.colstride;
-    if (nmb_max > 8) nmb_max = 8;
-    if (nmb_max < (bi == 2 ? 1 : 2)) continue;
-    const size_t smem_cap = (size_t)(227 * 1024) / per_sm - 1024;
-    for (; nmb_max >= (bi == 2 ? 1 : 2); nmb_max--) {
-      const int max_rows = nmb_max * 128;
-      int tD = 1, L = 0, Lr = 0, region = 0, tY = 0, tma_mode = -1;
-      bool tma = false;
-      // ---- tiles that are TMA boxes: whole lines (mode 0), slice runs (mode 1), 256-row blocks (mode 2) ----
-      if (p.sX == 1) {
-        if (p.kD > 1) {
-          L = p.X < 128 ? p.X : 128; Lr = L;
-          tD = max_rows / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
-          region = (tD + p.kD - 1) * L;
-          tma = tD + p.kD - 1 <= 256; tma_mode = 1;
-        } else if (p.Y == 1 && p.D == 1 && p.kY == 1 && p.kX == 1) {
-          if (p.X % 256 == 0) {
-            int nblk = max_rows / 256; if (nblk < 1) nblk = 1;
-            if (nblk * 256 > p.X) nblk = p.X / 256;
-            L = nblk * 256; Lr = L; tD = 1; region = L;
-            tma = nblk <= 256 && max_rows >= 256; tma_mode = 2;
-          }
-        } else if (p.Xp <= 256) {
-          tY = max_rows / p.Xp;
-          if (tY >= 1) {
-            if (tY >= p.oY) {
-              tY = p.oY;
-              Lr = (tY + p.kY - 1) * p.Xp;
-              tD = (max_rows - tY * p.Xp) / Lr + 1; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
-            } else {
-              Lr = (tY + p.kY - 1) * p.Xp; tD = 1;
-            }
-            L = tY * p.Xp; region = tD * Lr;
-            tma = tY + p.kY - 1 <= 256 && tD <= 256; tma_mode = 0;
-          }
-        }
-      }
-      if (!tma) {
-        tma_mode = -1; tY = 0;
-        if (p.kD > 1) {
-          L = p.X < 128 ? p.X : 128; Lr = L;
-          tD = max_rows / L; if (tD > p.oD) tD = p.oD; if (tD < 1) tD = 1;
-        } else if (p.Qout >= max_rows) {
-          const int nt = (p.Qout + max_rows - 1) / max_rows;
-          L = (((p.Qout + nt - 1) / nt) + 127) & ~127; if (L > max_rows) L = max_rows;
-          Lr = L + maxinner; tD = 1;
-        } else {
-          L = p.Qout; Lr = L + maxinner;
-          tD = (max_rows - L) / Lr + 1; if (tD > p.oD) tD = p.oD;
-        }
-        region = (tD + p.kD - 1) * Lr;
-      }
-      const int M_total = (tD - 1) * Lr + L;
-      const int nmb = (M_total + 127) / 128;
-      const int maxoff = (p.kD - 1) * Lr + maxinner;
-      int rows_alloc;
-      size_t a_bytes;
-      if (tma) {
-        rows_alloc = (region + 7) & ~7;                           // each plane is its own TMA box; 128-byte aligned
-        const int over = nmb * 128 + maxoff - rows_alloc;         // MMA rows read past the last plane
-        a_bytes = (size_t)(KG / 8) * rows_alloc * 16 + (size_t)(over > 0 ? over : 0) * 16;
-      } else {
-        rows_alloc = nmb * 128 + maxoff;
-        if (rows_alloc < region) rows_alloc = region;
-        a_bytes = (size_t)p.nsets * rows_alloc * KG * 2;
-      }
-      a_bytes = (a_bytes + 127) & ~(size_t)127;
-      const size_t smem = fixed + (size_t)nbuf * a_bytes;
-      if (smem > smem_cap) continue;
-      pl.simple = nbuf == 1;
-      p.tD = tD; p.L = L; p.Lr = Lr; p.tY = tY;
-      p.use_tma = tma ? 1 : 0; p.tma_mode = tma_mode;
-      p.rows_alloc = rows_alloc; p.region_rows = region;
-      p.tma_bytes = (unsigned)((size_t)(KG / 8) * region * 16);
-      p.a_bytes = (unsigned)a_bytes;
-      int cols = nmb * p.colstride, tc = 32;
-      while (tc < cols) tc <<= 1;
-      if (nbuf == 2) tc <<= 1;                        // two accumulator buffers
-      p.tmem_cols = tc;
-      p.nD = (p.oD + tD - 1) / tD;
-      p.nI = (p.Qout + L - 1) / L;
-      pl.smem = smem;
-      const int ntiles = p.NB * p.nD * p.nI;
-      pl.grid = ntiles < per_sm * num_sms ? ntiles : per_sm * num_sms;
-      pl.ok = ((uint64_t)p.nsets * (KG / 8) * rows_alloc * 16 < (1u << 18)) && tc <= 512;
-      return pl;
-    }
-  }
+  // Geometry only: the kernels tile on top of it (make_ws_plan, make_wgrad_ws_plan) and decide themselves what they take.
+  if (p.kD * p.kY * p.kX > 27) return pl;
+  pl.ok = true;
   return pl;
 }
 

@@ -934,6 +934,33 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   return 0;
 }
 
+// Plan introspection (host only, no GPU needed): which kernel family takes this conv and how it is tiled.
+bool ffpn_wgrad_ws_supported(const ffpn_conv_desc* d);
+extern "C" int ffpn_conv_plan_info(const ffpn_conv_desc* d, int transposed, char* buf, size_t n) {
+  if (!d || !buf || n == 0) return 1;
+  if (transposed == 2) {                                    // weight gradient
+    snprintf(buf, n, ffpn_wgrad_ws_supported(d) ? "conv_wgrad_ws" : "not on the warp-specialised kernel (weight gradient)");
+    return 0;
+  }
+  ffpn_conv_desc dp;
+  int mult = 1;
+  const bool s111 = !transposed && ffpn_make_strided111_desc(d, &dp, &mult);
+  const bool pair = !s111 && ffpn_make_pair_desc(d, &dp);
+  const Plan base = ffpn_tc_make_plan((s111 || pair) ? &dp : d, transposed != 0, 148);
+  const WsPlan pl = make_ws_plan((s111 || pair) ? &dp : d, transposed != 0, 148);
+  if (!pl.ok) {
+    snprintf(buf, n, "not on the warp-specialised kernel (base geometry %s, view %s)", base.ok ? "ok" : "unsupported",
+             s111 ? "strided-1x1x1" : pair ? "pair" : "none");
+    return 0;
+  }
+  const WsParams& p = pl.p;
+  snprintf(buf, n, "conv_ws %s view %s: Cin %d Cout %d Npad %d x%d taps %dx%dx%d mode %d tD %d tY %d L %d Lr %d Kc %d kgu %d upt %d resident %d "
+           "stages %d issuers %d smem %zu tmem %d x%d grid (%u,%u) tiles %d", transposed ? "dgrad" : "fwd", s111 ? "strided-1x1x1" : pair ? "pair" : "none",
+           p.Cin, p.Cout, p.Npad, pl.nchunks, p.kD, p.kY, p.kX, p.tma_mode, p.tD, p.tY, p.L, p.Lr, p.Kc, p.kgu, p.upt, p.w_resident, p.nstages, p.niss,
+           pl.smem, p.tmem_cols, p.nbuf, pl.grid.x, pl.grid.y, p.NB * p.nD * p.nI);
+  return 0;
+}
+
 // Would conv_ws_launch take this geometry (host-side planning only, no launch)?
 bool ffpn_conv_ws_supported(const ffpn_conv_desc* d, bool transposed, bool has_aff, bool relu) {
   if (d->dtype != FFPN_BF16 || !ws_enabled()) return false;

@@ -74,6 +74,7 @@ NO_CTX = {
     'ffpn_last_error': ([_P], C.c_char_p),
     'ffpn_launch_count': ([_P], C.c_int64),
     'ffpn_conv_workspace_bytes': ([_DP], C.c_size_t),
+    'ffpn_conv_plan_info': ([_DP, _I, C.c_char_p, _Z], C.c_int),
     'ffpn_head_bwd_workspace_bytes': ([_I, _I], C.c_size_t),
     'ffpn_mix_loss_workspace_bytes': ([_I], C.c_size_t),
 }

@@ -303,3 +303,55 @@ def test_ensemble_averages_like_the_reference():
         ck.average_outputs([1, 2], int)
     with pytest.raises(ValueError):
         ck.Ensemble([])
+
+
+def _conv_geometries(B, S, H, W, S2, W2, ch=(16, 32, 64, 128, 256)):
+    """Every convolution of one FPNHybridFusion forward as (phys input shape, cout, kernel, stride, pad), from the shape algebra
+    of SURVEY.md App. A / B (pools floor, projection halves with ceil)."""
+    out = []
+    sp3 = [(S, W, H), (S, W // 2, H // 2), (S, W // 4, H // 4), (S // 2, W // 8, H // 8), (S // 4, W // 16, H // 16)]
+    sp2 = [(S2, W2), (S2, W2 // 2), (S2, W2 // 4), (S2 // 2, W2 // 8), (S2 // 4, W2 // 16)]
+    for l in range(5):
+        cin, c = (1 if l == 0 else ch[l - 1]), ch[l]
+        s, w, h = sp3[l]
+        out += [((B, s, w, h, cin), c, (1, 3, 3), (1, 1, 1), (0, 1, 1)), ((B, s, w, h, cin), c, (1, 1, 1), (1, 1, 1), (0, 0, 0))]
+        out += [((B, s, w, h, c), c, (1, 3, 3), (1, 1, 1), (0, 1, 1)), ((B, s, w, h, c), c, (3, 1, 1), (1, 1, 1), (1, 0, 0))]
+        n, hh = 4 - l, h
+        if n > 0:
+            out.append(((B, s, w, h, c), c, (1, 1, 1), (1, 1, 2 ** n), (0, 0, 0)))
+        for _ in range(n):
+            out.append(((B, s, w, hh, c), c, (1, 1, 3), (1, 1, 2), (0, 0, 1)))
+            hh = (hh - 1) // 2 + 1
+        out.append(((B, s, w, hh, c), c, (1, 1, 4), (1, 1, 1), (0, 0, 0)))
+        s2, w2 = sp2[l]
+        out += [((B, s2, w2, 1, cin), c, (1, 3, 1), (1, 1, 1), (0, 1, 0)), ((B, s2, w2, 1, cin), c, (1, 1, 1), (1, 1, 1), (0, 0, 0))]
+        out += [((B, s2, w2, 1, c), c, (1, 3, 1), (1, 1, 1), (0, 1, 0)), ((B, s2, w2, 1, c), c, (3, 1, 1), (1, 1, 1), (1, 0, 0))]
+    for l in (4, 3, 2, 1):
+        low, cur = (ch[4] * 2 if l == 4 else ch[l]), ch[l - 1]
+        s, w, _ = sp3[l - 1]
+        out += [((B, s, w, 1, low + 2 * cur), cur, (3, 3, 1), (1, 1, 1), (1, 1, 0)), ((B, s, w, 1, cur), cur, (3, 3, 1), (1, 1, 1), (1, 1, 0)),
+                ((B, s, w, 1, low + 2 * cur), cur, (1, 1, 1), (1, 1, 1), (0, 0, 0))]
+    return out
+
+
+@pytest.mark.parametrize('shape', [(1, 64, 128, 128, 128, 128), (8, 32, 128, 128, 320, 128), (8, 32, 496, 128, 320, 128),
+                                   (16, 32, 128, 128, 320, 128), (2, 8, 64, 32, 20, 48)],
+                         ids=['C1', 'C2', 'C3', 'C4', 'toy'])
+def test_every_conv_of_the_model_has_a_tensor_core_plan(shape):
+    """Host-only plan introspection (ffpn_conv_plan_info): at every BASELINE.json shape -- and at the toy shape of the golden
+    fixtures -- forward, dgrad and weight gradient of every convolution with Cin >= 16 are taken by the warp-specialised tcgen05
+    kernels (the Cin == 1 stems have their own streaming kernels); nothing on the bf16 path falls to the CUDA-core kernels."""
+    import ctypes as C
+    from ffpn import lib, ops
+    handle = lib.load()
+    buf = C.create_string_buffer(800)
+    missing = []
+    for (x_shape, cout, k, s, p) in _conv_geometries(*shape):
+        if x_shape[-1] == 1:
+            continue
+        d = ops.make_desc(x_shape, cout, k, s, p, torch.bfloat16)
+        for mode, what in ((0, 'fwd'), (1, 'dgrad'), (2, 'wgrad')):
+            assert handle.ffpn_conv_plan_info(C.byref(d), mode, buf, 800) == 0
+            if buf.value.decode().startswith('not on'):
+                missing.append((what, x_shape, cout, k, s))
+    assert not missing, missing
