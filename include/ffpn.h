@@ -205,6 +205,16 @@ int ffpn_pack_volume(ffpn_ctx* ctx, int dtype, int64_t R, int64_t H, int64_t W, 
                      void* stream);
 int ffpn_cast(ffpn_ctx* ctx, int dtype, int64_t n, const float* src, void* dst, void* stream);
 
+/* ---- input pipeline / evaluation metric around the path ---------------------------------
+ * z-score of every one of R slices of n contiguous fp32 values: y = (x - mean) / (std + eps), population std
+ * (ZScoreNormalization(axis=(2,3)), common/mytransforms.py:277-296 with training_config.py:60: a slice = one B-scan of the
+ * (B,1,S,H,W) volume, R = B*S, n = H*W).  stats: scratch of 2*R floats (mean, 1/(std+eps) per slice); y may alias x. */
+int ffpn_zscore_slices(ffpn_ctx* ctx, int64_t R, int64_t n, const float* x, float eps, float* stats, float* y, void* stream);
+/* Dice metric of common/metrics.py:216-253: out[b] = 2 |P & G| / (|P| + |G|) for sample b on channel `slice` of the
+ * (B, n_channels, per_channel) prediction / mask thresholded at pred_threshold / target_threshold; 1 when both are empty. */
+int ffpn_dice_metric(ffpn_ctx* ctx, int64_t B, int n_channels, int64_t per_channel, int slice, float pred_threshold,
+                     float target_threshold, const float* pred, const float* mask, float* out, void* stream);
+
 /* ---- optimiser: torch.optim.SGD(momentum, weight_decay) of train.py:126-133 on flat fp32 buffers;
  *      g is first scaled by grad_scale (1/world_size after the NCCL sum all-reduce). ----------------- */
 int ffpn_sgd_step(ffpn_ctx* ctx, int64_t n, float* p, const float* g, float* mom, float lr, float momentum,

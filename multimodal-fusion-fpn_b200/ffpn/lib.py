@@ -59,6 +59,8 @@ SIGNATURES = {
     'ffpn_pack_volume': [_I, _L, _L, _L, _P, _P, _P],
     'ffpn_cast': [_I, _L, _P, _P, _P],
     'ffpn_sgd_step': [_L, _P, _P, _P, _F, _F, _F, _F, _I, _P],
+    'ffpn_zscore_slices': [_L, _L, _P, _F, _P, _P, _P],
+    'ffpn_dice_metric': [_L, _I, _L, _I, _F, _F, _P, _P, _P, _P],
     'ffpn_weight_arena_begin': [_P, _Z],
     'ffpn_weight_arena_seal': [],
     'ffpn_weight_arena_pack': [_P],

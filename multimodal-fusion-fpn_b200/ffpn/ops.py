@@ -366,6 +366,30 @@ def sgd_step(p, g, mom, lr, momentum, weight_decay, grad_scale, first_step):
              float(weight_decay), float(grad_scale), int(bool(first_step)), _stream(p))
 
 
+def zscore_bscans(image: torch.Tensor, eps: float = 1e-8, out=None) -> torch.Tensor:
+    """(B,1,S,H,W) fp32 volume -> every B-scan z-scored over (H,W): (x - mean) / (std + eps), population std
+    (ZScoreNormalization(axis=(2,3)), mytransforms.py:277-296).  ``out`` may be ``image`` itself (in place)."""
+    if image.dtype != torch.float32 or not image.is_contiguous() or image.dim() < 3:
+        raise lib.FfpnError('zscore_bscans expects a contiguous fp32 (..., H, W) tensor')
+    n = image.shape[-1] * image.shape[-2]
+    R = image.numel() // n
+    y = torch.empty_like(image) if out is None else out
+    stats = torch.empty(2 * R, dtype=torch.float32, device=image.device)
+    lib.call('ffpn_zscore_slices', _dev(image), R, n, _ptr(image), float(eps), _ptr(stats), _ptr(y), _stream(image))
+    return y
+
+
+def dice_metric(pred: torch.Tensor, mask: torch.Tensor, channel: int = 0, pred_threshold: float = 0.5, target_threshold: float = 0.5):
+    """Per-sample Dice of metrics.py:216-253 -> (B,) fp32 on the device (no synchronisation)."""
+    pc, mc = pred.contiguous().float(), mask.contiguous().float()
+    B, n = pc.shape[0], pc.shape[1]
+    per = pc.numel() // (B * n)
+    out = torch.empty(B, dtype=torch.float32, device=pc.device)
+    lib.call('ffpn_dice_metric', _dev(pc), B, n, per, int(channel), float(pred_threshold), float(target_threshold), _ptr(pc), _ptr(mc),
+             _ptr(out), _stream(pc))
+    return out
+
+
 # ---- packed-weight arena (include/ffpn.h: ffpn_weight_arena_*) ---------------------------------------------
 def weight_arena_begin(arena: torch.Tensor):
     lib.call('ffpn_weight_arena_begin', _dev(arena), _ptr(arena), arena.numel() * arena.element_size())

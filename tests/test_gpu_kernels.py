@@ -352,3 +352,39 @@ def test_pack_volume_and_sgd(ops):
         O.sgd_step(params, {'p': gr * (step + 1)}, bufs, 0.1, 0.9, 1e-4)
         ops.sgd_step(pc, (gr * (step + 1) * 4).cuda(), mom, 0.1, 0.9, 1e-4, 0.25, step == 0)
     assert rel(pc.cpu(), params['p']) <= 1e-6
+
+
+def test_zscore_bscans_and_device_dice(ops):
+    """GPU input pipeline / metric kernels against the reference's formulas restated in numpy: ZScoreNormalization(axis=(2,3))
+    (mytransforms.py:277-296: population std, eps 1e-8 added to the std) and metrics.Dice.calculate_batch (metrics.py:232-253:
+    thresholds 0.5, per sample, 1 where both are empty)."""
+    from ffpn.pipeline import DeviceDice, GpuInputPipeline
+    g = torch.Generator().manual_seed(31)
+    img = (torch.randn(2, 1, 5, 37, 45, generator=g) * 800 + 9000)
+    img[1, 0, 3] = 7.0                                          # a constant B-scan: std 0 -> (x - mean) / 1e-8 = 0
+    x = img.numpy()[:, 0]                                       # the dataloader's [1, S, H, W] per sample
+    want = np.stack([(v - v.mean(axis=(1, 2), keepdims=True)) / (v.std(axis=(1, 2), keepdims=True) + 1e-8) for v in x])[:, None]
+    got = ops.zscore_bscans(img.cuda())
+    assert np.allclose(got.cpu().numpy(), want, rtol=1e-4, atol=2e-4)
+    pipe = GpuInputPipeline()
+    host = {'image': img.pin_memory(), 'mask': (torch.rand(2, 1, 5, 1, 45, generator=g) > 0.5).float().pin_memory()}
+    for _ in range(3):                                          # both buffer sets, reuse
+        pipe.prepare(host)
+        dev = pipe.get()
+        assert np.allclose(dev['image'].cpu().numpy(), want, rtol=1e-4, atol=2e-4) and torch.equal(dev['mask'].cpu(), host['mask'])
+        pipe.release()
+    pred = torch.rand(3, 2, 6, 1, 40, generator=g)
+    mask = (torch.rand(3, 2, 6, 1, 40, generator=g) > 0.6).float()
+    pred[2], mask[2] = 0.1, 0.0                                 # empty prediction and mask -> 1
+    for ch in (0, 1):
+        p, t = (pred[:, ch] > 0.5).float().view(3, -1), (mask[:, ch] > 0.5).float().view(3, -1)
+        num, den = (p * t).sum(1).numpy(), (p + t).sum(1).numpy()
+        r = 2 * num / np.where(den == 0, 1, den)
+        r[den == 0] = 1
+        m = DeviceDice('prediction', 'mask', slice=ch)
+        m.update({'mask': mask.cuda()}, {'prediction': pred.cuda()})
+        m.update({'mask': mask.cuda()}, {'prediction': pred.cuda()})
+        assert np.allclose(m.accumulator[0].cpu().numpy(), r, atol=1e-6)
+        assert abs(m.get() - float(np.nanmean(np.concatenate([r, r])))) <= 1e-6
+        m.reset()
+        assert m.accumulator == []
