@@ -71,6 +71,64 @@ def save_checkpoint(module: nn.Module, path: str, epoch: int = 0, global_step: i
                path)
 
 
+class InferenceArena:
+    """Packed bf16 weight images for eval-mode forwards of one or several models on a device: recorded during the first
+    forward, looked up afterwards (no per-conv weight-packing launch), regenerated when any parameter changed (tensor version
+    counters).  Uses the per-device packed-weight arena of the library, which has one owner at a time (a live FusionTrainer on
+    the same device keeps it: the session then simply runs without an arena)."""
+
+    def __init__(self, modules: Iterable[nn.Module], device):
+        from . import trainer as _t
+        self._t = _t
+        self.params = [p for m in modules for p in m.parameters()]
+        self.device = torch.device(device)
+        self.dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _t._ARENA_TOKENS[0] += 1
+        self.token = _t._ARENA_TOKENS[0]
+        self.state, self.buf, self.versions = 0, None, None        # 0 none, 1 recording, 2 sealed
+
+    def _version(self):
+        return sum(p._version for p in self.params)
+
+    def __enter__(self):
+        from . import ops
+        from .functional import get_compute_dtype
+        if get_compute_dtype() != torch.bfloat16 or torch.cuda.is_current_stream_capturing():
+            return self
+        if self.state == 0 and self._t._ARENA_OWNER.get(self.dev) is None:
+            self.buf = torch.empty(96 << 20, dtype=torch.uint8, device=self.device)
+            ops.weight_arena_begin(self.buf)
+            self._t._ARENA_OWNER[self.dev] = self.token
+            self.state, self.versions = 1, self._version()
+        elif self.state == 2:
+            if self._version() != self.versions:
+                ops.weight_arena_pack(self.buf)
+                self.versions = self._version()
+            ops.weight_arena_enable(self.dev, True)
+        return self
+
+    def __exit__(self, *exc):
+        from . import ops
+        if self.state == 1:
+            ops.weight_arena_seal(self.dev)
+            self.state = 2
+        if self.state == 2:
+            ops.weight_arena_enable(self.dev, False)
+
+    def close(self):
+        if self.state and self._t._ARENA_OWNER.get(self.dev) == self.token:
+            from . import ops
+            ops.weight_arena_end(self.dev)
+            del self._t._ARENA_OWNER[self.dev]
+        self.state, self.buf = 0, None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Ensemble(nn.Module):
     """The evaluation ensemble of ``test_utils.run_evaluation_instance``: all members in ``eval()`` mode (BatchNorm on
     running statistics), one forward each under ``no_grad``, outputs averaged."""
@@ -97,5 +155,12 @@ class Ensemble(nn.Module):
 
     @torch.no_grad()
     def forward(self, batch):
-        outputs = [m(batch) for m in self.members]
+        first = next(self.members[0].parameters())
+        if first.is_cuda:
+            if getattr(self, '_arena', None) is None:
+                self._arena = InferenceArena(self.members, first.device)
+            with self._arena:
+                outputs = [m(batch) for m in self.members]
+        else:
+            outputs = [m(batch) for m in self.members]
         return average_outputs(outputs, type(outputs[0]))
