@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FFPN_ABI_VERSION 2
+#define FFPN_ABI_VERSION 3
 #define FFPN_F32 0
 #define FFPN_BF16 1
 /* rows of a per-block partial-statistics buffer: [FFPN_STAT_ROWS][ncols] floats */
@@ -94,6 +94,16 @@ int ffpn_conv_fwd_bn(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, cons
  *        fusion3D2D.py:724-725's backward. */
 int ffpn_conv_dgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* dy, const float* w,
                     const void* addend, void* dx, void* ws, size_t ws_bytes, void* stream);
+/* dgrad + pass 1 of the backward of the BatchNorm + ReLU that produced the conv's input, as ONE call (the backward of
+ *        fusion3D2D.py:717-732's conv -> BN -> ReLU -> conv: aten::convolution_backward's grad_input followed by
+ *        aten::threshold_backward and the reductions of aten::native_batch_norm_backward).  y_prev is that BatchNorm's raw
+ *        input (the previous conv's output, same shape/dtype as dx), bn_scale / bn_shift its affine.  dx receives
+ *        conv_transpose(dy, w) exactly as ffpn_conv_dgrad writes it; partial receives [rows][2][Cin] = sums of G and
+ *        G*y_prev with G = dx * (bn_scale*y_prev + bn_shift > 0), what ffpn_bn_bwd_reduce(dx, y_prev, relu=1) produces.  On the tcgen05 path the sums come
+ *        out of the dgrad kernel's epilogue (no extra pass over dx and y_prev); otherwise the two kernels are launched. */
+int ffpn_conv_dgrad_bnr(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* dy, const float* w, const void* y_prev,
+                        const float* bn_scale, const float* bn_shift, void* dx, float* partial, int* rows, void* ws,
+                        size_t ws_bytes, void* stream);
 /* wgrad: dw += sum_pos dy[pos] (x) f(x)[pos*stride - pad + tap]; dw is fp32 [Cout,Cin,kS,kW,kH] and is
  *        ACCUMULATED into (caller zeroes it). */
 int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale,

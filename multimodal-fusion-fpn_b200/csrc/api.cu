@@ -27,6 +27,10 @@ struct ffpn_bn_fin;
 int ffpn_conv_fwd_ws_bn(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const float*, int, const float*, void*, float*, int*,
                         void*, size_t, cudaStream_t, double count, float momentum, float eps, const float* gamma, const float* beta,
                         float* rmean, float* rvar, float* scale, float* shift, float* smean, float* sinvstd);
+int ffpn_conv_dgrad_ws_bnr(ffpn_ctx*, const ffpn_conv_desc*, const void*, const float*, const void*, const float*, const float*, void*, float*,
+                           int*, void*, size_t, cudaStream_t);
+extern "C" int ffpn_bn_bwd_reduce(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* dA, const void* y, const float* scale,
+                                  const float* shift, int relu, float* partial, int* rows, void* stream);
 extern "C" int ffpn_bn_finalize(ffpn_ctx* ctx, const float* stat_partial, int stat_rows, int C, double count, const float* gamma,
                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps, int training,
                                 float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
@@ -150,6 +154,19 @@ extern "C" int ffpn_conv_dgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const voi
   ctx->routes[FFPN_ROUTE_SIMT]++;
   if (d->dtype == FFPN_BF16) ffpn_log_route("conv_dgrad -> CUDA-core kernel", d);
   return ffpn_conv_dgrad_simt(ctx, d, dy, w, addend, dx, (cudaStream_t)stream);
+}
+
+extern "C" int ffpn_conv_dgrad_bnr(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* dy, const float* w, const void* y_prev,
+                                   const float* bn_scale, const float* bn_shift, void* dx, float* partial, int* rows, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  if (check_desc(ctx, d, "conv_dgrad_bnr")) return 1;
+  if (!y_prev || !bn_scale || !bn_shift || !partial || !rows) FFPN_FAIL(ctx, "conv_dgrad_bnr: null argument");
+  if (d->impl != 1 && d->dtype == FFPN_BF16 && ffpn_tc_dgrad_supported(d)) {
+    const int r = ffpn_conv_dgrad_ws_bnr(ctx, d, dy, w, y_prev, bn_scale, bn_shift, dx, partial, rows, ws, ws_bytes, (cudaStream_t)stream);
+    if (r >= 0) return r;                                  // one kernel: the sums come out of the dgrad epilogue
+  }
+  if (ffpn_conv_dgrad(ctx, d, dy, w, nullptr, dx, ws, ws_bytes, stream)) return 1;
+  return ffpn_bn_bwd_reduce(ctx, d->dtype, d->B * d->S * d->W * d->H, d->Cin, dx, y_prev, bn_scale, bn_shift, 1, partial, rows, stream);
 }
 
 extern "C" int ffpn_conv_wgrad(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* x, const float* in_scale,

@@ -18,7 +18,12 @@ namespace {
 
 constexpr int WS_THREADS = 512;
 constexpr int WS_MAX_STAGES = 6;
-constexpr int WS_NT = 128;            // transform threads: warps 12..15, one per SM sub-partition (FFPN_WS_NT=160 adds warp 3: a fifth warp doubles one scheduler's share)
+constexpr int WS_NT = 128;            // transform threads: warps 12..15, one per SM sub-partition
+// Register split between the warpgroups (setmaxnreg; 128 threads each, 512 x 128 registers in all): the TMA / MMA issuers and the
+// transform warps need few, the epilogue warps keep two batches of accumulator rows, the addend / BatchNorm-backward operands
+// and the per-channel sums in registers.
+constexpr int WS_REGS_ISSUE = 64, WS_REGS_XFORM = 80, WS_REGS_EPI = 184;
+static_assert(WS_REGS_ISSUE + WS_REGS_XFORM + 2 * WS_REGS_EPI == 4 * 128, "the four warpgroups share 512 x 128 registers");
 constexpr int WS_NEPI = 8;            // epilogue warps 4..11
 constexpr int WS_STAT_BYTES = 8 * 2 * 256 * 4;   // one statistics slot per epilogue warp (fixed-order sum: deterministic)
 constexpr int WS_TAB_BYTES = 1024 * 8;           // row table of the epilogue: 8 accumulator blocks x 128 rows x (offset, packed j|y|x)
@@ -40,13 +45,16 @@ struct WsParams {
   const float* sc;
   const float* sh;
   const bf16* wp;
-  const bf16* addend;
+  const bf16* addend;                 // MODE 1: tensor added to the output; MODE 2: raw output y of the BatchNorm whose backward sums are taken
+  const float* bsc;                   // MODE 2: scale / shift of that BatchNorm (the ReLU mask is scale * y + shift > 0)
+  const float* bsh;
+  int bn_mod;                         // MODE 2 on the pair view of dx: the BatchNorm vectors are indexed modulo the real channel count (0 = off)
+  int fold;                           // statistics columns c and c + fold are the same channel (pair views): folded when the CTA writes its row (0 = off)
   bf16* y;
   float* stat;
   unsigned tapdesc[27];               // per tap: row offset of the A view in descriptor units ((rows * pitch) >> 4)
   unsigned tap_dx, tap_dy, tap_dd;    // its increments per dx / dy / dd step (the issue loop only loads tapdesc[0])
   int pdl_early;                      // wait for the predecessor grid only after the prologue (FFPN_PDL_EARLY)
-  int nt;                             // transform threads (128, or 160 with warp 3)
   int pair2;                          // stride-1 conv on the pair view of input and output: real Cout (statistics are folded to it), 0 = off
   int xseg, oXtot;                    // lines wider than one TMA box: X is cut into segments of xseg outputs that take the place of the batch axis (0 = off)
   int fin_on;                         // BatchNorm finalize by the last CTA to finish (ffpn_conv_fwd_bn)
@@ -101,8 +109,14 @@ struct WsRing {
   }
 };
 
+template <int N> static __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> static __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // NREG: 16-column chunks whose statistics are accumulated in registers (Npad == 16 * NREG); 0 = shuffle per chunk.
-template <int NREG, bool ADD, bool SPLITC>
+// MODE: 0 plain; 1 the epilogue adds a tensor (residual-branch gradient of a dgrad); 2 dgrad fused with pass 1 of the backward of
+// the BatchNorm + ReLU that produced the conv's input: the epilogue loads that BatchNorm's raw input y at the output position,
+// masks the gradient with the ReLU (scale * y + shift > 0) and accumulates the per-channel sums of G and G * y.
+template <int NREG, int MODE, bool SPLITC>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ WsParams p,
                                                                 const __grid_constant__ CUtensorMap tmap) {
   pdl_trigger();
@@ -131,7 +145,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < WS_MAX_STAGES; s++) {
       mbar_init(FULL(s), 1);
-      mbar_init(READY(s), (uint32_t)(p.nt >> 5));
+      mbar_init(READY(s), (uint32_t)(WS_NT >> 5));
       mbar_init(EMPTY(s), 1);
     }
     for (int b = 0; b < 4; b++) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), SPLITC ? WS_NEPI : WS_NEPI / 2); }
@@ -151,6 +165,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t buf_cols = (uint32_t)(p.tmem_cols / p.nbuf);
 
+  // Every warpgroup sets its register budget at the top of its own branch (the budget must dominate the role code).  Nobody
+  // returns to the launch allocation afterwards: an early finisher asking for its registers back (the spare warp 3, the
+  // transform warps of a conv without prologue) would race the epilogue warps for the pool and starve them.  The common tail
+  // is therefore compiled for the smallest budget.
+  if (warp < 4) {
+  reg_dec<WS_REGS_ISSUE>();
   if (warp == 0) {
     // ================= TMA producer (one elected lane) =================
     if (elect_one()) {
@@ -269,12 +289,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         __syncwarp();
       }
     }
-  } else if (warp >= 4 && warp < 4 + WS_NEPI) {
+  }
+  } else if (warp < 4 + WS_NEPI) {
+    reg_inc<WS_REGS_EPI>();
     // ================= epilogue =================
     // Two warps per TMEM lane quadrant.  SPLITC = false: they take ALTERNATE TILES (tile parity), so the two warps that share an
     // SM sub-partition are in different phases of their tcgen05.ld -> convert -> store chains and hide each other's latency.
     // SPLITC = true (N = 64 with statistics): both work on every tile and take half of the 16-column chunks each, which keeps
     // the per-thread statistics of 32 channels in registers instead of 2 x 16 warp shuffles per item.
+    constexpr bool ADD = MODE == 1, BNR = MODE == 2, LD = MODE != 0;
     const int quad = warp & 3, half = (warp - 4) >> 2;
     const int etid = tid - 128;                                    // 0..255 over the epilogue warps
     // ---- row table: tile-local output position of every accumulator row, once per CTA (the decomposition of a row index into
@@ -297,7 +320,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     const int nch_all = p.Npad >> 4;
     const int nch = NREG > 0 ? NREG : (SPLITC ? (nch_all >> 1) : nch_all);      // 16-column chunks this warp takes per accumulator block
     const int ch0 = SPLITC ? half * nch : 0;
-    constexpr int BATCH = NREG == 2 ? 2 : 4;                                        // TMEM loads in flight per thread
+    // Items (one 32-row x 16-column accumulator block each) are processed in half-batches of HB with TWO half-batches of TMEM
+    // loads (+ their addend / y loads) in flight: while one is converted and stored the next one is already on its way.
+    constexpr int HB = BNR ? 1 : 2;                                  // (MODE 2 also keeps y and the BatchNorm coefficients: one item per half)
     int tl = 0;
     WsTile tc;
     for (tc.init(p); tc.valid(p); tc.next(p), tl++) {
@@ -309,71 +334,68 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       const int ox_base = p.tma_mode == 0 ? 0 : tc.i0, oy_base = p.tma_mode == 0 ? tc.it * p.tY : 0;
       const int remD = tc.tD_t, remY = p.oY - oy_base, remX = min(p.oX, p.oXtot - tc.nb * p.xseg) - ox_base;
       const long long tbase = (long long)tc.nb * p.outNB + (long long)tc.d0 * p.outD + (long long)oy_base * p.outY + ox_base;
-      uint32_t raw[BATCH][16];
-      long long oposv[BATCH];
-      bool validv[BATCH];
-      uint4 addv[ADD ? BATCH : 1][2];
-      // output position of every item of a batch (+ the residual-branch gradient loads, all issued before anything waits)
-      auto prep = [&](int it0) {
+      const uint32_t t_tile = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
+      uint32_t raw[2][HB][16];
+      long long oposv[2][HB];
+      bool validv[2][HB];
+      uint4 addv[LD ? 2 : 1][LD ? HB : 1][2];
+      // output position of every item of a half-batch (+ its addend / y loads, issued long before they are used)
+      auto prep = [&](const int hh, const int it0) {
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
+        for (int u = 0; u < HB; u++) {
           const int idx = it0 + u;
-          validv[u] = false; oposv[u] = 0;
-          if (ADD) addv[ADD ? u : 0][0] = addv[ADD ? u : 0][1] = make_uint4(0u, 0u, 0u, 0u);
+          validv[hh][u] = false; oposv[hh][u] = 0;
+          if (LD) addv[LD ? hh : 0][LD ? u : 0][0] = addv[LD ? hh : 0][LD ? u : 0][1] = make_uint4(0u, 0u, 0u, 0u);
           if (idx < nitems) {
-            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? u % NREG : idx - mbi * nch);
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? (hh * HB + u) % NREG : idx - mbi * nch);
             const uint2 e = row_tab[mbi * 128 + quad * 32 + lane];
             const int j = (int)(e.y >> 24), oyl = (int)((e.y >> 12) & 0xfffu), oxl = (int)(e.y & 0xfffu);
-            validv[u] = (e.x != 0xffffffffu) && (j < remD) && (oyl < remY) && (oxl < remX);
-            oposv[u] = tbase + (long long)e.x;
-            if (ADD && validv[u]) {
+            validv[hh][u] = (e.x != 0xffffffffu) && (j < remD) && (oyl < remY) && (oxl < remX);
+            oposv[hh][u] = tbase + (long long)e.x;
+            if (LD && validv[hh][u]) {
               const int cbase = n0 + ch * 16;
-              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + oposv[u] * p.Cout + cbase);
+              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + oposv[hh][u] * p.Cout + cbase);
               if (cbase + 16 <= p.Cout) {
                 uint32_t t8[8];
                 ld_global_v8(ap, t8);
-                addv[ADD ? u : 0][0] = make_uint4(t8[0], t8[1], t8[2], t8[3]);
-                addv[ADD ? u : 0][1] = make_uint4(t8[4], t8[5], t8[6], t8[7]);
+                addv[LD ? hh : 0][LD ? u : 0][0] = make_uint4(t8[0], t8[1], t8[2], t8[3]);
+                addv[LD ? hh : 0][LD ? u : 0][1] = make_uint4(t8[4], t8[5], t8[6], t8[7]);
               } else if (cbase < p.Cout) {
-                addv[ADD ? u : 0][0] = ap[0];
+                addv[LD ? hh : 0][LD ? u : 0][0] = ap[0];
               }
             }
           }
         }
       };
-      // the addend loads of the first batch go out BEFORE the wait for the accumulators: their DRAM latency hides behind the MMAs
-      if (ADD) prep(0);
-      mbar_wait(TFULL(buf), (uint32_t)(tl / p.nbuf) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp == 4 && lane == 0) WS_TRACE(8, tl);
-      const uint32_t t_tile = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
-      for (int it0 = 0; it0 < nitems; it0 += BATCH) {
-        if (!ADD || it0 > 0) prep(it0);
+      auto issue = [&](const int hh, const int it0) {
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
+        for (int u = 0; u < HB; u++) {
           const int idx = it0 + u;
           if (idx < nitems) {
-            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? u % NREG : idx - mbi * nch);
-            tmem_ld16_nowait(t_tile + (uint32_t)(mbi * p.colstride + ch * 16), raw[u]);
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? (hh * HB + u) % NREG : idx - mbi * nch);
+            tmem_ld16_nowait(t_tile + (uint32_t)(mbi * p.colstride + ch * 16), raw[hh][u]);
           }
         }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      };
+      auto process = [&](const int hh, const int it0) {
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
+        for (int u = 0; u < HB; u++) {
           const int idx = it0 + u;
           if (idx < nitems) {
-            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? u % NREG : idx - mbi * nch);
-            const bool valid = validv[u];
-            const long long opos = oposv[u];
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? (hh * HB + u) % NREG : idx - mbi * nch);
+            const bool valid = validv[hh][u];
+            const long long opos = oposv[hh][u];
             float v[16];
 #pragma unroll
-            for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[u][q]);
+            for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[hh][u][q]);
             const int cbase = n0 + ch * 16;
+            float yv[BNR ? 16 : 1];
+            uint32_t mbits = BNR ? 0u : 0xffffu;                    // MODE 2: ReLU mask of the 16 channels (the stored gradient stays unmasked)
             if (ADD && valid) {
 #pragma unroll
               for (int h2 = 0; h2 < 2; h2++) {
                 if (cbase + h2 * 8 < p.Cout) {
-                  const uint4 a4 = addv[ADD ? u : 0][h2];
+                  const uint4 a4 = addv[LD ? hh : 0][LD ? u : 0][h2];
                   const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
                   for (int q = 0; q < 4; q++) {
@@ -383,11 +405,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                 }
               }
             }
+            if (BNR) {
+              // ReLU mask of the producer BatchNorm (same expression as bn_bwd_reduce / bn_bwd_apply): it only enters the sums, the
+              // stored gradient is the plain dgrad; rows outside the tensor are dropped from the sums through `valid` below
+#pragma unroll
+              for (int h2 = 0; h2 < 2; h2++) {
+                const uint4 a4 = addv[LD ? hh : 0][LD ? u : 0][h2];
+                const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                  yv[BNR ? h2 * 8 + 2 * q : 0] = __uint_as_float(w4[q] << 16);
+                  yv[BNR ? h2 * 8 + 2 * q + 1 : 0] = __uint_as_float(w4[q] & 0xffff0000u);
+                }
+              }
+              const int cb = p.bn_mod ? cbase % p.bn_mod : cbase;
+              const float4* scp = reinterpret_cast<const float4*>(p.bsc + cb);
+              const float4* shp = reinterpret_cast<const float4*>(p.bsh + cb);
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const float4 s4 = __ldg(scp + q), h4 = __ldg(shp + q);
+                mbits |= (fmaf(yv[BNR ? 4 * q : 0], s4.x, h4.x) > 0.f ? 1u : 0u) << (4 * q);
+                mbits |= (fmaf(yv[BNR ? 4 * q + 1 : 0], s4.y, h4.y) > 0.f ? 1u : 0u) << (4 * q + 1);
+                mbits |= (fmaf(yv[BNR ? 4 * q + 2 : 0], s4.z, h4.z) > 0.f ? 1u : 0u) << (4 * q + 2);
+                mbits |= (fmaf(yv[BNR ? 4 * q + 3 : 0], s4.w, h4.w) > 0.f ? 1u : 0u) << (4 * q + 3);
+              }
+            }
             uint32_t packed[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-              __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-              packed[q] = *reinterpret_cast<uint32_t*>(&hh);
+              __nv_bfloat162 hh2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+              packed[q] = *reinterpret_cast<uint32_t*>(&hh2);
             }
             if (valid && !(p.dbg & 16)) {
               uint4* yp = reinterpret_cast<uint4*>(p.y + opos * p.Cout + cbase);
@@ -395,23 +442,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
               else if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
             if (p.has_stats && !(p.dbg & 32)) {
-              // statistics of the stored (rounded) values
+              // statistics of the stored (rounded) values: sum v and sum v * v (BatchNorm forward), or sum G and sum G * y (MODE 2)
 #pragma unroll
               for (int q = 0; q < 8; q++) {
-                v[2 * q] = valid ? __uint_as_float(packed[q] << 16) : 0.f;
-                v[2 * q + 1] = valid ? __uint_as_float(packed[q] & 0xffff0000u) : 0.f;
+                v[2 * q] = (valid && (!BNR || ((mbits >> (2 * q)) & 1u))) ? __uint_as_float(packed[q] << 16) : 0.f;
+                v[2 * q + 1] = (valid && (!BNR || ((mbits >> (2 * q + 1)) & 1u))) ? __uint_as_float(packed[q] & 0xffff0000u) : 0.f;
               }
               if (NREG > 0) {
                 constexpr int CH = NREG > 0 ? NREG : 1;
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
-                  ssum[16 * (u % CH) + q] += v[q];
-                  ssq[16 * (u % CH) + q] = fmaf(v[q], v[q], ssq[16 * (u % CH) + q]);
+                  ssum[16 * ((hh * HB + u) % CH) + q] += v[q];
+                  ssq[16 * ((hh * HB + u) % CH) + q] = fmaf(v[q], BNR ? yv[BNR ? q : 0] : v[q], ssq[16 * ((hh * HB + u) % CH) + q]);
                 }
               } else {
                 float w2[16];
 #pragma unroll
-                for (int q = 0; q < 16; q++) w2[q] = v[q] * v[q];
+                for (int q = 0; q < 16; q++) w2[q] = v[q] * (BNR ? yv[BNR ? q : 0] : v[q]);
                 const float a = warp_transpose_sum16(v, lane);
                 const float b = warp_transpose_sum16(w2, lane);
                 if ((lane & 1) == 0) {
@@ -421,6 +468,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                 }
               }
             }
+          }
+        }
+      };
+      // the first half-batch's positions and addend / y loads go out BEFORE the wait for the accumulators: their DRAM latency hides
+      // behind the MMAs
+      prep(0, 0);
+      mbar_wait(TFULL(buf), (uint32_t)(tl / p.nbuf) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 4 && lane == 0) WS_TRACE(8, tl);
+      issue(0, 0);
+      for (int it0 = 0; it0 < nitems; it0 += 2 * HB) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const int cur = it0 + hh * HB;
+          if (cur < nitems) {                                         // warp-uniform
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");   // half-batch hh has landed (nothing else is outstanding)
+            if (cur + HB < nitems) { prep(hh ^ 1, cur + HB); issue(hh ^ 1, cur + HB); }
+            process(hh, cur);
           }
         }
       }
@@ -444,12 +509,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         }
       }
     }
-  } else if (warp >= 12 || p.nt > WS_NT) {
+  } else {
+    reg_dec<WS_REGS_XFORM>();
     // ================= in-place BatchNorm scale/shift + ReLU of landed tiles =================
     if (p.has_aff) {
-      const int tix = p.nt > WS_NT ? (warp < 4 ? tid - 96 : tid - 384 + 32) : tid - 384;   // 0..nt-1
+      const int tix = tid - 384;                                   // 0..WS_NT-1
       const int cpu = p.kgu * (p.Kc >> 3);                         // 16-byte channel chunks per row of a unit
-      const int rstep = p.nt / cpu;
+      const int rstep = WS_NT / cpu;
       const bool active = tix < rstep * cpu;
       const int c = tix % cpu, r0 = tix / cpu;
       const int kgi = c / (p.Kc >> 3), cc = c % (p.Kc >> 3);
@@ -527,14 +593,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (p.has_stats && p.pair2) {
-    // pair view: columns c and c + Cout_real are the same channel (even / odd position) -> one statistics column
-    for (int i = tid; i < 2 * p.pair2; i += WS_THREADS) {
-      const int which = i / p.pair2, c = i - which * p.pair2;
+  if (p.has_stats && p.fold) {
+    // pair view: columns c and c + fold are the same channel (even / odd position) -> one statistics column
+    for (int i = tid; i < 2 * p.fold; i += WS_THREADS) {
+      const int which = i / p.fold, c = i - which * p.fold;
       float t = 0.f;
 #pragma unroll
-      for (int e = 0; e < WS_NEPI; e++) t += stat_s[e * 2 * p.Npad + which * p.Npad + c] + stat_s[e * 2 * p.Npad + which * p.Npad + c + p.pair2];
-      p.stat[((size_t)blockIdx.x * 2 + which) * p.pair2 + c] = t;
+      for (int e = 0; e < WS_NEPI; e++) t += stat_s[e * 2 * p.Npad + which * p.Npad + c] + stat_s[e * 2 * p.Npad + which * p.Npad + c + p.fold];
+      p.stat[((size_t)blockIdx.x * 2 + which) * p.fold + c] = t;
     }
   } else if (p.has_stats) {
     for (int i = tid; i < 2 * p.Npad; i += WS_THREADS) {
@@ -828,10 +894,15 @@ bool ws_enabled() {
 }  // namespace
 
 // Returns 0 = launched, 1 = error (message set), -1 = geometry not handled by this kernel (caller falls back).
+// bsc / bsh != nullptr (dgrad only): MODE 2 -- `addend` is then the raw output y of the BatchNorm + ReLU that produced the conv's
+// input, and stat_partial receives [rows][2][Cout] = sums of G and G * y (ffpn_bn_bwd_reduce's layout).
 static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, const void* x, const float* in_scale,
                           const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
-                          int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st, const ffpn_bn_fin* fin) {
+                          int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st, const ffpn_bn_fin* fin,
+                          const float* bsc = nullptr, const float* bsh = nullptr) {
   if (!ws_enabled()) return -1;
+  const bool bnr = bsc != nullptr;
+  if (bnr && (!transposed || addend == nullptr || bsh == nullptr || stat_partial == nullptr || fin != nullptr || d->Cin % 16 != 0)) return -1;
   if (in_scale != nullptr && !in_relu) return -1;                       // NaN-fill halo needs the ReLU
   ffpn_conv_desc dp;
   int in_mult = 1;
@@ -842,13 +913,15 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   // vs 10.13 ms -- the MMA / shared-memory work drops as predicted but the epilogue (N = 2 Cout columns per row, statistics by
   // shuffles) becomes the bound.  Correct (parity suite green with it on) but off unless FFPN_WS_PAIR2=1.
   if (pair2_on < 0) { const char* e = getenv("FFPN_WS_PAIR2"); pair2_on = (e && atoi(e) == 1) ? 1 : 0; }
-  bool pair2 = !pair && !strided111 && pair2_on && fin == nullptr && ffpn_make_pair2_desc(d, &dp);   // narrow 3-tap stride-1 conv -> pair view of input and output
+  bool pair2 = !pair && !strided111 && pair2_on && fin == nullptr && !bnr && ffpn_make_pair2_desc(d, &dp);   // narrow 3-tap stride-1 conv -> pair view of input and output
   WsPlan pl = make_ws_plan((pair || pair2 || strided111) ? &dp : d, transposed, ctx->num_sms);
   if (pair2 && (!pl.ok || pl.nchunks != 1 || pl.p.kgu != 1 || pl.p.upt != 1 || pl.p.kX != 3)) {   // one resident K-group expected
     pair2 = false;
     pl = make_ws_plan(d, transposed, ctx->num_sms);
   }
   if (!pl.ok) return -1;
+  if (bnr && pair && pl.nchunks != 1) return -1;                       // the two halves of a pair would land in different CTAs
+  if (bnr && !pair && pl.p.Cout != d->Cin) return -1;                  // dgrad of an X-strided conv: N = stride x Cin interleaved positions
   WsParams& p = pl.p;
   const size_t need = (size_t)pl.nchunks * p.b_total_bytes;
   if (ws == nullptr || ws_bytes < need) return -1;
@@ -865,6 +938,9 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     if (packed_now) FFPN_CHECK_LAUNCH(ctx, "pack_weights");
   }
   p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)wimg; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
+  p.bsc = bsc; p.bsh = bsh;
+  p.bn_mod = (bnr && pair) ? d->Cin : 0;
+  p.fold = pair2 ? (transposed ? d->Cin : d->Cout) : (bnr && pair) ? d->Cin : 0;
   p.dbg = ffpn_debug_env("FFPN_TC_DEBUG");
   p.fin_on = 0;
   if (fin != nullptr) {
@@ -881,15 +957,15 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   p.aff_mod = ((pair || pair2) && !transposed) ? d->Cin : 0;
   { const char* e = getenv("FFPN_PDL_EARLY"); p.pdl_early = (e && atoi(e) == 0) ? 0 : 1; }
   p.pair2 = pair2 ? (transposed ? d->Cin : d->Cout) : 0;
-  { const char* e = getenv("FFPN_WS_NT"); p.nt = (e && atoi(e) == 160) ? 160 : WS_NT; }
-  p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr;
+  p.relu = in_relu; p.has_aff = in_scale != nullptr; p.has_stats = stat_partial != nullptr; p.has_add = addend != nullptr && !bnr;
   if (!(ctx->attr_mask & FFPN_ATTR_WS)) {                              // per device: the attribute belongs to the function ON the current device
-    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ws_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_ws: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+    const void* fns[] = {(const void*)conv_ws_kernel<0, 0, false>, (const void*)conv_ws_kernel<0, 1, false>, (const void*)conv_ws_kernel<1, 0, false>,
+                         (const void*)conv_ws_kernel<2, 0, false>, (const void*)conv_ws_kernel<2, 0, true>,  (const void*)conv_ws_kernel<0, 2, false>,
+                         (const void*)conv_ws_kernel<1, 2, false>, (const void*)conv_ws_kernel<2, 2, false>, (const void*)conv_ws_kernel<2, 2, true>};
+    for (const void* fn : fns) {
+      const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) FFPN_FAIL(ctx, "conv_ws: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+    }
     ctx->attr_mask |= FFPN_ATTR_WS;
   }
   {
@@ -910,11 +986,15 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   }
   // statistics in registers: N = 16 / 32 per warp; N = 64 with the two warps of a quadrant splitting the columns (32 each)
   const int nreg = p.has_add ? 0 : (p.has_stats && p.Npad == 16) ? 1 : (p.has_stats && (p.Npad == 32 || p.Npad == 64)) ? 2 : 0;
-  if (p.has_add) ffpn_launch(conv_ws_kernel<0, true, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
-  else if (nreg == 1) ffpn_launch(conv_ws_kernel<1, false, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
-  else if (nreg == 2 && p.Npad == 64) ffpn_launch(conv_ws_kernel<2, false, true>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
-  else if (nreg == 2) ffpn_launch(conv_ws_kernel<2, false, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
-  else ffpn_launch(conv_ws_kernel<0, false, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  if (p.has_add) ffpn_launch(conv_ws_kernel<0, 1, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (bnr && nreg == 1) ffpn_launch(conv_ws_kernel<1, 2, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (bnr && nreg == 2 && p.Npad == 64) ffpn_launch(conv_ws_kernel<2, 2, true>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (bnr && nreg == 2) ffpn_launch(conv_ws_kernel<2, 2, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (bnr) ffpn_launch(conv_ws_kernel<0, 2, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (nreg == 1) ffpn_launch(conv_ws_kernel<1, 0, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (nreg == 2 && p.Npad == 64) ffpn_launch(conv_ws_kernel<2, 0, true>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else if (nreg == 2) ffpn_launch(conv_ws_kernel<2, 0, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
+  else ffpn_launch(conv_ws_kernel<0, 0, false>, pl.grid, WS_THREADS, pl.smem, st, p, tmap);
   FFPN_CHECK_LAUNCH(ctx, transposed ? "conv_dgrad_ws" : "conv_fwd_ws");
   if (trace_mode) {
     static long long h[64 * 16];
@@ -975,6 +1055,14 @@ int ffpn_conv_fwd_ws(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transposed, co
                      const float* in_shift, int in_relu, const float* w, const void* addend, void* y, float* stat_partial,
                      int* stat_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
   return conv_ws_launch(ctx, d, transposed, x, in_scale, in_shift, in_relu, w, addend, y, stat_partial, stat_rows, ws, ws_bytes, st, nullptr);
+}
+
+// dgrad fused with pass 1 of the BatchNorm + ReLU backward of the conv's input.  -1: geometry not handled here.
+int ffpn_conv_dgrad_ws_bnr(ffpn_ctx* ctx, const ffpn_conv_desc* d, const void* dy, const float* w, const void* y_prev, const float* bn_scale,
+                           const float* bn_shift, void* dx, float* partial, int* rows, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int r = conv_ws_launch(ctx, d, true, dy, nullptr, nullptr, 0, w, y_prev, dx, partial, rows, ws, ws_bytes, st, nullptr, bn_scale, bn_shift);
+  if (r >= 0) ctx->routes[FFPN_ROUTE_WS]++;
+  return r;
 }
 
 // Forward conv with the BatchNorm finalize of its output fused in (training mode).  -1: geometry not handled here.

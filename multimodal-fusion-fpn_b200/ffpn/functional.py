@@ -366,9 +366,9 @@ class ConvXFunction(torch.autograd.Function):
             grads[5 * i] = _wgrad(inp, dy, w.shape, spec.kernels[i], spec.strides[i], spec.pads[i], a_in, b_in, i > 0,
                                   _sink(w))
             if i > 0:
-                dA = ops.conv_dgrad(dy, w, inp.shape, spec.kernels[i], spec.strides[i], spec.pads[i])
+                # dgrad with the ReLU mask and the BatchNorm-backward sums of the previous conv's BN taken in its epilogue
+                dA, partial, rows = ops.conv_dgrad_bnr(dy, w, inp, a_in, b_in, spec.kernels[i], spec.strides[i], spec.pads[i])
                 cnt = inp.numel() // inp.shape[-1] if spec.training else inf
-                partial, rows = ops.bn_bwd_reduce(dA, inp, a_in, b_in, True)
                 dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, 2, 1, cnt, tensors[5 * (i - 1) + 1],
                                                          affs[i - 1][2], affs[i - 1][3], _sink(tensors[5 * (i - 1) + 1]),
                                                          _sink(tensors[5 * (i - 1) + 2]))

@@ -36,6 +36,7 @@ SIGNATURES = {
     'ffpn_conv_fwd': [_DP, _P, _P, _P, _I, _P, _P, _P, _IP, _P, _Z, _P],
     'ffpn_conv_fwd_bn': [_DP, _P, _P, _P, _I, _P, _P, _P, _IP, _D, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _Z, _P],
     'ffpn_conv_dgrad': [_DP, _P, _P, _P, _P, _P, _Z, _P],
+    'ffpn_conv_dgrad_bnr': [_DP, _P, _P, _P, _P, _P, _P, _P, _IP, _P, _Z, _P],
     'ffpn_conv_wgrad': [_DP, _P, _P, _P, _I, _P, _P, _P, _Z, _P],
     'ffpn_bn_finalize': [_P, _I, _I, _D, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P],
     'ffpn_bn_bwd_reduce': [_I, _L, _I, _P, _P, _P, _P, _I, _P, _IP, _P],
@@ -111,7 +112,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.ffpn_abi_version() != 2:
+        if lib.ffpn_abi_version() != 3:
             raise FfpnError('libfusionfpn.so ABI version mismatch')
         _lib = lib
     return _lib

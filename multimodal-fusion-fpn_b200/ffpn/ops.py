@@ -98,6 +98,7 @@ def conv_fwd_bn(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, gamma, b
         # until one of those tensors changes (tensor version counters); the forward is then the conv alone, no finalize launch
         y, _, _ = conv_fwd(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, want_stats=False)
         return y, eval_bn_coefficients(gamma, beta, running_mean, running_var, eps)
+    note_bn_statistics_update()
     cout = w.shape[0]
     d = make_desc(x.shape, cout, kernel, stride, pad, x.dtype)
     y = torch.empty((d.B, d.oS, d.oW, d.oH, cout), dtype=x.dtype, device=x.device)
@@ -113,23 +114,30 @@ def conv_fwd_bn(x, w, kernel, stride, pad, in_scale, in_shift, in_relu, gamma, b
     return y, (out[0], out[1], out[2], out[3])
 
 
-_EVAL_BN_CACHE = {}
+# Running statistics are updated by the library's kernels through raw pointers (and by CUDA-graph replays), which torch's version
+# counters do not see: every training-mode BatchNorm finalize and every trainer step / replay bumps this epoch instead, and an
+# eval-mode coefficient cache entry is only valid within the epoch it was made in.
+_BN_TRAIN_EPOCH = [0]
+
+
+def note_bn_statistics_update():
+    _BN_TRAIN_EPOCH[0] += 1
 
 
 def eval_bn_coefficients(gamma, beta, running_mean, running_var, eps):
-    """(scale, shift, mean, invstd) of an eval-mode BatchNorm, cached per module: key = the buffers' identity, validity = their
-    version counters (any in-place update -- a training step, load_state_dict -- bumps them).  Not used while a CUDA graph is
-    being captured (a cached tensor must not be created inside a capture)."""
-    key = (running_mean.data_ptr(), running_var.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps))
+    """(scale, shift, mean, invstd) of an eval-mode BatchNorm, cached per module.  The cache entry lives ON the running_mean
+    tensor object (a module buffer keeps its identity across load_state_dict / in-place updates) and is valid while the four
+    tensors are the same objects with the same version counters (load_state_dict, torch in-place ops) and no training step has
+    run since (_BN_TRAIN_EPOCH).  Nothing is keyed by address: a freed model's storage may be reused by another one.  Not
+    used while a CUDA graph is being captured (a cached tensor must not be created inside a capture)."""
     ver = (running_mean._version, running_var._version, gamma._version, beta._version)
-    hit = _EVAL_BN_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
+    hit = getattr(running_mean, '_ffpn_eval_bn', None)
+    if (hit is not None and hit[0] == ver and hit[2] is running_var and hit[3] is gamma and hit[4] is beta and hit[5] == float(eps)
+            and hit[6] == running_mean.data_ptr() and hit[7] == _BN_TRAIN_EPOCH[0]):
         return hit[1]
     out = bn_finalize(None, 0, 1.0, gamma, beta, running_mean, running_var, 0.0, eps, False)
     if not torch.cuda.is_current_stream_capturing():
-        if len(_EVAL_BN_CACHE) > 4096:
-            _EVAL_BN_CACHE.clear()
-        _EVAL_BN_CACHE[key] = (ver, out)
+        running_mean._ffpn_eval_bn = (ver, out, running_var, gamma, beta, float(eps), running_mean.data_ptr(), _BN_TRAIN_EPOCH[0])
     return out
 
 
@@ -141,6 +149,22 @@ def conv_dgrad(dy, w, x_shape, kernel, stride, pad, addend=None):
     ws, nws = _workspace(d, dy)
     lib.call('ffpn_conv_dgrad', _dev(dy), C.byref(d), _ptr(dy), _ptr(w), _ptr(addend), _ptr(dx), _ptr(ws), nws, _stream(dy))
     return dx
+
+
+def conv_dgrad_bnr(dy, w, y_prev, bn_scale, bn_shift, kernel, stride, pad):
+    """dgrad fused with pass 1 of the backward of the BatchNorm + ReLU that produced the conv's input (``y_prev`` = that
+    BatchNorm's raw input) -> (dx, partial, rows): dx as conv_dgrad gives it, partial = sums of G and G * y_prev with
+    G = dx under the ReLU mask (what bn_bwd_reduce(dx, y_prev, relu=True) gives)."""
+    _chk(dy, 'dy'); _chk(y_prev, 'y_prev')
+    d = make_desc(y_prev.shape, w.shape[0], kernel, stride, pad, dy.dtype)
+    assert tuple(dy.shape) == (d.B, d.oS, d.oW, d.oH, w.shape[0]), (tuple(dy.shape), (d.B, d.oS, d.oW, d.oH, w.shape[0]))
+    dx = torch.empty_like(y_prev)
+    partial = new_partial(dy.device, 2, y_prev.shape[-1])
+    rows = C.c_int(0)
+    ws, nws = _workspace(d, dy)
+    lib.call('ffpn_conv_dgrad_bnr', _dev(dy), C.byref(d), _ptr(dy), _ptr(w), _ptr(y_prev), _ptr(bn_scale), _ptr(bn_shift), _ptr(dx),
+             _ptr(partial), C.byref(rows), _ptr(ws), nws, _stream(dy))
+    return dx, partial, rows.value
 
 
 def conv_wgrad(x, dy, w_shape, kernel, stride, pad, in_scale=None, in_shift=None, in_relu=False, out=None):
@@ -158,6 +182,8 @@ def conv_wgrad(x, dy, w_shape, kernel, stride, pad, in_scale=None, in_shift=None
 def bn_finalize(partial, rows, count, gamma, beta, running_mean, running_var, momentum, eps, training):
     """-> (scale, shift, save_mean, save_invstd)"""
     C_ = gamma.numel()
+    if training:
+        note_bn_statistics_update()
     out = torch.empty(4, C_, dtype=torch.float32, device=gamma.device)
     lib.call('ffpn_bn_finalize', _dev(gamma), _ptr(partial), rows, C_, float(count), _ptr(gamma), _ptr(beta),
              _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), int(bool(training)), _ptr(out[0]),

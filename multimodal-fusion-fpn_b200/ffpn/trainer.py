@@ -363,6 +363,8 @@ class FusionTrainer:
                 if k in self._static:
                     self._static[k].copy_(v, non_blocking=True)
         self._repack_if_dirty()                # load_state_dict since the last step: the graph reads the arena images
+        from . import ops
+        ops.note_bn_statistics_update()        # the replay updates the running statistics behind torch's version counters
         self._graph.replay()
         if self._fused_opt:
             self.steps += 1

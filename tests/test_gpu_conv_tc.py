@@ -150,6 +150,19 @@ def test_conv_tc(case):
         torch.cuda.synchronize()
         assert rel(logical(dx.float()), xr.grad) <= 1e-2, ('dgrad', rel(logical(dx.float()), xr.grad))
         assert rel(logical(dx2.float()), xr.grad + add.float()) <= 1e-2
+        # dgrad fused with pass 1 of the backward of the BatchNorm + ReLU that produced the conv's input (ffpn_conv_dgrad_bnr): the
+        # stored gradient is the plain dgrad, bit for bit; the sums are those of bn_bwd_reduce on it (ReLU mask applied)
+        yprev = phys(torch.randn(B, cin, S, W, H, generator=g).cuda()).to(dt)
+        G, part, prow = ops.conv_dgrad_bnr(phys(dy), w, yprev, sc, sh, k, s1, p)
+        G1, part1, prow1 = ops.conv_dgrad_bnr(phys(dy), w, yprev, sc, sh, k, s1, p)
+        torch.cuda.synchronize()
+        mask = torch.addcmul(sh, yprev.float(), sc) > 0
+        assert torch.equal(G, dx)
+        Gd, yd_ = torch.where(mask, dx.float(), torch.zeros((), device='cuda')).double().reshape(-1, cin), yprev.double().reshape(-1, cin)
+        st = part.view(-1, 2, cin)[:prow].double().sum(0)
+        assert torch.allclose(st[0], Gd.sum(0), rtol=1e-3, atol=1e-3 * Gd.abs().sum(0).max().item()), ('dgrad_bnr sum G', (st[0] - Gd.sum(0)).abs().max())
+        assert torch.allclose(st[1], (Gd * yd_).sum(0), rtol=1e-3, atol=1e-3 * (Gd * yd_).abs().sum(0).max().item())
+        assert torch.equal(G, G1) and prow == prow1 and torch.equal(part[:prow * 2 * cin], part1[:prow * 2 * cin])
         # wgrad on tensor cores (fused BN+ReLU prologue on x), against torch autograd
         for affine in (False, True):
             xin = torch.relu(xq * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)) if affine else xq

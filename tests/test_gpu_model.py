@@ -384,6 +384,46 @@ def _crit(mirror):
                             'BCE': mirror.loss.BCE_Lossv2('prediction', 'mask')})
 
 
+def test_eval_after_training_sees_the_updated_running_statistics(mirror):
+    """The eval-mode BatchNorm coefficients are cached per module; the library's kernels (and CUDA-graph replays) update the
+    running statistics through raw pointers, which torch's version counters do not see -- an eval forward after an eager step
+    and after a graph replay must nevertheless equal that of a fresh model loaded with the current state_dict."""
+    import ffpn
+    from ffpn.trainer import FusionTrainer
+    ffpn.set_compute_dtype(torch.bfloat16)
+    sd = O.make_state_dict(seed=33)
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(2, 4, 64, 32, 16, 32, seed=7).items()}
+
+    def evaluate(m):
+        m.eval()
+        with torch.no_grad():
+            out = m(batch)['prediction'].clone()
+        m.train()
+        return out
+
+    def fresh_copy(m):
+        f = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+        f.load_state_dict({k: v.clone() for k, v in m.state_dict().items()}, strict=True)
+        return f
+
+    model = mirror.build('FPNHybridFusion', 'relative_2d_max').cuda()
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    first = evaluate(model)                                      # fills the cache
+    tr = FusionTrainer(model, _crit(mirror))
+    tr.step(batch)
+    torch.cuda.synchronize()
+    after_eager = evaluate(model)
+    assert not torch.equal(after_eager, first)
+    assert torch.equal(after_eager, evaluate(fresh_copy(model)))
+    tr.capture(batch, warmup=1)
+    evaluate(model)                                              # cache again, then replay behind it
+    tr.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(evaluate(model), evaluate(fresh_copy(model)))
+    tr.close()
+
+
 def test_weights_loaded_behind_the_trainer_are_never_stale(mirror):
     """The packed bf16 weight arena (recorded by the trainer's first step, baked into its CUDA graph) must not serve stale
     images: (a) conv calls made outside FusionTrainer.forward_backward -- an eval forward of the same model -- pack from the

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
     for name in declared:
         assert hasattr(handle, name), name
-    assert handle.ffpn_abi_version() == 2
+    assert handle.ffpn_abi_version() == 3
     d = lib.ConvDesc()
     assert handle.ffpn_conv_workspace_bytes(d) >= 0          # pure host call, no GPU needed
 
