@@ -317,12 +317,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     float ssum[NREG > 0 ? 16 * NREG : 1], ssq[NREG > 0 ? 16 * NREG : 1];
 #pragma unroll
     for (int i = 0; i < (NREG > 0 ? 16 * NREG : 1); i++) { ssum[i] = 0.f; ssq[i] = 0.f; }
+    float bsc_r[BNR && NREG == 1 ? 16 : 1], bsh_r[BNR && NREG == 1 ? 16 : 1];   // MODE 2, N = 16: the BatchNorm coefficients stay in registers
+    if (BNR && NREG == 1) {
+#pragma unroll
+      for (int q = 0; q < 16; q++) { bsc_r[BNR && NREG == 1 ? q : 0] = p.bsc[q]; bsh_r[BNR && NREG == 1 ? q : 0] = p.bsh[q]; }
+    }
     const int nch_all = p.Npad >> 4;
     const int nch = NREG > 0 ? NREG : (SPLITC ? (nch_all >> 1) : nch_all);      // 16-column chunks this warp takes per accumulator block
     const int ch0 = SPLITC ? half * nch : 0;
     // Items (one 32-row x 16-column accumulator block each) are processed in half-batches of HB with TWO half-batches of TMEM
     // loads (+ their addend / y loads) in flight: while one is converted and stored the next one is already on its way.
-    constexpr int HB = BNR ? 1 : 2;                                  // (MODE 2 also keeps y and the BatchNorm coefficients: one item per half)
+    #ifndef WS_HB
+#define WS_HB 2
+#endif
+    // Measured (B200, level-1 forward / dgrad): HB = 2 beats 3 and 4 (80.1 vs 85.8 us, 70.6 vs 78.8 us) although the registers would
+    // allow them -- short dependent chains interleave better between the two warps of a scheduler.  MODE 2 also keeps y and the
+    // BatchNorm coefficients: one item per half.
+#ifndef WS_HB_BNR
+#define WS_HB_BNR 1
+#endif
+    constexpr int HB = BNR ? WS_HB_BNR : WS_HB;
     int tl = 0;
     WsTile tc;
     for (tc.init(p); tc.valid(p); tc.next(p), tl++) {
@@ -335,6 +349,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       const int remD = tc.tD_t, remY = p.oY - oy_base, remX = min(p.oX, p.oXtot - tc.nb * p.xseg) - ox_base;
       const long long tbase = (long long)tc.nb * p.outNB + (long long)tc.d0 * p.outD + (long long)oy_base * p.outY + ox_base;
       const uint32_t t_tile = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(quad * 32) << 16);
+      if (LD) {
+        // the addend / y rows of the NEXT tile this warp takes are pulled into L2 now: the per-item register loads (one half-batch
+        // ahead, i.e. a few hundred ns) then find them there instead of paying the DRAM latency item by item
+        WsTile nx = tc;
+        nx.next(p);
+        if (!SPLITC) nx.next(p);
+        if (nx.valid(p)) {
+          const int nox = p.tma_mode == 0 ? 0 : nx.i0, noy = p.tma_mode == 0 ? nx.it * p.tY : 0;
+          const int nremD = nx.tD_t, nremY = p.oY - noy, nremX = min(p.oX, p.oXtot - nx.nb * p.xseg) - nox;
+          const long long nbase = (long long)nx.nb * p.outNB + (long long)nx.d0 * p.outD + (long long)noy * p.outY + nox;
+          const int nit = nx.nmb * nch;
+          for (int idx = 0; idx < nit; idx++) {
+            const int mbi = NREG > 0 ? idx / NREG : idx / nch, ch = ch0 + (NREG > 0 ? idx % NREG : idx - mbi * nch);
+            const uint2 e = row_tab[mbi * 128 + quad * 32 + lane];
+            const int j = (int)(e.y >> 24), oyl = (int)((e.y >> 12) & 0xfffu), oxl = (int)(e.y & 0xfffu);
+            const int cbase = n0 + ch * 16;
+            if ((e.x != 0xffffffffu) && (j < nremD) && (oyl < nremY) && (oxl < nremX) && cbase < p.Cout)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.addend + (nbase + (long long)e.x) * p.Cout + cbase));
+          }
+        }
+      }
       uint32_t raw[2][HB][16];
       long long oposv[2][HB];
       bool validv[2][HB];
@@ -389,8 +424,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
 #pragma unroll
             for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[hh][u][q]);
             const int cbase = n0 + ch * 16;
-            float yv[BNR ? 16 : 1];
-            uint32_t mbits = BNR ? 0u : 0xffffu;                    // MODE 2: ReLU mask of the 16 channels (the stored gradient stays unmasked)
             if (ADD && valid) {
 #pragma unroll
               for (int h2 = 0; h2 < 2; h2++) {
@@ -405,31 +438,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                 }
               }
             }
-            if (BNR) {
-              // ReLU mask of the producer BatchNorm (same expression as bn_bwd_reduce / bn_bwd_apply): it only enters the sums, the
-              // stored gradient is the plain dgrad; rows outside the tensor are dropped from the sums through `valid` below
-#pragma unroll
-              for (int h2 = 0; h2 < 2; h2++) {
-                const uint4 a4 = addv[LD ? hh : 0][LD ? u : 0][h2];
-                const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                  yv[BNR ? h2 * 8 + 2 * q : 0] = __uint_as_float(w4[q] << 16);
-                  yv[BNR ? h2 * 8 + 2 * q + 1 : 0] = __uint_as_float(w4[q] & 0xffff0000u);
-                }
-              }
-              const int cb = p.bn_mod ? cbase % p.bn_mod : cbase;
-              const float4* scp = reinterpret_cast<const float4*>(p.bsc + cb);
-              const float4* shp = reinterpret_cast<const float4*>(p.bsh + cb);
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const float4 s4 = __ldg(scp + q), h4 = __ldg(shp + q);
-                mbits |= (fmaf(yv[BNR ? 4 * q : 0], s4.x, h4.x) > 0.f ? 1u : 0u) << (4 * q);
-                mbits |= (fmaf(yv[BNR ? 4 * q + 1 : 0], s4.y, h4.y) > 0.f ? 1u : 0u) << (4 * q + 1);
-                mbits |= (fmaf(yv[BNR ? 4 * q + 2 : 0], s4.z, h4.z) > 0.f ? 1u : 0u) << (4 * q + 2);
-                mbits |= (fmaf(yv[BNR ? 4 * q + 3 : 0], s4.w, h4.w) > 0.f ? 1u : 0u) << (4 * q + 3);
-              }
-            }
             uint32_t packed[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -442,23 +450,52 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
               else if (cbase < p.Cout) yp[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
             if (p.has_stats && !(p.dbg & 32)) {
-              // statistics of the stored (rounded) values: sum v and sum v * v (BatchNorm forward), or sum G and sum G * y (MODE 2)
+              // statistics of the stored (rounded) values: sum v and sum v * v (BatchNorm forward); MODE 2: sum G and sum G * y with
+              // G = v under the ReLU mask of the producer BatchNorm (same expression as bn_bwd_reduce / bn_bwd_apply -- the mask only
+              // enters the sums, the stored gradient is the plain dgrad).  Rows outside the tensor are zeroed word by word.
+              float w2[16];
+              float bs[BNR ? 16 : 1], bh[BNR ? 16 : 1];
+              if (BNR) {
+                if (NREG == 1) {
+#pragma unroll
+                  for (int q = 0; q < 16; q++) { bs[BNR ? q : 0] = bsc_r[BNR && NREG == 1 ? q : 0]; bh[BNR ? q : 0] = bsh_r[BNR && NREG == 1 ? q : 0]; }
+                } else {
+                  const int cb = p.bn_mod ? cbase % p.bn_mod : cbase;
+                  const float4* scp = reinterpret_cast<const float4*>(p.bsc + cb);
+                  const float4* shp = reinterpret_cast<const float4*>(p.bsh + cb);
+#pragma unroll
+                  for (int q = 0; q < 4; q++) {
+                    const float4 s4 = __ldg(scp + q), h4 = __ldg(shp + q);
+                    bs[BNR ? 4 * q : 0] = s4.x; bs[BNR ? 4 * q + 1 : 0] = s4.y; bs[BNR ? 4 * q + 2 : 0] = s4.z; bs[BNR ? 4 * q + 3 : 0] = s4.w;
+                    bh[BNR ? 4 * q : 0] = h4.x; bh[BNR ? 4 * q + 1 : 0] = h4.y; bh[BNR ? 4 * q + 2 : 0] = h4.z; bh[BNR ? 4 * q + 3 : 0] = h4.w;
+                  }
+                }
+              }
 #pragma unroll
               for (int q = 0; q < 8; q++) {
-                v[2 * q] = (valid && (!BNR || ((mbits >> (2 * q)) & 1u))) ? __uint_as_float(packed[q] << 16) : 0.f;
-                v[2 * q + 1] = (valid && (!BNR || ((mbits >> (2 * q + 1)) & 1u))) ? __uint_as_float(packed[q] & 0xffff0000u) : 0.f;
+                const uint32_t pk = valid ? packed[q] : 0u;
+                float g0 = __uint_as_float(pk << 16), g1 = __uint_as_float(pk & 0xffff0000u);
+                if (BNR) {
+                  const uint4 a4 = addv[LD ? hh : 0][LD ? u : 0][q >> 2];
+                  const uint32_t yw = (q & 3) == 0 ? a4.x : (q & 3) == 1 ? a4.y : (q & 3) == 2 ? a4.z : a4.w;
+                  const float y0 = __uint_as_float(yw << 16), y1 = __uint_as_float(yw & 0xffff0000u);
+                  g0 = fmaf(y0, bs[BNR ? 2 * q : 0], bh[BNR ? 2 * q : 0]) > 0.f ? g0 : 0.f;
+                  g1 = fmaf(y1, bs[BNR ? 2 * q + 1 : 0], bh[BNR ? 2 * q + 1 : 0]) > 0.f ? g1 : 0.f;
+                  w2[2 * q] = g0 * y0; w2[2 * q + 1] = g1 * y1;
+                } else {
+                  w2[2 * q] = g0 * g0; w2[2 * q + 1] = g1 * g1;
+                }
+                v[2 * q] = g0; v[2 * q + 1] = g1;
               }
               if (NREG > 0) {
                 constexpr int CH = NREG > 0 ? NREG : 1;
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                   ssum[16 * ((hh * HB + u) % CH) + q] += v[q];
-                  ssq[16 * ((hh * HB + u) % CH) + q] = fmaf(v[q], BNR ? yv[BNR ? q : 0] : v[q], ssq[16 * ((hh * HB + u) % CH) + q]);
+                  if (BNR) ssq[16 * ((hh * HB + u) % CH) + q] += w2[q];
+                  else ssq[16 * ((hh * HB + u) % CH) + q] = fmaf(v[q], v[q], ssq[16 * ((hh * HB + u) % CH) + q]);
                 }
               } else {
-                float w2[16];
-#pragma unroll
-                for (int q = 0; q < 16; q++) w2[q] = v[q] * (BNR ? yv[BNR ? q : 0] : v[q]);
                 const float a = warp_transpose_sum16(v, lane);
                 const float b = warp_transpose_sum16(w2, lane);
                 if ((lane & 1) == 0) {
@@ -903,7 +940,18 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
   if (!ws_enabled()) return -1;
   const bool bnr = bsc != nullptr;
   if (bnr && (!transposed || addend == nullptr || bsh == nullptr || stat_partial == nullptr || fin != nullptr || d->Cin % 16 != 0)) return -1;
-  if (in_scale != nullptr && !in_relu) return -1;                       // NaN-fill halo needs the ReLU
+  if (bnr) {
+    // Measured on B200 (C2 shapes, same box), fused vs dgrad + bn_bwd_reduce: level 1 123 vs 70 + 48 us, level 2 83 vs 47 + 27,
+    // level 3 54 vs 31 + 16, level 4 41 vs 31 + 10; training step 9.12 ms with the fusion everywhere, 8.99 ms for maps of up to
+    // 40 000 positions only, 8.95 ms without it.  The epilogue is the critical path of this kernel and the fused variant adds a
+    // dependent global load (y) per 32-row block to it -- one or two kilobytes in flight per warp cannot cover the DRAM latency
+    // (an L2 prefetch one tile ahead recovers 18 of the 71 us at level 1), while the separate reduce kernel streams at 85 % of
+    // HBM peak and, in the step, hides behind the weight gradients of the side streams.  So the fused path is OFF unless
+    // FFPN_WS_BNR_MAXPOS (largest map, in positions, that takes it) says otherwise; the entry point then launches the two kernels.
+    const char* e = getenv("FFPN_WS_BNR_MAXPOS");                        // read per call: tests toggle it
+    const long long maxpos = e ? atoll(e) : 0;
+    if ((long long)d->B * d->S * d->W * d->H > maxpos) return -1;
+  }
   ffpn_conv_desc dp;
   int in_mult = 1;
   const bool strided111 = !transposed && ffpn_make_strided111_desc(d, &dp, &in_mult);   // strided 1x1x1 shortcut -> flat conv over a strided view

@@ -81,7 +81,7 @@ def _impl(name, call):
 
 @pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
 def test_conv_tc(case):
-    from ffpn import ops
+    from ffpn import lib, ops
     torch.backends.cudnn.allow_tf32 = False
     name, cin, cout, k, p, (B, S, W, H) = case[:6]
     s1 = case[6] if len(case) > 6 else (1, 1, 1)
@@ -153,9 +153,22 @@ def test_conv_tc(case):
         # dgrad fused with pass 1 of the backward of the BatchNorm + ReLU that produced the conv's input (ffpn_conv_dgrad_bnr): the
         # stored gradient is the plain dgrad, bit for bit; the sums are those of bn_bwd_reduce on it (ReLU mask applied)
         yprev = phys(torch.randn(B, cin, S, W, H, generator=g).cuda()).to(dt)
-        G, part, prow = ops.conv_dgrad_bnr(phys(dy), w, yprev, sc, sh, k, s1, p)
-        G1, part1, prow1 = ops.conv_dgrad_bnr(phys(dy), w, yprev, sc, sh, k, s1, p)
+        # (default: dgrad + bn_bwd_reduce as two launches; FFPN_WS_BNR_MAXPOS switches the one-kernel epilogue variant on,
+        # measured slower on B200 -- both must give the same numbers)
+        G0, part0, prow0 = ops.conv_dgrad_bnr(phys(dy), w, yprev, sc, sh, k, s1, p)
+        os.environ['FFPN_WS_BNR_MAXPOS'] = str(1 << 40)
+        try:
+            n0 = lib.launch_count()
+            G, part, prow = ops.conv_dgrad_bnr(phys(dy), w, yprev, sc, sh, k, s1, p)
+            fused = lib.launch_count() - n0 <= 2                    # (a per-call weight-packing launch + the conv kernel)
+            G1, part1, prow1 = ops.conv_dgrad_bnr(phys(dy), w, yprev, sc, sh, k, s1, p)
+        finally:
+            os.environ.pop('FFPN_WS_BNR_MAXPOS', None)
         torch.cuda.synchronize()
+        if s1 == (1, 1, 1) and cin % 16 == 0:
+            assert fused, 'the one-kernel dgrad + BatchNorm-backward-sums path declined a stride-1 geometry'
+        assert torch.equal(G0, dx)
+        s0 = part0.view(-1, 2, cin)[:prow0].double().sum(0)
         mask = torch.addcmul(sh, yprev.float(), sc) > 0
         assert torch.equal(G, dx)
         Gd, yd_ = torch.where(mask, dx.float(), torch.zeros((), device='cuda')).double().reshape(-1, cin), yprev.double().reshape(-1, cin)
@@ -163,6 +176,7 @@ def test_conv_tc(case):
         assert torch.allclose(st[0], Gd.sum(0), rtol=1e-3, atol=1e-3 * Gd.abs().sum(0).max().item()), ('dgrad_bnr sum G', (st[0] - Gd.sum(0)).abs().max())
         assert torch.allclose(st[1], (Gd * yd_).sum(0), rtol=1e-3, atol=1e-3 * (Gd * yd_).abs().sum(0).max().item())
         assert torch.equal(G, G1) and prow == prow1 and torch.equal(part[:prow * 2 * cin], part1[:prow * 2 * cin])
+        assert torch.allclose(s0, st, rtol=1e-4, atol=1e-4 * Gd.abs().sum(0).max().item())     # two launches == one launch
         # wgrad on tensor cores (fused BN+ReLU prologue on x), against torch autograd
         for affine in (False, True):
             xin = torch.relu(xq * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)) if affine else xq

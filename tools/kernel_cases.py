@@ -57,6 +57,17 @@ def build(torch, ops):
             elif kind == 'dgrad':
                 dy = torch.randn(yshape, device='cuda', generator=g).to(dt)
                 fn = lambda: ops.conv_dgrad(dy, w, tuple(x.shape), kernel, stride, pad)
+            elif kind == 'dgrad_add':
+                # dgrad with the residual-branch gradient added in the epilogue: reads dy and the addend, writes dx
+                dy = torch.randn(yshape, device='cuda', generator=g).to(dt)
+                add = torch.randn_like(x)
+                fn = lambda: ops.conv_dgrad(dy, w, tuple(x.shape), kernel, stride, pad, addend=add)
+                nbytes = (2 * x.numel() + npos_out * Cout) * 2
+            elif kind == 'dgrad_bnr':
+                # dgrad + BatchNorm-backward sums of the input's BN in the epilogue: reads dy and the BN's raw input, writes dx
+                dy = torch.randn(yshape, device='cuda', generator=g).to(dt)
+                fn = lambda: ops.conv_dgrad_bnr(dy, w, x, sc, sh, kernel, stride, pad)
+                nbytes = (2 * x.numel() + npos_out * Cout) * 2
             else:
                 dy = torch.randn(yshape, device='cuda', generator=g).to(dt)
                 dw = torch.zeros_like(w)
@@ -70,6 +81,8 @@ def build(torch, ops):
         conv_case(f'conv_fwd_l{lvl}', lvl, 'fwd', (1, 3, 3), (0, 1, 1), note=f'(1,3,3) {C}->{C}, BN+ReLU on load, statistics epilogue')
         conv_case(f'conv_dgrad_l{lvl}', lvl, 'dgrad', (1, 3, 3), (0, 1, 1), note=f'(1,3,3) {C}->{C}')
         conv_case(f'conv_wgrad_l{lvl}', lvl, 'wgrad', (1, 3, 3), (0, 1, 1), note=f'(1,3,3) {C}->{C}, + partial-tile reduce')
+        conv_case(f'conv_dgrad_add_l{lvl}', lvl, 'dgrad_add', (1, 3, 3), (0, 1, 1), note=f'(1,3,3) {C}->{C} dgrad + residual-branch gradient added in the epilogue')
+        conv_case(f'conv_dgrad_bnr_l{lvl}', lvl, 'dgrad_bnr', (1, 3, 3), (0, 1, 1), note=f'(1,3,3) {C}->{C} dgrad + ReLU mask + BatchNorm-backward sums of the input BN (replaces dgrad + bn_bwd_reduce)')
     conv_case('proj_conv_l1', 1, 'fwd', (1, 1, 3), (0, 0, 1), stride=(1, 1, 2), note='projection (1,1,3) s(1,1,2) 16->16 on the pair view')
     conv_case('proj_wgrad_l1', 1, 'wgrad', (1, 1, 3), (0, 0, 1), stride=(1, 1, 2), note='projection wgrad')
     conv_case('up4_fwd', 4, 'fwd', (3, 3, 1), (1, 1, 0), cin=768, cout=128, H=1, note='up_concat4 first conv (3,3,1) 768->128 @16x16 en-face')
@@ -137,7 +150,7 @@ def build(torch, ops):
     return cases
 
 
-DEFAULT_BENCH = ['conv_fwd_l1', 'proj_conv_l1', 'conv_wgrad_l1', 'conv_dgrad_l1', 'conv_fwd_l2', 'conv_fwd_l3', 'conv_fwd_l4',
+DEFAULT_BENCH = ['conv_fwd_l1', 'proj_conv_l1', 'conv_wgrad_l1', 'conv_dgrad_l1', 'conv_dgrad_add_l2', 'conv_fwd_l2', 'conv_fwd_l3', 'conv_fwd_l4',
                  'conv_fwd_l5', 'up4_fwd', 'conv_wgrad_l4', 'block_end_fwd_l1', 'block_end_bwd_l1', 'bn_bwd_reduce_l1',
                  'bn_bwd_apply_l1', 'proj_tail_fwd_l1', 'proj_tail_bwd_l1', 'resize2d_max_into_slot_l1', 'upsample_into_slot_l1']
 RIDGE_FLOP_PER_BYTE = 212.0                    # MEASURED_PEAKS: 1389 TFLOP/s sustained / 6.55 TB/s
