@@ -211,8 +211,10 @@ block_end_fwd_kernel(int64_t nvec, int C, const T* __restrict__ y, const float* 
 }
 
 // ---- block end backward (+ pool routing) ---------------------------------------------------------------
-template <typename T, int NCOL>
-__global__ void __launch_bounds__(EW_THREADS)
+// POOL = false (no pooled-branch gradient to route: most launches of a step) compiles the window scan out: 121 -> ~60 registers,
+// i.e. four instead of two resident CTAs per SM and twice the loads in flight.
+template <typename T, int NCOL, bool POOL>
+__global__ void __launch_bounds__(EW_THREADS, POOL ? 1 : 4)
 block_end_bwd_kernel(int B, int S, int W, int H, int C, int kS, int kW, int kH, const T* __restrict__ dz,
                      const T* __restrict__ dzp, const T* __restrict__ z, const T* __restrict__ y,
                      const T* __restrict__ yres, T* __restrict__ G, float* __restrict__ partial) {
@@ -239,7 +241,7 @@ block_end_bwd_kernel(int B, int S, int W, int H, int C, int kS, int kW, int kH, 
 #pragma unroll
         for (int j = 0; j < VEC; j++) g[j] = 0.f;
       }
-      if (dzp != nullptr) {
+      if (POOL && dzp != nullptr) {
         int64_t r = p;
         const int h = (int)(r % H); r /= H;
         const int w = (int)(r % W); r /= W;
@@ -568,9 +570,14 @@ extern "C" int ffpn_block_end_bwd(ffpn_ctx* ctx, int dtype, int64_t B, int64_t S
 #undef DISPATCH_BP
 #undef LAUNCH_BP
   }
-#define LAUNCH_BE(T, N) ffpn_launch(block_end_bwd_kernel<T, N>, g, EW_THREADS, 0, st, (int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const T*)dz, (const T*)dzp, (const T*)z, (const T*)y, (const T*)yres, (T*)G, partial)
-  if (dtype == FFPN_F32) { if (yres) LAUNCH_BE(float, 3); else LAUNCH_BE(float, 2); }
-  else { if (yres) LAUNCH_BE(bf16, 3); else LAUNCH_BE(bf16, 2); }
+#define LAUNCH_BE(T, N, PL) ffpn_launch(block_end_bwd_kernel<T, N, PL>, g, EW_THREADS, 0, st, (int)B, (int)S, (int)W, (int)H, C, kS, kW, kH, (const T*)dz, (const T*)dzp, (const T*)z, (const T*)y, (const T*)yres, (T*)G, partial)
+  if (dzp != nullptr) {
+    if (dtype == FFPN_F32) { if (yres) LAUNCH_BE(float, 3, true); else LAUNCH_BE(float, 2, true); }
+    else { if (yres) LAUNCH_BE(bf16, 3, true); else LAUNCH_BE(bf16, 2, true); }
+  } else {
+    if (dtype == FFPN_F32) { if (yres) LAUNCH_BE(float, 3, false); else LAUNCH_BE(float, 2, false); }
+    else { if (yres) LAUNCH_BE(bf16, 3, false); else LAUNCH_BE(bf16, 2, false); }
+  }
 #undef LAUNCH_BE
   *rows = g;
   FFPN_CHECK_LAUNCH(ctx, "block_end_bwd");
