@@ -143,6 +143,19 @@ def build(torch, ops):
         return (lambda: ops.resize2d_fwd(x, 32, 128, '2d_max', out=out, coff=16)), (x.numel() + x.numel() // 10) * 2, 1.0 * x.numel()
     simple('resize2d_max_into_slot_l1', 'resize2d_fwd_kernel', mk_resize, 'adaptive max 320x128 -> 32x128 into the concat slot')
 
+    def mk_stem_wgrad():
+        x = torch.randn(B, 32, 128, 128, 1, device='cuda', generator=g).to(dt)       # the OCT volume, one channel
+        dy = act(1)
+        dw = torch.zeros(16, 1, 1, 3, 3, device='cuda')
+        return (lambda: ops.conv_wgrad(x, dy, dw.shape, (1, 3, 3), (1, 1, 1), (0, 1, 1), out=dw)), (x.numel() + dy.numel()) * 2, 2.0 * dy.numel() * 9
+    simple('stem_wgrad_l1', 'stem_wgrad_kernel', mk_stem_wgrad, 'weight gradient of the first conv (Cin = 1, CUDA cores), level 1')
+
+    def mk_stem_fwd():
+        x = torch.randn(B, 32, 128, 128, 1, device='cuda', generator=g).to(dt)
+        w = torch.randn(16, 1, 1, 3, 3, device='cuda', generator=g) * 0.3
+        return (lambda: ops.conv_fwd(x, w, (1, 3, 3), (1, 1, 1), (0, 1, 1))), (x.numel() + 16 * x.numel()) * 2, 2.0 * 16 * x.numel() * 9
+    simple('stem_fwd_l1', 'stem_fwd_kernel', mk_stem_fwd, 'first conv (Cin = 1, CUDA cores) + statistics, level 1')
+
     def mk_maxpool():
         z = act(1)
         return (lambda: ops.maxpool_fwd(z, (1, 2, 2))), (z.numel() + z.numel() // 4) * 2, 1.0 * z.numel()
