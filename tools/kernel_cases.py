@@ -104,6 +104,12 @@ def build(torch, ops):
         return (lambda: ops.block_end_bwd(dz, dzp, z, y, None, (1, 2, 2))), (4 * z.numel() + dzp.numel()) * 2, 6.0 * z.numel()
     simple('block_end_bwd_l1', 'block_end_bwd', mk_block_end_bwd, 'ReLU bwd + pool routing + BN-bwd sums, level 1')
 
+    def mk_block_end_bwd_plain():
+        z, y, dz, yres = act(1), act(1), act(1), act(1)
+        return (lambda: ops.block_end_bwd(dz, None, z, y, yres, None)), 5 * z.numel() * 2, 8.0 * z.numel()
+    simple('block_end_bwd_plain_l1', 'block_end_bwd_kernel', mk_block_end_bwd_plain,
+           'ReLU bwd + BN-bwd sums of the block\'s last BN and of its shortcut BN, no pooled branch, level 1')
+
     def mk_bn_bwd_reduce():
         x, y = act(1), act(1)
         sc, sh = vec(16)
@@ -164,7 +170,7 @@ def build(torch, ops):
 
 
 DEFAULT_BENCH = ['conv_fwd_l1', 'proj_conv_l1', 'conv_wgrad_l1', 'conv_dgrad_l1', 'conv_dgrad_add_l2', 'conv_fwd_l2', 'conv_fwd_l3', 'conv_fwd_l4',
-                 'conv_fwd_l5', 'up4_fwd', 'conv_wgrad_l4', 'block_end_fwd_l1', 'block_end_bwd_l1', 'bn_bwd_reduce_l1',
+                 'conv_fwd_l5', 'up4_fwd', 'conv_wgrad_l4', 'block_end_fwd_l1', 'block_end_bwd_l1', 'block_end_bwd_plain_l1', 'bn_bwd_reduce_l1',
                  'bn_bwd_apply_l1', 'proj_tail_fwd_l1', 'proj_tail_bwd_l1', 'resize2d_max_into_slot_l1', 'upsample_into_slot_l1']
 RIDGE_FLOP_PER_BYTE = 212.0                    # MEASURED_PEAKS: 1389 TFLOP/s sustained / 6.55 TB/s
 
