@@ -135,6 +135,14 @@ int ffpn_bn_bwd_apply(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* dA
                       const float* scale, const float* shift, int relu, const float* cA,
                       const float* cP, const float* cQ, void* dy, void* stream);
 
+/* backward pass 3 of a block whose shortcut is conv + BN (fusion3D2D.py:717-727: out = relu(bn_k(conv_k(..)) + bn_s(conv_s(x)))):
+ *      both BatchNorms receive the same gradient G (ffpn_block_end_bwd's output, already ReLU-masked), so
+ *      dy1 = cA1*G + cP1*y1 + cQ1 and dy2 = cA2*G + cP2*y2 + cQ2 are produced by ONE pass that reads G once -- the same values
+ *      as two ffpn_bn_bwd_apply(relu = 0) calls. */
+int ffpn_bn_bwd_apply2(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* G, const void* y1, const void* y2,
+                       const float* cA1, const float* cP1, const float* cQ1, const float* cA2, const float* cP2,
+                       const float* cQ2, void* dy1, void* dy2, void* stream);
+
 /* ---- residual block end (replaces BN-apply + add_ + relu_, fusion3D2D.py:724-727) --------------------
  * z = relu(a*y + b + r),  r = ra*res + rb (raw shortcut conv output), res (identity shortcut, ra==NULL)
  * or 0 (res == NULL, non-residual block). */

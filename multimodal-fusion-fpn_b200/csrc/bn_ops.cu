@@ -183,6 +183,33 @@ bn_bwd_apply_kernel(int64_t nvec, int C, const T* __restrict__ dA, const T* __re
   }
 }
 
+// ---- backward pass 3 for a block with a conv + BN shortcut: the block's last BN and the shortcut's BN both receive the
+// same masked gradient G (block_end_bwd).  One pass reads G once and writes both conv gradients.
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS)
+bn_bwd_apply2_kernel(int64_t nvec, int C, const T* __restrict__ G, const T* __restrict__ y1, const T* __restrict__ y2,
+                     const float* __restrict__ cA1, const float* __restrict__ cP1, const float* __restrict__ cQ1,
+                     const float* __restrict__ cA2, const float* __restrict__ cP2, const float* __restrict__ cQ2,
+                     T* __restrict__ dy1, T* __restrict__ dy2) {
+  pdl_prologue();
+  constexpr int VEC = Elem<T>::VEC;
+  const int cvecs = C / VEC;
+  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * EW_THREADS) {
+    const int c0 = (int)(i % cvecs) * VEC;
+    float g[VEC], a[VEC], b[VEC], o1[VEC], o2[VEC];
+    Elem<T>::load(G + i * VEC, g);
+    Elem<T>::load(y1 + i * VEC, a);
+    Elem<T>::load(y2 + i * VEC, b);
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      o1[j] = fmaf(cA1[c0 + j], g[j], fmaf(cP1[c0 + j], a[j], cQ1[c0 + j]));
+      o2[j] = fmaf(cA2[c0 + j], g[j], fmaf(cP2[c0 + j], b[j], cQ2[c0 + j]));
+    }
+    Elem<T>::store(dy1 + i * VEC, o1);
+    Elem<T>::store(dy2 + i * VEC, o2);
+  }
+}
+
 // ---- block end forward ----------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
@@ -520,6 +547,24 @@ extern "C" int ffpn_bn_bwd_apply(ffpn_ctx* ctx, int dtype, int64_t P, int C, con
     ffpn_launch(bn_bwd_apply_kernel<bf16>, ew_grid(ctx, nvec), EW_THREADS, 0, st, nvec, C, (const bf16*)dA, (const bf16*)y, scale, shift, relu, cA, cP, cQ, (bf16*)dy);
   }
   FFPN_CHECK_LAUNCH(ctx, "bn_bwd_apply");
+  return 0;
+}
+
+extern "C" int ffpn_bn_bwd_apply2(ffpn_ctx* ctx, int dtype, int64_t P, int C, const void* G, const void* y1, const void* y2,
+                                  const float* cA1, const float* cP1, const float* cQ1, const float* cA2, const float* cP2,
+                                  const float* cQ2, void* dy1, void* dy2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!G || !y1 || !y2 || !dy1 || !dy2 || !cA1 || !cP1 || !cQ1 || !cA2 || !cP2 || !cQ2) FFPN_FAIL(ctx, "bn_bwd_apply2: null argument");
+  if (dtype == FFPN_F32) {
+    CHECK_C(ctx, C, 4, "bn_bwd_apply2");
+    const int64_t nvec = P * C / 4;
+    ffpn_launch(bn_bwd_apply2_kernel<float>, ew_grid(ctx, nvec), EW_THREADS, 0, st, nvec, C, (const float*)G, (const float*)y1, (const float*)y2, cA1, cP1, cQ1, cA2, cP2, cQ2, (float*)dy1, (float*)dy2);
+  } else {
+    CHECK_C(ctx, C, 8, "bn_bwd_apply2");
+    const int64_t nvec = P * C / 8;
+    ffpn_launch(bn_bwd_apply2_kernel<bf16>, ew_grid(ctx, nvec), EW_THREADS, 0, st, nvec, C, (const bf16*)G, (const bf16*)y1, (const bf16*)y2, cA1, cP1, cQ1, cA2, cP2, cQ2, (bf16*)dy1, (bf16*)dy2);
+  }
+  FFPN_CHECK_LAUNCH(ctx, "bn_bwd_apply2");
   return 0;
 }
 

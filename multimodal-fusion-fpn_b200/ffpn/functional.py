@@ -339,16 +339,18 @@ class ConvXFunction(torch.autograd.Function):
             G, partial, rows, ncols = ops.block_end_bwd(dz_p, dzp_p, z, y_last, yd, spec.pool)
             dg, db, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 1, count, g_last, affs[-1][2], affs[-1][3],
                                                      _sink(g_last), _sink(tensors[5 * (k - 1) + 2]))
-            dy = ops.bn_bwd_apply(G, y_last, affs[-1][0], affs[-1][1], False, cA, cP, cQ)
+            if not (spec.residual and yd is not None):
+                dy = ops.bn_bwd_apply(G, y_last, affs[-1][0], affs[-1][1], False, cA, cP, cQ)
         grads[5 * (k - 1) + 1], grads[5 * (k - 1) + 2] = dg, db
         # shortcut branch
         dx_short = None
         if spec.residual:
             if yd is not None:
                 wd, gd = tensors[5 * k], tensors[5 * k + 1]
-                dgd, dbd, cA, cP, cQ = ops.bn_bwd_finalize(partial, rows, ncols, 2, yd.numel() // yd.shape[-1] if spec.training else inf, gd,
-                                                           affd[2], affd[3], _sink(gd), _sink(tensors[5 * k + 2]))
-                dyd = ops.bn_bwd_apply(G, yd, affd[0], affd[1], False, cA, cP, cQ)
+                dgd, dbd, cAd, cPd, cQd = ops.bn_bwd_finalize(partial, rows, ncols, 2, yd.numel() // yd.shape[-1] if spec.training else inf, gd,
+                                                              affd[2], affd[3], _sink(gd), _sink(tensors[5 * k + 2]))
+                # the block's last BN and the shortcut's BN take the same G: one pass writes both conv gradients
+                dy, dyd = ops.bn_bwd_apply2(G, y_last, yd, (cA, cP, cQ), (cAd, cPd, cQd))
                 grads[5 * k] = _wgrad(xp, dyd, wd.shape, (1, 1, 1), spec.ds_stride, (0, 0, 0), None, None, False, _sink(wd))
                 grads[5 * k + 1], grads[5 * k + 2] = dgd, dbd
                 if spec.need_dx:

@@ -42,6 +42,7 @@ SIGNATURES = {
     'ffpn_bn_bwd_reduce': [_I, _L, _I, _P, _P, _P, _P, _I, _P, _IP, _P],
     'ffpn_bn_bwd_finalize': [_P, _I, _I, _I, _I, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'ffpn_bn_bwd_apply': [_I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
+    'ffpn_bn_bwd_apply2': [_I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'ffpn_block_end_fwd': [_I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     'ffpn_block_end_bwd': [_I, _L, _L, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _IP, _P],
     'ffpn_maxpool_fwd': [_I, _L, _L, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P],

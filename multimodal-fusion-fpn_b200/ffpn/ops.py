@@ -223,6 +223,17 @@ def bn_bwd_apply(dA, y, scale, shift, relu, cA, cP, cQ, out=None):
     return dy
 
 
+def bn_bwd_apply2(G, y1, y2, c1, c2):
+    """Both BatchNorm-backward applies of a block with a conv + BN shortcut in one pass over G: c1 / c2 = (cA, cP, cQ) of the
+    block's last BN / of the shortcut's BN -> (dy1, dy2), the same values as two bn_bwd_apply(relu=False) calls."""
+    C_ = y1.shape[-1]
+    assert y1.shape == y2.shape == G.shape
+    dy1, dy2 = torch.empty_like(y1), torch.empty_like(y2)
+    lib.call('ffpn_bn_bwd_apply2', _dev(G), lib.dtype_code(G.dtype), G.numel() // C_, C_, _ptr(G), _ptr(y1), _ptr(y2), _ptr(c1[0]), _ptr(c1[1]),
+             _ptr(c1[2]), _ptr(c2[0]), _ptr(c2[1]), _ptr(c2[2]), _ptr(dy1), _ptr(dy2), _stream(G))
+    return dy1, dy2
+
+
 def block_end_fwd(y, a, b, res=None, ra=None, rb=None):
     C_ = y.shape[-1]
     z = torch.empty_like(y)

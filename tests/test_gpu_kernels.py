@@ -128,6 +128,13 @@ def test_bn_finalize_and_backward(ops, dt):
     dy = ops.bn_bwd_apply(phys(dA), yp, a, b, True, cA, cP, cQ)
     assert rel(dg, bn.weight.grad) <= 10 * tol(dt) and rel(db, bn.bias.grad) <= 10 * tol(dt)
     assert rel(logical(dy.float()), yr.grad) <= 3 * tol(dt)
+    # a block with a conv + BN shortcut: both applies in one pass over G (ffpn_bn_bwd_apply2) == two separate applies, bit for bit
+    y2 = phys((torch.randn(B, C, S, W, H, generator=g) - 0.3).cuda().to(dt))
+    c2 = (cA * 0.7 + 0.1, cP * 1.3 - 0.05, cQ + 0.2)
+    one_a = ops.bn_bwd_apply(phys(dA), yp, a, b, False, cA, cP, cQ)
+    one_b = ops.bn_bwd_apply(phys(dA), y2, a, b, False, *c2)
+    two_a, two_b = ops.bn_bwd_apply2(phys(dA), yp, y2, (cA, cP, cQ), c2)
+    assert torch.equal(one_a, two_a) and torch.equal(one_b, two_b)
     # eval mode: running statistics
     bn.eval()
     a2, b2, _, _ = ops.bn_finalize(None, 0, flat.shape[0], bn.weight.detach(), bn.bias.detach(), bn.running_mean,
