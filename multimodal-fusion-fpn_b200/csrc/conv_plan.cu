@@ -20,12 +20,12 @@ namespace {
 // Pack fp32 master weights [Cout][Cin][taps] to the bf16 smem image [nchunk][kg][tap][kc][n (Npad)][8].
 // transposed: the operator applied is the dgrad conv: n <-> ci, k <-> co, taps flipped.
 // Kc = reduction channels of the packed operator, Nc = its output channels, Npad = channels per N-chunk
-__device__ __forceinline__ float pack_value(const float* __restrict__ w, int64_t i, int Cout, int Cin, int ntaps, int Kc, int Nc,
-                                            int Npad, int KG, int mode, int sH, int pH, int kH, int tmin) {
+// (r, e): r = index of the 8-element group (the innermost [8] of the image), e = element within it -- the eight elements of a
+// group share everything but e, so a caller that produces whole groups pays the index decomposition once
+__device__ __forceinline__ float pack_value_ge(const float* __restrict__ w, uint32_t r, const int e, int Cout, int Cin, int ntaps, int Kc,
+                                               int Nc, int Npad, int KG, int mode, int sH, int pH, int kH, int tmin) {
   const uint32_t nkc = (uint32_t)KG >> 3;
   const uint32_t nkg = (uint32_t)(Kc / KG);
-  uint32_t r = (uint32_t)i;                   // one image has < 2^31 elements: 32-bit index arithmetic
-  const int e = (int)(r & 7u); r >>= 3;
   int n = (int)(r % (uint32_t)Npad); r /= (uint32_t)Npad;
   const int kc = (int)(r % nkc); r /= nkc;
   const int tap = (int)(r % (uint32_t)ntaps); r /= (uint32_t)ntaps;
@@ -59,6 +59,12 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ w, int64_t
   return v;
 }
 
+__device__ __forceinline__ float pack_value(const float* __restrict__ w, int64_t i, int Cout, int Cin, int ntaps, int Kc, int Nc,
+                                            int Npad, int KG, int mode, int sH, int pH, int kH, int tmin) {
+  const uint32_t u = (uint32_t)i;             // one image has < 2^31 elements: 32-bit index arithmetic
+  return pack_value_ge(w, u >> 3, (int)(u & 7u), Cout, Cin, ntaps, Kc, Nc, Npad, KG, mode, sH, pH, kH, tmin);
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ntaps,
                                     int Kc, int Nc, int Npad, int KG, int nchunks, int mode, int sH, int pH, int kH,
                                     int tmin) {
@@ -68,10 +74,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     out[i] = __float2bfloat16_rn(pack_value(w, i, Cout, Cin, ntaps, Kc, Nc, Npad, KG, mode, sH, pH, kH, tmin));
 }
 
-// All images of the packed-weight arena in one launch: element -> job by binary search on the prefix sums.
+// All images of the packed-weight arena in one launch: a thread produces one 8-element group (16 bytes of the image: job totals,
+// prefixes and destinations are all multiples of 8 elements) -> job by binary search on the prefix sums, one index decomposition
+// and one 16-byte store per group instead of per element (this launch sits on the serial tail of the step, after the optimiser).
 __global__ void pack_all_kernel(const ffpn_pack_job* __restrict__ jobs, int njobs, long long total, bf16* __restrict__ arena) {
   pdl_prologue();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const long long ngroups = total >> 3;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += (long long)gridDim.x * blockDim.x) {
+    const long long i = gi << 3;
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -79,7 +89,16 @@ __global__ void pack_all_kernel(const ffpn_pack_job* __restrict__ jobs, int njob
     }
     const ffpn_pack_job& j = jobs[lo];
     const long long li = i - j.prefix;
-    arena[j.dst + li] = __float2bfloat16_rn(pack_value(j.w, li, j.Cout, j.Cin, j.ntaps, j.Kc, j.Nc, j.Npad, j.KG, j.mode, j.sH, j.pH, j.kH, j.tmin));
+    const uint32_t r = (uint32_t)(li >> 3);
+    uint32_t pk[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float v0 = pack_value_ge(j.w, r, 2 * q, j.Cout, j.Cin, j.ntaps, j.Kc, j.Nc, j.Npad, j.KG, j.mode, j.sH, j.pH, j.kH, j.tmin);
+      const float v1 = pack_value_ge(j.w, r, 2 * q + 1, j.Cout, j.Cin, j.ntaps, j.Kc, j.Nc, j.Npad, j.KG, j.mode, j.sH, j.pH, j.kH, j.tmin);
+      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      pk[q] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(arena + j.dst + li) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -280,7 +299,9 @@ extern "C" int ffpn_weight_arena_pack(ffpn_ctx* ctx, void* stream) {
   if (!ctx) return 1;
   if (ctx->arena_state != 2) return 0;
   const long long total = ctx->arena_elems;
-  const int g = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (total & 7) FFPN_FAIL(ctx, "weight_arena_pack: an image is not a whole number of 8-element groups");
+  const long long ngroups = total >> 3;
+  const int g = (int)((ngroups + 255) / 256 < 148 * 16 ? (ngroups + 255) / 256 : 148 * 16);
   ffpn_launch(pack_all_kernel, g, 256, 0, (cudaStream_t)stream, ctx->d_jobs, ctx->njobs, total, (bf16*)ctx->arena);
   FFPN_CHECK_LAUNCH(ctx, "weight_arena_pack");
   return 0;
