@@ -28,6 +28,42 @@ def test_library_exports_every_declared_symbol():
     assert handle.ffpn_conv_workspace_bytes(d) >= 0          # pure host call, no GPU needed
 
 
+def test_binding_matches_the_header_argument_for_argument():
+    """ffpn/lib.py declares the ctypes signature of every entry point by hand: the number of arguments and their kinds
+    (pointer / 32-bit / 64-bit / float / double / size_t) must be those of the prototype in include/ffpn.h -- a binding that is one
+    argument off would still load and then hand the kernels garbage."""
+    import ctypes as C
+    from ffpn import lib
+    header = re.sub(r'/\*.*?\*/', ' ', open(os.path.join(REPO, 'include', 'ffpn.h')).read(), flags=re.S)
+    protos = dict(re.findall(r'\b(ffpn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', header))
+
+    def kind(decl):
+        decl = decl.strip()
+        if '*' in decl:
+            return 'ptr'
+        t = decl.rsplit(None, 1)[0] if ' ' in decl else decl
+        return {'int': 'i32', 'int32_t': 'i32', 'int64_t': 'i64', 'float': 'f32', 'double': 'f64', 'size_t': 'size'}[t.replace('const ', '').strip()]
+
+    def ckind(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, 'contents') or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return 'ptr'
+        return {C.c_int: 'i32', C.c_int64: 'i64', C.c_float: 'f32', C.c_double: 'f64', C.c_size_t: 'size'}[t]
+
+    checked = 0
+    for name, args in list(lib.SIGNATURES.items()) + [(n, a) for n, (a, _) in lib.NO_CTX.items()]:
+        params = [q for q in protos[name].split(',') if q.strip() and q.strip() != 'void']
+        if name in lib.SIGNATURES:
+            assert 'ffpn_ctx' in params[0], name
+            params = params[1:]
+        want = [kind(q) for q in params]
+        got = [ckind(t) for t in args]
+        # size_t and int64 have the same width on this ABI; everything else must agree exactly
+        norm = lambda ks: ['i64' if k == 'size' else k for k in ks]
+        assert norm(want) == norm(got), (name, want, got)
+        checked += 1
+    assert checked == len(lib.EXPORTS)
+
+
 def test_sass_has_no_foreign_arch():
     import subprocess
     from ffpn import lib
