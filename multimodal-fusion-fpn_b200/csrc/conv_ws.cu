@@ -48,6 +48,7 @@ struct WsParams {
   const bf16* addend;                 // MODE 1: tensor added to the output; MODE 2: raw output y of the BatchNorm whose backward sums are taken
   const float* bsc;                   // MODE 2: scale / shift of that BatchNorm (the ReLU mask is scale * y + shift > 0)
   const float* bsh;
+  unsigned zero;                      // always 0, but only the host knows: ties the issue of an epilogue load to the arrival of the previous one (see consume)
   int bn_mod;                         // MODE 2 on the pair view of dx: the BatchNorm vectors are indexed modulo the real channel count (0 = off)
   int fold;                           // statistics columns c and c + fold are the same channel (pair views): folded when the CTA writes its row (0 = off)
   bf16* y;
@@ -374,8 +375,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       long long oposv[2][HB];
       bool validv[2][HB];
       uint4 addv[LD ? 2 : 1][LD ? HB : 1][2];
+      float fa[LD ? HB : 1][LD ? 16 : 1];                 // the current half-batch's addend / y, unpacked (see consume)
       // output position of every item of a half-batch (+ its addend / y loads, issued long before they are used)
-      auto prep = [&](const int hh, const int it0) {
+      auto prep = [&](const int hh, const int it0, const uint32_t dep) {
 #pragma unroll
         for (int u = 0; u < HB; u++) {
           const int idx = it0 + u;
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
             oposv[hh][u] = tbase + (long long)e.x;
             if (LD && validv[hh][u]) {
               const int cbase = n0 + ch * 16;
-              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + oposv[hh][u] * p.Cout + cbase);
+              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + oposv[hh][u] * p.Cout + cbase + dep);
               if (cbase + 16 <= p.Cout) {
                 uint32_t t8[8];
                 ld_global_v8(ap, t8);
@@ -412,6 +414,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           }
         }
       };
+      // All addend / y loads of this warp share one hardware scoreboard, and waiting on a scoreboard waits for EVERY load
+      // outstanding on it: if the registers of half-batch k were first read inside process(k), i.e. after the loads of k + 1
+      // have been issued, each half-batch would wait for the loads it has only just issued and nothing would overlap (measured:
+      // the addend dgrad at level 1 took 130 us against 70 us without addend, and MORE loads in flight made it slower).  So the
+      // loaded words are read BEFORE the next loads go out, one whole process() after they were issued themselves.  Neither the
+      // compiler nor ptxas would keep that order on their own (the reads sink to their use, the loads float up), so the address
+      // of the next loads is made to depend on the words just read: they are folded, ANDed with a kernel parameter that is
+      // always zero but unknown at compile time, and added to the address.
+      auto consume = [&](const int hh) -> uint32_t {
+        uint32_t fold = 0u;
+#pragma unroll
+        for (int u = 0; u < HB; u++) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; h2++) {
+            const uint4 a4 = addv[LD ? hh : 0][LD ? u : 0][h2];
+            const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              // the UNPACKED words feed the dependency and are then made opaque to the compiler: nothing after this point can be
+              // derived from the load's destination registers again (a later read of those would wait on the scoreboard anew)
+              uint32_t lo = w4[q] << 16, hi = w4[q] & 0xffff0000u;
+              asm volatile("" : "+r"(lo), "+r"(hi));
+              fold ^= lo ^ hi;
+              fa[LD ? u : 0][LD ? h2 * 8 + 2 * q : 0] = __uint_as_float(lo);
+              fa[LD ? u : 0][LD ? h2 * 8 + 2 * q + 1 : 0] = __uint_as_float(hi);
+            }
+          }
+        }
+        return fold & p.zero;                                         // 0 -- but a true data dependency of the next loads' addresses
+      };
       auto process = [&](const int hh, const int it0) {
 #pragma unroll
         for (int u = 0; u < HB; u++) {
@@ -424,19 +456,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
 #pragma unroll
             for (int q = 0; q < 16; q++) v[q] = __uint_as_float(raw[hh][u][q]);
             const int cbase = n0 + ch * 16;
-            if (ADD && valid) {
+            if (ADD && valid) {                                      // (words that were not loaded are zero: prep)
 #pragma unroll
-              for (int h2 = 0; h2 < 2; h2++) {
-                if (cbase + h2 * 8 < p.Cout) {
-                  const uint4 a4 = addv[LD ? hh : 0][LD ? u : 0][h2];
-                  const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-                  for (int q = 0; q < 4; q++) {
-                    v[h2 * 8 + 2 * q] += __uint_as_float(w4[q] << 16);
-                    v[h2 * 8 + 2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
-                  }
-                }
-              }
+              for (int q = 0; q < 16; q++) v[q] += fa[LD ? u : 0][LD ? q : 0];
             }
             uint32_t packed[8];
 #pragma unroll
@@ -476,9 +498,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                 const uint32_t pk = valid ? packed[q] : 0u;
                 float g0 = __uint_as_float(pk << 16), g1 = __uint_as_float(pk & 0xffff0000u);
                 if (BNR) {
-                  const uint4 a4 = addv[LD ? hh : 0][LD ? u : 0][q >> 2];
-                  const uint32_t yw = (q & 3) == 0 ? a4.x : (q & 3) == 1 ? a4.y : (q & 3) == 2 ? a4.z : a4.w;
-                  const float y0 = __uint_as_float(yw << 16), y1 = __uint_as_float(yw & 0xffff0000u);
+                  const float y0 = fa[LD ? u : 0][LD ? 2 * q : 0], y1 = fa[LD ? u : 0][LD ? 2 * q + 1 : 0];
                   g0 = fmaf(y0, bs[BNR ? 2 * q : 0], bh[BNR ? 2 * q : 0]) > 0.f ? g0 : 0.f;
                   g1 = fmaf(y1, bs[BNR ? 2 * q + 1 : 0], bh[BNR ? 2 * q + 1 : 0]) > 0.f ? g1 : 0.f;
                   w2[2 * q] = g0 * y0; w2[2 * q + 1] = g1 * y1;
@@ -510,7 +530,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       };
       // the first half-batch's positions and addend / y loads go out BEFORE the wait for the accumulators: their DRAM latency hides
       // behind the MMAs
-      prep(0, 0);
+      prep(0, 0, 0u);
       mbar_wait(TFULL(buf), (uint32_t)(tl / p.nbuf) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (warp == 4 && lane == 0) WS_TRACE(8, tl);
@@ -521,7 +541,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           const int cur = it0 + hh * HB;
           if (cur < nitems) {                                         // warp-uniform
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");   // half-batch hh has landed (nothing else is outstanding)
-            if (cur + HB < nitems) { prep(hh ^ 1, cur + HB); issue(hh ^ 1, cur + HB); }
+            uint32_t dep = 0u;
+            if (LD) dep = consume(hh);
+            if (cur + HB < nitems) { prep(hh ^ 1, cur + HB, dep); issue(hh ^ 1, cur + HB); }
             process(hh, cur);
           }
         }
@@ -986,7 +1008,7 @@ static int conv_ws_launch(ffpn_ctx* ctx, const ffpn_conv_desc* d, bool transpose
     if (packed_now) FFPN_CHECK_LAUNCH(ctx, "pack_weights");
   }
   p.sc = in_scale; p.sh = in_shift; p.wp = (const bf16*)wimg; p.addend = (const bf16*)addend; p.y = (bf16*)y; p.stat = stat_partial;
-  p.bsc = bsc; p.bsh = bsh;
+  p.bsc = bsc; p.bsh = bsh; p.zero = 0u;
   p.bn_mod = (bnr && pair) ? d->Cin : 0;
   p.fold = pair2 ? (transposed ? d->Cin : d->Cout) : (bnr && pair) ? d->Cin : 0;
   p.dbg = ffpn_debug_env("FFPN_TC_DEBUG");
