@@ -288,6 +288,38 @@ def test_branch_stream_toggle(monkeypatch):
     assert FF.streams_enabled() and FF.streams_enabled('wgrad')
 
 
+def test_eval_batchnorm_coefficient_cache_validity(monkeypatch):
+    """Host logic of ops.eval_bn_coefficients (no GPU: the finalize call is stubbed): an entry is reused only for the same
+    tensor OBJECTS with unchanged version counters within the same training epoch -- in-place updates through torch, a
+    training-mode finalize or a graph replay (ops.note_bn_statistics_update) and a different module with equal values all miss."""
+    from ffpn import ops
+    calls = []
+
+    def fake_finalize(partial, rows, count, gamma, beta, rm, rv, momentum, eps, training):
+        calls.append(1)
+        return tuple(torch.full((gamma.numel(),), float(len(calls))) for _ in range(4))
+
+    monkeypatch.setattr(ops, 'bn_finalize', fake_finalize)
+    monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)      # (raises without a GPU)
+    g, b, rm, rv = torch.ones(4), torch.zeros(4), torch.zeros(4), torch.ones(4)
+    first = ops.eval_bn_coefficients(g, b, rm, rv, 1e-5)
+    assert ops.eval_bn_coefficients(g, b, rm, rv, 1e-5)[0] is first[0] and len(calls) == 1      # hit
+    rm.add_(1.0)                                                                                  # torch in-place update: version bump
+    assert ops.eval_bn_coefficients(g, b, rm, rv, 1e-5)[0] is not first[0] and len(calls) == 2
+    ops.eval_bn_coefficients(g, b, rm, rv, 1e-5)
+    assert len(calls) == 2
+    ops.note_bn_statistics_update()                                                               # raw-pointer update (kernels, graph replay)
+    ops.eval_bn_coefficients(g, b, rm, rv, 1e-5)
+    assert len(calls) == 3
+    ops.eval_bn_coefficients(g, b, rm, rv, 1e-3)                                                  # another eps
+    assert len(calls) == 4
+    g2, b2, rm2, rv2 = g.clone(), b.clone(), rm.clone(), rv.clone()                               # another module, equal values
+    ops.eval_bn_coefficients(g2, b2, rm2, rv2, 1e-3)
+    assert len(calls) == 5
+    ops.eval_bn_coefficients(g2, b, rm, rv, 1e-3)                                                 # sibling tensor swapped
+    assert len(calls) == 6
+
+
 def test_checkpoint_roundtrip_reference_layout(mirror, tmp_path):
     """ffpn.checkpoint: pytorch-lightning 1.5.10 `save_weights_only` layout (wrapper keys, `model.` prefix), the loading
     rules of train.py:146-153 (with / without 'state_dict') and the legacy key fix of validate_ensemble.py:251-256."""
